@@ -1,0 +1,150 @@
+/* libpertgnn -- C-ABI of the B200 (sm_100a) hot path of PERT-GNN.
+ *
+ * The reference (handasontam/PERT-GNN-KDD23) is pure Python on top of torch_geometric 2.4.0 and has no
+ * FFI of its own; the "interface each entry point replaces" is therefore the Python/PyG call the
+ * reference makes at the cited file:line.  INTEGRATION.md shows the ctypes binding (the one this
+ * repository ships in pert_gnn_kdd23_b200/_lib.py) a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - every buffer is a CALLER-OWNED DEVICE pointer (the library never allocates or frees);
+ *     fp32 row-major, `ld*` = row stride in floats; indices int32 inside the library, int64 where the
+ *     reference's tensors are int64 (edge_index, edge_attr, batch, ids);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, nothing synchronises;
+ *   - return value: 0 = ok; > 0 = cudaError_t of a failed launch/memset; < 0 = library code
+ *     (PERT_ERR_*).  Never throws, never exits.  Out-of-range indices found ON THE DEVICE are
+ *     reported by writing PERT_ERR_RANGE into the optional device word `status`;
+ *   - no global mutable state: re-entrant, thread-safe per stream;
+ *   - rows of float matrices must be 16-byte aligned (ld % 4 == 0, base pointer 16-byte aligned)
+ *     unless stated otherwise.
+ */
+#ifndef PERTGNN_H_
+#define PERTGNN_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PERT_OK 0
+#define PERT_ERR_BADARG (-1)
+#define PERT_ERR_UNSUPPORTED (-2)
+#define PERT_ERR_RANGE (-3)
+
+/* ABI version (major*1000 + minor). */
+int pert_version(void);
+
+/* ---- index construction (integer, bit-exact) ---------------------------------------------------
+ * Replaces the COO handling PyG MessagePassing does implicitly for TransformerConv.propagate
+ * (reference model.py:100,104) and the edge_index offsetting/collation of pert_gnn.py:107-119,
+ * 201-209: builds, once per batch, a STABLE CSR by target and CSC by source.
+ *   edge_index int64 [2,E] (row 0 source, row 1 target);  edge_attr int64 [E,attr_cols] or NULL
+ *   (columns 0,1 = interface id, rpctype id -- reference model.py:93-94), ids checked < n_if/n_rpc.
+ * out (int32): rowptr[N+1], perm[E] (original edge id at CSR slot), csr_src[E], csr_if[E], csr_rpc[E],
+ *              colptr[N+1], csc_pos[E] (CSR slot of the edge at CSC slot), csc_dst[E].
+ * Definition of the layout: oracle/index_oracle.py:build_index. */
+long long pert_index_workspace_bytes(long long N, long long E);
+int pert_build_index(const int64_t* edge_index, const int64_t* edge_attr, int attr_cols, long long N, long long E,
+                     int n_if, int n_rpc, int* rowptr, int* perm, int* csr_src, int* csr_if, int* csr_rpc,
+                     int* colptr, int* csc_pos, int* csc_dst, void* workspace, long long workspace_bytes,
+                     int* status, void* stream);
+
+/* ptr[B+1] int32 from the PyG `batch` vector (Batch.ptr; pert_gnn.py:201-209 collation).
+ * workspace >= 64 KiB is always enough for B < 2^22. */
+int pert_graph_ptr(const int64_t* batch, long long N, long long B, int* ptr, void* workspace,
+                   long long workspace_bytes, int* status, void* stream);
+
+/* Level index: min hop depth from roots[g] over out-edges inside graph g, -1 if unreachable.
+ * Replaces misc.py:52-63 (DFS.dfs_min_node_depth) + :107-136.  gptr[B+1], colptr/csc_dst from
+ * pert_build_index, roots[B] global node ids, depth[N] int32 out. */
+int pert_min_depth(const int* gptr, long long B, const int* colptr, const int* csc_dst, const int* roots,
+                   int* depth, void* stream);
+
+/* ---- segmented reduce (the scatter-max / scatter-add metric kernel) -----------------------------
+ * out[i,:] = reduce over CSR segment i of msg rows; op 0 = sum, 1 = max; empty segment -> 0.
+ * Replaces torch_geometric.utils.scatter(reduce='max'|'sum') as used by utils.softmax and
+ * aggr='add' (call sites model.py:100,104) and global_add_pool (model.py:107).
+ * perm NULL: msg rows already in CSR order; else row of slot p is perm[p]. */
+int pert_segment_reduce_fwd(const float* msg, const int* rowptr, const int* perm, float* out, long long N, int H,
+                            int op, void* stream);
+int pert_segment_reduce_bwd(const float* dout, const float* msg, const float* out, const int* rowptr,
+                            const int* perm, float* dmsg, long long N, int H, int op, void* stream);
+
+/* ---- fused TransformerConv message passing -------------------------------------------------------
+ * Replaces torch_geometric.nn.TransformerConv.propagate/message/aggregate (heads=1, edge_dim set,
+ * root_weight) -- reference model.py:26-51 (construction), :100,:104 (calls).  q,k,v,s: [N,H] planes with
+ * row stride ld (s = lin_skip(x), may be NULL); t_if [n_if,H], t_rpc [n_rpc,H] = embedding tables already
+ * multiplied by the two halves of lin_edge.weight (NULL,NULL = no edge features).  out [N,H];
+ * alpha [E] (CSR order) is saved for backward.  H in {4,8,16,32,64,96,128,192,256}. */
+int pert_tconv_supported_width(int H);
+int pert_tconv_fwd(const float* q, const float* k, const float* v, const float* s, int ld, const int* rowptr,
+                   const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if, const float* t_rpc,
+                   float* out, int ld_out, float* alpha, long long N, int H, void* stream);
+/* g = dL/dout [N,H] (stride ld_g).  Writes dq,dk,dv [N,H] (stride ld_d), dsp [E] scratch; ACCUMULATES
+ * (+=, atomics) into dt_if [n_if,H] and dt_rpc [n_rpc,H] (caller zeroes them once per step). */
+int pert_tconv_bwd(const float* g, int ld_g, const float* q, const float* k, const float* v, int ld,
+                   const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr,
+                   const int* csc_pos, const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha,
+                   float* dq, float* dk, float* dv, int ld_d, float* dsp, float* dt_if, float* dt_rpc, int n_rpc,
+                   long long N, int H, void* stream);
+
+/* ---- dense linears (exact fp32) --------------------------------------------------------------------
+ * Replace torch_geometric.nn.Linear / the lin_* of TransformerConv (model.py:26-55,105,110-112).
+ * "Blocked" matrices: element (r,c) at base + (c / cb)*cbs + r*ld + (c % cb); cb <= 0 means a plain matrix.
+ *   NT: C[M,Nc] (=|+=) A[M,K] . B[Nc,K]^T (+ bias) (relu)
+ *   TN: C[Mc,Nc] += A[R,Mc]^T . B[R,Nc]      (atomic accumulation; weight gradients)
+ *   colsum: out[c] += sum_r A[r,c]            (bias gradients) */
+int pert_gemm_nt(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, const float* bias,
+                 float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K, int relu, int accumulate,
+                 void* stream);
+int pert_gemm_tn(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, int b_cb,
+                 long long b_cbs, float* C, int ldc, long long R, int Mc, int Nc, void* stream);
+int pert_colsum(const float* A, int lda, int a_cb, long long a_cbs, float* out, long long R, int Cc, void* stream);
+
+/* ---- embeddings / concat (model.py:87-97,108) -------------------------------------------------------
+ * fwd: out[n,0:H] (=|+=) table[ids[n*id_stride]];  bwd: dtable[ids[n*id_stride]] += dy[n,0:H]. */
+int pert_embedding_fwd(const float* table, int n_rows, const int64_t* ids, int id_stride, float* out, int ld_out,
+                       long long N, int H, int accumulate, int* status, void* stream);
+int pert_embedding_bwd(const float* dy, int ld_dy, const int64_t* ids, int id_stride, float* dtable, int n_rows,
+                       long long N, int H, void* stream);
+/* out[n, col0:col0+F] = x[n,0:F] (x dense [N,F], any F), out[n, col0+F:ld_out] = 0. */
+int pert_copy_cols(const float* x, int F, float* out, int ld_out, int col0, long long N, void* stream);
+
+/* ---- BatchNorm1d (+ fused ReLU) (model.py:33,43,101-102) ---------------------------------------------
+ * training: batch statistics (biased var), running stats updated with `momentum` (unbiased var),
+ * num_batches_tracked += 1; eval: running statistics.  mean/rstd [H] are outputs saved for backward. */
+long long pert_bn_workspace_bytes(long long N, int H);
+int pert_bn_fwd(const float* x, int ld_x, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, long long* num_batches_tracked, float eps, float momentum, int training,
+                int relu, float* mean, float* rstd, float* y, int ld_y, long long N, int H, void* workspace,
+                long long workspace_bytes, void* stream);
+/* dy = grad wrt the (post-ReLU) output y; sums = [2H] scratch; dgamma/dbeta (+=) may be NULL. */
+int pert_bn_bwd(const float* dy, int ld_dy, const float* y, int ld_y, const float* x, int ld_x, const float* mean,
+                const float* rstd, const float* gamma, int relu, int training, float* dx, int ld_dx, float* dgamma,
+                float* dbeta, float* sums, long long N, int H, void* stream);
+
+/* ---- local head + probability-weighted add-pool (model.py:105-107) -----------------------------------
+ * local[n] = <x_n, w_local> + b_local (skipped when local NULL);
+ * pool[batch[n], :] += (x_n * probs[n]) / pnn[n]   (pool [B,H] is zeroed by the call). */
+int pert_pool_fwd(const float* x, int ld, const float* probs, const float* pnn, const int64_t* batch,
+                  const float* w_local, const float* b_local, float* local, float* pool, long long N, long long B,
+                  int H, int* status, void* stream);
+int pert_pool_bwd(const float* dpool, const float* dlocal, const float* x, int ld, const float* probs,
+                  const float* pnn, const int64_t* batch, const float* w_local, float* dx, int ld_dx,
+                  float* dw_local, float* db_local, long long N, long long B, int H, void* stream);
+
+/* dy[i] = 0 where y[i] <= 0 (F.relu backward, model.py:111). */
+int pert_relu_bwd(const float* y, float* dy, long long n, void* stream);
+
+/* Pinball loss (pert_gnn.py:191-193): loss[0] = mean(max(tau*e,(tau-1)*e)), e = y - yhat;
+ * dyhat[B] = grad_scale * dloss/dyhat (either output may be NULL). */
+int pert_pinball_loss(const int64_t* y, const float* yhat, float tau, long long B, float grad_scale, float* loss,
+                      float* dyhat, void* stream);
+
+/* torch.optim.Adam step (pert_gnn.py:343,247) over one flat parameter buffer; g is scaled by grad_scale. */
+int pert_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, long long step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERTGNN_H_ */

@@ -1,0 +1,356 @@
+// Fused TransformerConv(heads=1, edge_dim, root_weight) message passing over CSR rows.
+//
+// Replaces, per layer, PyG 2.4.0's __collect__ gathers, lin_edge, logits, utils.softmax
+// (scatter-max + scatter-add), message and aggr='add' scatter (reference call sites
+// model.py:100,104; ~30 ATen launches and ~22 passes over [E,H] temporaries, SURVEY.md 2.2
+// K2..K10) with ONE launch forward and TWO launches backward, no [E,H] temporary at all.
+//
+// Semantics, for target node i with incoming edges t (source j, ids a,b):
+//   e_t = T_if[a] + T_rpc[b]                (== lin_edge(cat(if_emb[a], rpc_emb[b])): lin_edge has no bias,
+//                                             so it distributes over the concat; tables are [n,H] GEMM outputs)
+//   s_t = <q_i, k_j + e_t> / sqrt(H);  m_i = max_t s_t;  p_t = exp(s_t - m_i)
+//   Z_i = sum_t p_t + 1e-16;  alpha_t = p_t / Z_i;  out_i = sum_t alpha_t (v_j + e_t) + r_i
+// Backward (g = dL/dout):
+//   dalpha_t = <g_i, v_j + e_t>;  ds_t = alpha_t (dalpha_t - sum_t' alpha_t' dalpha_t')
+//   dq_i = sum_t ds_t (k_j + e_t)/sqrt(H)            (target-CSR pass)
+//   dk_j = sum_t ds_t q_i/sqrt(H);  dv_j = sum_t alpha_t g_i;  de_t = alpha_t g_i + ds_t q_i/sqrt(H)
+//                                                      (source-CSC pass; de_t reduced into dT_if / dT_rpc)
+//
+// Mapping: a group of LPR lanes owns one node row (H = 4*LPR*VPL floats, one or more float4 per
+// lane, 16-byte coalesced row reads); 32/LPR nodes per warp; dot products reduce with sub-warp
+// butterfly shuffles.  HBM-bound: algorithmic bytes forward = 16*N*H + 12*E + 4*(N+1).
+#include "common.cuh"
+#include <type_traits>
+
+namespace {
+
+template <int VPL>
+struct Row {
+  float4 v[VPL];
+};
+
+template <int LPR, int VPL>
+__device__ __forceinline__ Row<VPL> load_row(const float* __restrict__ base, int ld, int row, int lig) {
+  Row<VPL> r;
+  const float* p = base + (size_t)row * ld + lig * 4;
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) r.v[u] = ldg4(p + u * LPR * 4);
+  return r;
+}
+template <int LPR, int VPL>
+__device__ __forceinline__ void store_row(float* __restrict__ base, int ld, int row, int lig, const Row<VPL>& r) {
+  float* p = base + (size_t)row * ld + lig * 4;
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) st4(p + u * LPR * 4, r.v[u]);
+}
+template <int VPL>
+__device__ __forceinline__ Row<VPL> row_add(const Row<VPL>& a, const Row<VPL>& b) {
+  Row<VPL> r;
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) r.v[u] = f4add(a.v[u], b.v[u]);
+  return r;
+}
+template <int VPL>
+__device__ __forceinline__ float row_dot(const Row<VPL>& a, const Row<VPL>& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) s += f4dot(a.v[u], b.v[u]);
+  return s;
+}
+template <int VPL>
+__device__ __forceinline__ void row_fma(float s, const Row<VPL>& a, Row<VPL>& acc) {
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) acc.v[u] = f4fma(s, a.v[u], acc.v[u]);
+}
+template <int VPL>
+__device__ __forceinline__ Row<VPL> row_zero() {
+  Row<VPL> r;
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) r.v[u] = f4zero();
+  return r;
+}
+
+struct TconvArgs {
+  const float *q, *k, *v, *s;  // node planes, row stride ld
+  int ld;
+  const int *rowptr, *csr_src, *csr_if, *csr_rpc;
+  const float *t_if, *t_rpc;  // [n_if,H], [n_rpc,H] (may be null => no edge term)
+  float* out;
+  int ld_out;
+  float* alpha;  // [E] CSR order
+  int N;
+  float inv_sqrt_c;
+};
+
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) k_tconv_fwd(TconvArgs a) {
+  constexpr int H = 4 * LPR * VPL;
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % LPR;
+  const int grp = lane / LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int i = warp * GPW + grp;
+  if (i >= a.N) return;
+  const bool has_e = a.t_if != nullptr;
+  const int p0 = __ldg(a.rowptr + i), p1 = __ldg(a.rowptr + i + 1);
+  const Row<VPL> q = load_row<LPR, VPL>(a.q, a.ld, i, lig);
+  // pass 1: logits -> alpha[] (raw), running max
+  float m = -INFINITY;
+  for (int p = p0; p < p1; ++p) {
+    const int j = __ldg(a.csr_src + p);
+    Row<VPL> kj = load_row<LPR, VPL>(a.k, a.ld, j, lig);
+    if (has_e) {
+      kj = row_add(kj, load_row<LPR, VPL>(a.t_if, H, __ldg(a.csr_if + p), lig));
+      kj = row_add(kj, load_row<LPR, VPL>(a.t_rpc, H, __ldg(a.csr_rpc + p), lig));
+    }
+    const float s = group_sum<LPR>(row_dot(q, kj), gmask) * a.inv_sqrt_c;
+    m = fmaxf(m, s);
+    if (lig == 0) a.alpha[p] = s;
+  }
+  __syncwarp(gmask);
+  // pass 2: denominator (PyG: sum of exp(s - max) + 1e-16)
+  float Z = 0.f;
+  for (int p = p0; p < p1; ++p) Z += expf(a.alpha[p] - m);
+  Z += 1e-16f;
+  __syncwarp(gmask);
+  // pass 3: alpha and the weighted sum of (v_j + e_t)
+  Row<VPL> acc = row_zero<VPL>();
+  for (int p = p0; p < p1; ++p) {
+    const float al = expf(a.alpha[p] - m) / Z;
+    const int j = __ldg(a.csr_src + p);
+    Row<VPL> vj = load_row<LPR, VPL>(a.v, a.ld, j, lig);
+    if (has_e) {
+      vj = row_add(vj, load_row<LPR, VPL>(a.t_if, H, __ldg(a.csr_if + p), lig));
+      vj = row_add(vj, load_row<LPR, VPL>(a.t_rpc, H, __ldg(a.csr_rpc + p), lig));
+    }
+    row_fma(al, vj, acc);
+    __syncwarp(gmask);              // every lane has read the raw logit before lane 0 overwrites it
+    if (lig == 0) a.alpha[p] = al;
+  }
+  if (a.s) acc = row_add(acc, load_row<LPR, VPL>(a.s, a.ld, i, lig));
+  store_row<LPR, VPL>(a.out, a.ld_out, i, lig, acc);
+}
+
+struct TconvBwdDstArgs {
+  const float *g;   // dL/dout [N,H], row stride ld_g
+  int ld_g;
+  const float *q, *k, *v;
+  int ld;
+  const int *rowptr, *csr_src, *csr_if, *csr_rpc;
+  const float *t_if, *t_rpc;
+  const float* alpha;
+  float* dq;  // [N,H] row stride ld_d
+  int ld_d;
+  float* dsp;  // [E] ds/sqrt(C), CSR order
+  int N;
+  float inv_sqrt_c;
+};
+
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) k_tconv_bwd_dst(TconvBwdDstArgs a) {
+  constexpr int H = 4 * LPR * VPL;
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % LPR;
+  const int grp = lane / LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int i = warp * GPW + grp;
+  if (i >= a.N) return;
+  const bool has_e = a.t_if != nullptr;
+  const int p0 = __ldg(a.rowptr + i), p1 = __ldg(a.rowptr + i + 1);
+  const Row<VPL> g = load_row<LPR, VPL>(a.g, a.ld_g, i, lig);
+  float dot = 0.f;
+  for (int p = p0; p < p1; ++p) {
+    const int j = __ldg(a.csr_src + p);
+    Row<VPL> vj = load_row<LPR, VPL>(a.v, a.ld, j, lig);
+    if (has_e) {
+      vj = row_add(vj, load_row<LPR, VPL>(a.t_if, H, __ldg(a.csr_if + p), lig));
+      vj = row_add(vj, load_row<LPR, VPL>(a.t_rpc, H, __ldg(a.csr_rpc + p), lig));
+    }
+    const float da = group_sum<LPR>(row_dot(g, vj), gmask);
+    dot = fmaf(__ldg(a.alpha + p), da, dot);
+    if (lig == 0) a.dsp[p] = da;
+  }
+  __syncwarp(gmask);
+  Row<VPL> dq = row_zero<VPL>();
+  for (int p = p0; p < p1; ++p) {
+    const float ds = __ldg(a.alpha + p) * (a.dsp[p] - dot) * a.inv_sqrt_c;
+    const int j = __ldg(a.csr_src + p);
+    Row<VPL> kj = load_row<LPR, VPL>(a.k, a.ld, j, lig);
+    if (has_e) {
+      kj = row_add(kj, load_row<LPR, VPL>(a.t_if, H, __ldg(a.csr_if + p), lig));
+      kj = row_add(kj, load_row<LPR, VPL>(a.t_rpc, H, __ldg(a.csr_rpc + p), lig));
+    }
+    row_fma(ds, kj, dq);
+    __syncwarp(gmask);
+    if (lig == 0) a.dsp[p] = ds;
+  }
+  store_row<LPR, VPL>(a.dq, a.ld_d, i, lig, dq);
+}
+
+struct TconvBwdSrcArgs {
+  const float *g;
+  int ld_g;
+  const float* q;
+  int ld;
+  const int *colptr, *csc_pos, *csc_dst, *csr_if, *csr_rpc;
+  const float *alpha, *dsp;
+  float *dk, *dv;  // [N,H] row stride ld_d
+  int ld_d;
+  float *dt_if, *dt_rpc;  // [n_if,H], [n_rpc,H] accumulated with atomics (caller zeroes); may be null
+  int n_rpc;
+  int N;
+};
+
+// dynamic smem: n_rpc*H floats when the rpc-type table is privatised per CTA (few, hot rows)
+template <int LPR, int VPL, bool SMEM_RPC>
+__global__ void __launch_bounds__(256) k_tconv_bwd_src(TconvBwdSrcArgs a) {
+  constexpr int H = 4 * LPR * VPL;
+  constexpr int GPW = 32 / LPR;
+  extern __shared__ float s_rpc[];
+  const bool has_e = a.dt_if != nullptr;
+  if (SMEM_RPC && has_e) {
+    for (int x = threadIdx.x; x < a.n_rpc * H; x += blockDim.x) s_rpc[x] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % LPR;
+  const int grp = lane / LPR;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  for (int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp * GPW < a.N; warp += warps_total) {
+    const int j = warp * GPW + grp;
+    if (j >= a.N) continue;
+    const int c0 = __ldg(a.colptr + j), c1 = __ldg(a.colptr + j + 1);
+    Row<VPL> dk = row_zero<VPL>(), dv = row_zero<VPL>();
+    for (int c = c0; c < c1; ++c) {
+      const int p = __ldg(a.csc_pos + c);
+      const int i = __ldg(a.csc_dst + c);
+      const float al = __ldg(a.alpha + p), ds = __ldg(a.dsp + p);
+      const Row<VPL> gi = load_row<LPR, VPL>(a.g, a.ld_g, i, lig);
+      const Row<VPL> qi = load_row<LPR, VPL>(a.q, a.ld, i, lig);
+      row_fma(ds, qi, dk);
+      row_fma(al, gi, dv);
+      if (has_e) {
+        Row<VPL> de = row_zero<VPL>();
+        row_fma(al, gi, de);
+        row_fma(ds, qi, de);
+        float* pif = a.dt_if + (size_t)__ldg(a.csr_if + p) * H + lig * 4;
+        const int b = __ldg(a.csr_rpc + p);
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          red4(pif + u * LPR * 4, de.v[u]);
+          if (SMEM_RPC) {
+            float* ps = s_rpc + b * H + lig * 4 + u * LPR * 4;
+            atomicAdd(ps + 0, de.v[u].x);
+            atomicAdd(ps + 1, de.v[u].y);
+            atomicAdd(ps + 2, de.v[u].z);
+            atomicAdd(ps + 3, de.v[u].w);
+          } else {
+            red4(a.dt_rpc + (size_t)b * H + lig * 4 + u * LPR * 4, de.v[u]);
+          }
+        }
+      }
+    }
+    store_row<LPR, VPL>(a.dk, a.ld_d, j, lig, dk);
+    store_row<LPR, VPL>(a.dv, a.ld_d, j, lig, dv);
+  }
+  if (SMEM_RPC && has_e) {
+    __syncthreads();
+    for (int x = threadIdx.x; x < a.n_rpc * H; x += blockDim.x) {
+      float v = s_rpc[x];
+      if (v != 0.f) atomicAdd(a.dt_rpc + x, v);
+    }
+  }
+}
+
+template <typename F>
+int dispatch_h(int H, F&& f) {
+  switch (H) {
+    case 4: return f(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+    case 8: return f(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{});
+    case 16: return f(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
+    case 32: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
+    case 64: return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 1>{});
+    case 96: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 3>{});
+    case 128: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 1>{});
+    case 192: return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 3>{});
+    case 256: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 2>{});
+    default: return PERT_ERR_UNSUPPORTED;
+  }
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int pert_tconv_supported_width(int H) {
+  return dispatch_h(H, [](auto, auto) { return 1; }) == 1 ? 1 : 0;
+}
+
+int pert_tconv_fwd(const float* q, const float* k, const float* v, const float* s, int ld, const int* rowptr,
+                   const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if, const float* t_rpc,
+                   float* out, int ld_out, float* alpha, long long N, int H, void* stream) {
+  if (N < 0 || !q || !k || !v || !rowptr || !out) return PERT_ERR_BADARG;
+  if (ld % 4 || ld_out % 4 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) ||
+      (s && !aligned16(s)) || (t_if && (!aligned16(t_if) || !aligned16(t_rpc) || !t_rpc || !csr_if || !csr_rpc)))
+    return PERT_ERR_BADARG;
+  if (N == 0) return PERT_OK;
+  TconvArgs a{q, k, v, s, ld, rowptr, csr_src, csr_if, csr_rpc, t_if, t_rpc, out, ld_out, alpha, (int)N,
+              1.0f / sqrtf((float)H)};
+  int rc = dispatch_h(H, [&](auto lpr, auto vpl) {
+    constexpr int LPR = decltype(lpr)::value, VPL = decltype(vpl)::value;
+    const int gpw = 32 / LPR;
+    const long long warps = (N + gpw - 1) / gpw;
+    k_tconv_fwd<LPR, VPL><<<pert_cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    return PERT_OK;
+  });
+  if (rc) return rc;
+  PERT_LAUNCH_CHECK();
+  return PERT_OK;
+}
+
+int pert_tconv_bwd(const float* g, int ld_g, const float* q, const float* k, const float* v, int ld,
+                   const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr,
+                   const int* csc_pos, const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha,
+                   float* dq, float* dk, float* dv, int ld_d, float* dsp, float* dt_if, float* dt_rpc, int n_rpc,
+                   long long N, int H, void* stream) {
+  if (N < 0 || !g || !q || !k || !v || !rowptr || !colptr || !dq || !dk || !dv) return PERT_ERR_BADARG;
+  if (ld % 4 || ld_g % 4 || ld_d % 4 || !aligned16(g) || !aligned16(q) || !aligned16(k) || !aligned16(v) ||
+      !aligned16(dq) || !aligned16(dk) || !aligned16(dv))
+    return PERT_ERR_BADARG;
+  if (t_if && (!t_rpc || !dt_if || !dt_rpc || !csr_if || !csr_rpc || !aligned16(dt_if) || !aligned16(dt_rpc)))
+    return PERT_ERR_BADARG;
+  if (N == 0) return PERT_OK;
+  const float isc = 1.0f / sqrtf((float)H);
+  TconvBwdDstArgs ad{g, ld_g, q, k, v, ld, rowptr, csr_src, csr_if, csr_rpc, t_if, t_rpc, alpha, dq, ld_d, dsp,
+                     (int)N, isc};
+  TconvBwdSrcArgs as{g, ld_g, q, ld, colptr, csc_pos, csc_dst, csr_if, csr_rpc, alpha, dsp, dk, dv, ld_d,
+                     t_if ? dt_if : nullptr, t_if ? dt_rpc : nullptr, n_rpc, (int)N};
+  int rc = dispatch_h(H, [&](auto lpr, auto vpl) {
+    constexpr int LPR = decltype(lpr)::value, VPL = decltype(vpl)::value;
+    constexpr int HH = 4 * LPR * VPL;
+    const int gpw = 32 / LPR;
+    const long long warps = (N + gpw - 1) / gpw;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_tconv_bwd_dst<LPR, VPL><<<pert_cdiv(warps * 32, 256), 256, 0, st>>>(ad);
+    const size_t smem = t_if ? (size_t)n_rpc * HH * sizeof(float) : 0;
+    // persistent-ish grid (multiple of the SM count) so the privatised rpc table is flushed few times
+    const long long blocks = (warps * 32 + 255) / 256;
+    const int grid = (int)(blocks < (long long)PERT_NUM_SMS * 8 ? blocks : (long long)PERT_NUM_SMS * 8);
+    if (smem > 0 && smem <= 32 * 1024)
+      k_tconv_bwd_src<LPR, VPL, true><<<grid, 256, smem, st>>>(as);
+    else
+      k_tconv_bwd_src<LPR, VPL, false><<<grid, 256, 0, st>>>(as);
+    return PERT_OK;
+  });
+  if (rc) return rc;
+  PERT_LAUNCH_CHECK();
+  return PERT_OK;
+}
+
+}  // extern "C"

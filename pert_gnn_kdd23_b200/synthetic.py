@@ -1,0 +1,173 @@
+"""Seeded synthetic call-graph generator for the BASELINE.json configurations.
+
+The reference trains on the Alibaba 2021 micro-service traces (200 GB, not
+available); its per-sample tensor schema is reference pert_gnn.py:163-173.
+This module emits ``Data`` objects of exactly that schema with the shapes
+SURVEY.md section 8d defines:
+
+  x [n,9] f32 (8 resource stats + missing indicator, stats zeroed where the
+  indicator is 1 -- mirrors pert_gnn.py:44-66), edge_index [2,e] i64,
+  edge_attr [e,2|4] i64 (interface id, rpctype id[, call_ind, same_ms]),
+  cat_X [n,1] i64 (micro-service id), node_depth [n,1] i64,
+  pattern_num_nodes [n,1] f32, pattern_probs [P,1] f32, entry_id [1] i64,
+  y 0-dim i64, plus ``rt_probs`` [n,1] f32 = the per-node pattern probability the
+  reference's train loop rebuilds on the host every step (pert_gnn.py:220-230).
+
+DAG law: n nodes on L levels, node 0 the sole root (level 0); every other node
+gets one parent drawn uniformly from the previous level (so min-depth == level);
+the remaining m-(n-1) edges are uniform (lower level -> strictly higher level)
+pairs, no duplicates; node ids (except the root) and the edge order are
+shuffled -- sorting is part of the measured collation.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .data import Data
+
+N_MS, N_IF, N_RPC, N_ENTRY, N_FEAT = 4096, 1024, 8, 64, 9
+
+# id -> (graphs, nodes, edges, hidden, num_layers, levels);  nodes=None => power law
+CONFIGS = {
+    1: dict(graphs=64, nodes=50, edges=150, hidden=32, num_layers=1, levels=5),
+    2: dict(graphs=256, nodes=200, edges=600, hidden=64, num_layers=3, levels=8),
+    3: dict(graphs=1024, nodes=None, edges=None, hidden=128, num_layers=3, levels=None),
+    4: dict(graphs=4096, nodes=200, edges=600, hidden=128, num_layers=3, levels=8),
+    5: dict(graphs=256, nodes=1000, edges=3000, hidden=128, num_layers=5, levels=12),
+}
+
+
+def model_args(cfg_id):
+    """Positional ctor args of SAGEDeterministic for a config."""
+    c = CONFIGS[cfg_id]
+    return (N_FEAT, [N_MS], N_ENTRY - 1, N_IF - 1, N_RPC - 1, c["hidden"], c["num_layers"], 0.0)
+
+
+def _level_sizes(rng, n, L):
+    L = max(1, min(L, n))
+    if L == 1:
+        return np.array([n], dtype=np.int64)
+    sizes = np.ones(L, dtype=np.int64)
+    extra = n - L
+    if extra > 0:
+        sizes[1:] += np.bincount(rng.integers(1, L, size=extra), minlength=L)[1:] if L > 1 else 0
+    return sizes
+
+
+def random_dag(rng, n, m, L):
+    """Returns (edge_index int64 [2,m'], level int64 [n]); m' = min(m, max possible)."""
+    sizes = _level_sizes(rng, n, L)
+    L = len(sizes)
+    level_sorted = np.repeat(np.arange(L), sizes)               # level of position p (sorted)
+    ids = np.concatenate([[0], 1 + rng.permutation(n - 1)]) if n > 1 else np.array([0])
+    level = np.empty(n, dtype=np.int64)
+    level[ids] = level_sorted
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    # spanning tree: parent uniform in previous level
+    pos = np.arange(sizes[0], n)
+    lv = level_sorted[pos]
+    par_pos = starts[lv - 1] + (rng.random(pos.shape[0]) * sizes[lv - 1]).astype(np.int64)
+    src = ids[par_pos]
+    dst = ids[pos]
+    have = set((src * n + dst).tolist())
+    # cap by the number of admissible (lower -> strictly higher level) pairs
+    cum = np.cumsum(sizes)
+    max_pairs = int(sum(int(sizes[l]) * int(n - cum[l]) for l in range(L)))
+    m = min(m, max_pairs)
+    extra_s, extra_d = [], []
+    need = m - (n - 1)
+    while need > 0:
+        k = max(64, 3 * need)
+        u = rng.integers(0, n, size=k)
+        v = rng.integers(0, n, size=k)
+        ok = level[u] < level[v]
+        for a, b in zip(u[ok].tolist(), v[ok].tolist()):
+            key = a * n + b
+            if key not in have:
+                have.add(key)
+                extra_s.append(a)
+                extra_d.append(b)
+                need -= 1
+                if need == 0:
+                    break
+    src = np.concatenate([src, np.array(extra_s, dtype=np.int64)])
+    dst = np.concatenate([dst, np.array(extra_d, dtype=np.int64)])
+    order = rng.permutation(src.shape[0])
+    return np.stack([src[order], dst[order]]).astype(np.int64), level
+
+
+def _node_depth(level):
+    # reference quirk (misc.py:166-175,215): depth/max truncated to long -> {0,1}
+    mx = max(int(level.max()), 1)
+    return (level.astype(np.float64) / mx).astype(np.int64).reshape(-1, 1)
+
+
+def make_graph(rng, n, m, L, patterns=1, edge_attr_cols=2):
+    """One reference-schema ``Data``: disjoint union of ``patterns`` runtime-pattern
+    DAGs (pert_gnn.py:134-173)."""
+    eis, levels, pnn, rtp = [], [], [], []
+    probs = rng.random(patterns) + 0.1
+    probs = probs / probs.sum()
+    off = 0
+    for p in range(patterns):
+        np_ = n if patterns == 1 else max(2, int(n // patterns))
+        mp_ = m if patterns == 1 else max(np_ - 1, int(m // patterns))
+        ei, lv = random_dag(rng, np_, mp_, L)
+        eis.append(ei + off)
+        levels.append(lv)
+        pnn.append(np.full((np_, 1), float(np_), dtype=np.float32))
+        rtp.append(np.full((np_, 1), float(probs[p]), dtype=np.float32))
+        off += np_
+    edge_index = np.concatenate(eis, axis=1)
+    level = np.concatenate(levels)
+    nn_, ne = off, edge_index.shape[1]
+    x = rng.random((nn_, N_FEAT), dtype=np.float32)
+    miss = rng.random(nn_) < 0.2
+    x[:, 8] = miss.astype(np.float32)
+    x[miss, :8] = 0.0
+    ea = np.zeros((ne, edge_attr_cols), dtype=np.int64)
+    ea[:, 0] = rng.integers(0, N_IF, size=ne)
+    ea[:, 1] = rng.integers(0, N_RPC, size=ne)
+    if edge_attr_cols == 4:
+        ea[:, 2] = rng.integers(0, 2, size=ne)
+        ea[:, 3] = rng.integers(0, 2, size=ne)
+    return Data(
+        x=torch.from_numpy(x),
+        edge_index=torch.from_numpy(edge_index),
+        edge_attr=torch.from_numpy(ea),
+        cat_X=torch.from_numpy(rng.integers(0, N_MS, size=(nn_, 1))),
+        node_depth=torch.from_numpy(np.concatenate([_node_depth(l) for l in levels])),
+        pattern_num_nodes=torch.from_numpy(np.concatenate(pnn)),
+        pattern_probs=torch.from_numpy(probs.astype(np.float32).reshape(-1, 1)),
+        entry_id=torch.from_numpy(rng.integers(0, N_ENTRY, size=1)),
+        y=torch.tensor(int(rng.integers(1, 5000)), dtype=torch.long),
+        rt_probs=torch.from_numpy(np.concatenate(rtp)),
+        level=torch.from_numpy(level),
+    )
+
+
+def _powerlaw_nodes(rng, lo=20, hi=500, alpha=1.5):
+    # truncated Pareto(alpha) on [lo, hi] by inverse CDF
+    u = rng.random()
+    a = lo ** (-alpha)
+    b = hi ** (-alpha)
+    return int((a - u * (a - b)) ** (-1.0 / alpha))
+
+
+def make_data_list(cfg_id, num_graphs=None, seed=None, patterns=1, edge_attr_cols=2):
+    """List of ``Data`` for one BASELINE config; seed defaults to 1000+cfg_id."""
+    c = CONFIGS[cfg_id]
+    rng = np.random.default_rng(1000 + cfg_id if seed is None else seed)
+    out = []
+    for _ in range(c["graphs"] if num_graphs is None else num_graphs):
+        if c["nodes"] is None:
+            n = _powerlaw_nodes(rng)
+            m = 3 * n
+            L = int(min(10, max(3, round(math.log2(n)))))
+        else:
+            n, m, L = c["nodes"], c["edges"], c["levels"]
+        out.append(make_graph(rng, n, m, L, patterns=patterns, edge_attr_cols=edge_attr_cols))
+    return out

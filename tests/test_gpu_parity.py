@@ -1,0 +1,358 @@
+"""-m gpu parity tests: libpertgnn CUDA kernels (through the C-ABI) vs the CPU oracle on the same seeded inputs.
+Bar: integer/index outputs bit-exact; fp32 within 1e-4 relative (BASELINE.json north_star)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import index_oracle, model_oracle
+from tests.helpers import RTOL, assert_close, forward_args, make_batch, make_models, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(t):
+    return t.cuda()
+
+
+# ------------------------------------------------------------------ index construction (bit-exact)
+@pytest.mark.parametrize("cfg,ng", [(1, None), (2, 32), (3, 64), (5, 4)])
+def test_build_index_bit_exact(cfg, ng):
+    from pert_gnn_kdd23_b200.index import build_index
+
+    b = make_batch(cfg, ng)
+    N = b.x.size(0)
+    gi = build_index(_dev(b.edge_index), N, _dev(b.edge_attr), 1024, 8).check()
+    ref = index_oracle.build_index(b.edge_index.numpy(), N)
+    for k in ("rowptr", "perm", "csr_src", "colptr", "csc_pos", "csc_dst"):
+        assert np.array_equal(getattr(gi, k).cpu().numpy(), ref[k]), k
+    ea = b.edge_attr.numpy()
+    assert np.array_equal(gi.csr_if.cpu().numpy(), ea[ref["perm"], 0].astype(np.int32))
+    assert np.array_equal(gi.csr_rpc.cpu().numpy(), ea[ref["perm"], 1].astype(np.int32))
+
+
+def test_build_index_hubs_duplicates_empty():
+    from pert_gnn_kdd23_b200.index import build_index
+
+    rng = np.random.default_rng(7)
+    N = 500
+    # star hub with in-degree 3000 (long-segment path), duplicate edges, self loops, isolated nodes
+    src = np.concatenate([rng.integers(0, N, 3000), rng.integers(0, 50, 2000), np.array([3, 3, 3, 7])])
+    dst = np.concatenate([np.full(3000, 11), rng.integers(0, 50, 2000), np.array([4, 4, 4, 7])])
+    ei = torch.from_numpy(np.stack([src, dst]).astype(np.int64))
+    gi = build_index(_dev(ei), N).check()
+    ref = index_oracle.build_index(ei.numpy(), N)
+    for k in ("rowptr", "perm", "csr_src", "colptr", "csc_pos", "csc_dst"):
+        assert np.array_equal(getattr(gi, k).cpu().numpy(), ref[k]), k
+    # empty edge set
+    gi0 = build_index(torch.zeros(2, 0, dtype=torch.long).cuda(), 5)
+    assert gi0.rowptr.cpu().tolist() == [0] * 6 and gi0.colptr.cpu().tolist() == [0] * 6
+
+
+def test_index_range_error_is_reported():
+    from pert_gnn_kdd23_b200 import _lib
+    from pert_gnn_kdd23_b200.index import build_index
+
+    ei = torch.tensor([[0, 1], [1, 9]], dtype=torch.long).cuda()
+    with pytest.raises(_lib.PertGnnError):
+        build_index(ei, 3, check=True)
+
+
+def test_graph_ptr_and_min_depth():
+    from pert_gnn_kdd23_b200.index import build_index, graph_ptr, min_depth
+
+    b = make_batch(3, 48)
+    N, B = b.x.size(0), b.num_graphs
+    gi = build_index(_dev(b.edge_index), N)
+    gp = graph_ptr(_dev(b.batch), B)
+    assert np.array_equal(gp.cpu().numpy(), b.ptr.numpy().astype(np.int32))
+    roots = b.ptr[:-1].to(torch.int32).cuda()          # node 0 of every graph is its root
+    d = min_depth(gp, gi, roots).cpu().numpy()
+    assert np.array_equal(d, b.level.numpy().astype(np.int32))      # generator: min-depth == level
+    # against the DFS restatement graph by graph, incl. unreachable nodes (root != 0)
+    g0 = slice(int(b.ptr[0]), int(b.ptr[1]))
+    ei = b.edge_index[:, (b.edge_index[0] < b.ptr[1])]
+    roots2 = roots.clone()
+    roots2[0] = 5
+    d2 = min_depth(gp, gi, roots2).cpu().numpy()[g0]
+    assert np.array_equal(d2, index_oracle.dfs_min_depth(ei.numpy(), int(b.ptr[1]), 5))
+
+
+# ------------------------------------------------------------------ segmented reduce (metric kernel)
+@pytest.mark.parametrize("H", [1, 3, 4, 32, 64, 128, 256])
+@pytest.mark.parametrize("op", ["max", "sum"])
+def test_segment_reduce(H, op):
+    from pert_gnn_kdd23_b200 import ops
+    from pert_gnn_kdd23_b200.index import build_index
+
+    b = make_batch(3, 40, seed=5)
+    N, E = b.x.size(0), b.edge_index.size(1)
+    gi = build_index(_dev(b.edge_index), N)
+    torch.manual_seed(1)
+    msg = torch.randn(E, H)
+    ref = model_oracle.scatter(msg, b.edge_index[1], N, op)
+    # (a) original COO order, gathered through the stable permutation
+    out = ops.segment_reduce(_dev(msg), gi.rowptr, gi.perm, op)
+    if op == "max":
+        assert torch.equal(out.cpu(), ref)                         # max is exact
+    else:
+        assert_close(out, ref, what="segsum")
+    # (b) pre-permuted (CSR-order) messages, no perm
+    out2 = ops.segment_reduce(_dev(msg[gi.perm.cpu().long()]), gi.rowptr, None, op)
+    if op == "max":
+        assert torch.equal(out2.cpu(), ref)
+    else:
+        assert_close(out2, ref, what="segsum-csr")
+
+
+def test_segment_reduce_backward():
+    from pert_gnn_kdd23_b200 import ops
+    from pert_gnn_kdd23_b200.index import build_index
+
+    b = make_batch(1, 8)
+    N, E = b.x.size(0), b.edge_index.size(1)
+    gi = build_index(_dev(b.edge_index), N)
+    torch.manual_seed(2)
+    for op in ("max", "sum"):
+        msg = torch.randn(E, 16, requires_grad=True)
+        w = torch.randn(N, 16)
+        (model_oracle.scatter(msg, b.edge_index[1], N, op) * w).sum().backward()
+        mg = msg.detach().cuda().requires_grad_()
+        (ops.segment_reduce(mg, gi.rowptr, gi.perm, op) * w.cuda()).sum().backward()
+        assert_close(mg.grad, msg.grad, what=f"d{op}")
+
+
+# ------------------------------------------------------------------ dense linears
+@pytest.mark.parametrize("M,K,Nc", [(1000, 80, 256), (257, 73, 33), (5, 1, 7), (64, 128, 1), (3000, 64, 128)])
+def test_linear_fwd_bwd(M, K, Nc):
+    from pert_gnn_kdd23_b200 import ops
+
+    torch.manual_seed(M + K)
+    x = torch.randn(M, K, requires_grad=True)
+    W = (torch.randn(Nc, K) / math.sqrt(K)).requires_grad_()
+    bia = torch.randn(Nc, requires_grad=True)
+    for relu in (False, True):
+        y = torch.nn.functional.linear(x.double(), W.double(), bia.double())
+        y = torch.relu(y) if relu else y
+        gy = torch.randn(M, Nc)
+        gx, gW, gb = torch.autograd.grad(y, (x, W, bia), gy.double())
+        xc, Wc, bc = (t.detach().cuda().requires_grad_() for t in (x, W, bia))
+        yc = ops.linear(xc, Wc, bc, relu=relu)
+        assert_close(yc, y, rtol=2e-6, what="linear fwd")
+        gxc, gWc, gbc = torch.autograd.grad(yc, (xc, Wc, bc), gy.cuda())
+        assert_close(gxc, gx, rtol=2e-6, what="dX")
+        assert_close(gWc, gW, rtol=2e-5, what="dW")
+        assert_close(gbc, gb, rtol=2e-5, what="db")
+
+
+def test_linear_blocked_planes():
+    from pert_gnn_kdd23_b200 import ops
+
+    torch.manual_seed(0)
+    M, K, H = 777, 80, 64
+    x = torch.randn(M, K).cuda().requires_grad_()
+    W = (torch.randn(4 * H, K) / 9).cuda().requires_grad_()
+    b = torch.randn(4 * H).cuda().requires_grad_()
+    planes = ops.linear(x, W, b, out_blocks=4)
+    ref = torch.nn.functional.linear(x.double(), W.double(), b.double())
+    assert_close(planes.permute(1, 0, 2).reshape(M, 4 * H), ref, rtol=2e-6)
+    g = torch.randn(4, M, H).cuda()
+    gx, gW, gb = torch.autograd.grad(planes, (x, W, b), g)
+    rx, rW, rb = torch.autograd.grad(ref, (x, W, b), g.permute(1, 0, 2).reshape(M, 4 * H).double())
+    assert_close(gx, rx, rtol=2e-6)
+    assert_close(gW, rW, rtol=2e-5)
+    assert_close(gb, rb, rtol=2e-5)
+
+
+# ------------------------------------------------------------------ fused TransformerConv
+@pytest.mark.parametrize("H", [4, 32, 64, 128])
+def test_tconv_layer_fwd_bwd(H):
+    """One conv layer incl. node linears, edge tables and skip vs the oracle conv, outputs and ALL gradients."""
+    from pert_gnn_kdd23_b200.index import build_index
+    from pert_gnn_kdd23_b200.nn import TransformerConv
+
+    b = make_batch(3, 24, seed=11)
+    N, E = b.x.size(0), b.edge_index.size(1)
+    Din = H
+    torch.manual_seed(3)
+    oc = model_oracle.OracleTransformerConv(Din, H, heads=1, edge_dim=2 * H).double()
+    cc = TransformerConv(Din, H, heads=1, edge_dim=2 * H)
+    cc.load_state_dict({k: v.float() for k, v in oc.state_dict().items()})
+    cc = cc.cuda()
+    if_emb = torch.randn(1024, H)
+    rpc_emb = torch.randn(8, H)
+    x = torch.randn(N, Din)
+    gout = torch.randn(N, H)
+    # oracle (fp64)
+    xo = x.double().requires_grad_()
+    ifo, rpo = if_emb.double().requires_grad_(), rpc_emb.double().requires_grad_()
+    ee = torch.cat([ifo[b.edge_attr[:, 0]], rpo[b.edge_attr[:, 1]]], dim=1)
+    yo, alpha_o = oc(xo, b.edge_index, ee, return_alpha=True)
+    yo.backward(gout.double())
+    # CUDA
+    gi = build_index(_dev(b.edge_index), N, _dev(b.edge_attr), 1024, 8)
+    xc = x.cuda().requires_grad_()
+    ifc, rpc = if_emb.cuda().requires_grad_(), rpc_emb.cuda().requires_grad_()
+    yc = cc.forward_tables(xc, gi, ifc, rpc)
+    yc.backward(gout.cuda())
+    assert_close(yc, yo, what="conv out")
+    assert_close(xc.grad, xo.grad, what="dx")
+    assert_close(ifc.grad, ifo.grad, what="d if_emb")
+    assert_close(rpc.grad, rpo.grad, what="d rpc_emb")
+    for (n, pc), (_, po) in zip(cc.named_parameters(), oc.named_parameters()):
+        assert_close(pc.grad, po.grad, what=f"d {n}")
+
+
+def test_tconv_generic_edge_features_and_no_edge_dim():
+    """PyG-signature forward(x, edge_index, edge_attr[E,De]) and the edge_dim=None variant."""
+    from pert_gnn_kdd23_b200.nn import TransformerConv
+
+    b = make_batch(1, 6, seed=3)
+    N, E = b.x.size(0), b.edge_index.size(1)
+    torch.manual_seed(5)
+    for edge_dim in (6, None):
+        oc = model_oracle.OracleTransformerConv(9, 16, edge_dim=edge_dim)
+        cc = TransformerConv(9, 16, edge_dim=edge_dim)
+        cc.load_state_dict(oc.state_dict())
+        cc = cc.cuda()
+        ea = torch.randn(E, 6) if edge_dim else None
+        xo = b.x.clone().requires_grad_()
+        yo = oc(xo, b.edge_index, ea)
+        yo.square().sum().backward()
+        xc = b.x.cuda().requires_grad_()
+        yc = cc(xc, b.edge_index.cuda(), ea.cuda() if ea is not None else None)
+        yc.square().sum().backward()
+        assert_close(yc, yo, what="generic conv")
+        assert_close(xc.grad, xo.grad, what="generic conv dx")
+        for (n, pc), (_, po) in zip(cc.named_parameters(), oc.named_parameters()):
+            assert_close(pc.grad, po.grad, what=f"generic d {n}")
+
+
+# ------------------------------------------------------------------ batch norm, pool
+@pytest.mark.parametrize("N,H", [(1000, 64), (37, 32), (5000, 128), (300, 4)])
+def test_batchnorm_relu(N, H):
+    from pert_gnn_kdd23_b200.nn import BatchNorm1d
+
+    torch.manual_seed(N)
+    x = torch.randn(N, H) * 3 + 5          # large mean: stresses the variance computation
+    bo = torch.nn.BatchNorm1d(H)
+    with torch.no_grad():
+        bo.weight.uniform_(0.5, 1.5)
+        bo.bias.uniform_(-1, 1)
+    bc = BatchNorm1d(H)
+    bc.load_state_dict(bo.state_dict())
+    bc = bc.cuda()
+    g = torch.randn(N, H)
+    for training in (True, False):
+        bo.train(training)
+        bc.train(training)
+        xo = x.clone().requires_grad_()
+        yo = torch.relu(bo(xo))
+        yo.backward(g)
+        xc = x.cuda().requires_grad_()
+        yc = bc(xc, relu=True)
+        yc.backward(g.cuda())
+        assert_close(yc, yo, what="bn y")
+        assert_close(xc.grad, xo.grad, what="bn dx")
+        if training:
+            assert_close(bc.weight.grad, bo.weight.grad, what="dgamma")
+            assert_close(bc.bias.grad, bo.bias.grad, what="dbeta")
+            assert_close(bc.running_mean, bo.running_mean, what="running_mean")
+            assert_close(bc.running_var, bo.running_var, what="running_var")
+            assert int(bc.num_batches_tracked) == int(bo.num_batches_tracked)
+        bo.zero_grad(); bc.zero_grad()
+
+
+def test_pool_local():
+    from pert_gnn_kdd23_b200 import ops
+
+    b = make_batch(3, 40, seed=2, patterns=1)
+    N, H, B = b.x.size(0), 64, b.num_graphs
+    torch.manual_seed(0)
+    x = torch.randn(N, H, requires_grad=True)
+    w = torch.randn(1, H, requires_grad=True)
+    bl = torch.randn(1, requires_grad=True)
+    probs, pnn = torch.rand(N, 1) + 0.1, b.pattern_num_nodes
+    local_o = torch.nn.functional.linear(x, w, bl)
+    pool_o = model_oracle.global_add_pool(x * probs / pnn, b.batch)
+    gp, gl = torch.randn(B, H), torch.randn(N, 1)
+    go = torch.autograd.grad((pool_o * gp).sum() + (local_o * gl).sum(), (x, w, bl))
+    xc, wc, bc = (t.detach().cuda().requires_grad_() for t in (x, w, bl))
+    pool_c, local_c = ops.pool_local(xc, probs.cuda(), pnn.cuda(), b.batch.cuda(), wc, bc, B)
+    gc = torch.autograd.grad((pool_c * gp.cuda()).sum() + (local_c * gl.cuda()).sum(), (xc, wc, bc))
+    assert_close(pool_c, pool_o, what="pool")
+    assert_close(local_c, local_o, what="local")
+    for a, r, n in zip(gc, go, ("dx", "dw", "db")):
+        assert_close(a, r, what=n)
+
+
+# ------------------------------------------------------------------ whole model
+def _model_parity(cfg, ng, patterns=1, cols=2, train=True, seed=0):
+    oracle, model = make_models(cfg, seed=seed)
+    b = make_batch(cfg, ng, patterns=patterns, edge_attr_cols=cols)
+    oracle.train(train)
+    model.train(train)
+    go, lo = oracle(*forward_args(b))
+    bc = b.to("cuda")
+    gc, lc = model(*forward_args(bc))
+    assert_close(gc, go, what="global_predict")
+    assert_close(lc, lo, what="local_predict")
+    if not train:
+        return
+    loss_o = model_oracle.torch_quantile_loss(b.y.float(), go.flatten(), 0.5) + 1e-3 * lo.square().mean()
+    loss_c = model_oracle.torch_quantile_loss(bc.y.float(), gc.flatten(), 0.5) + 1e-3 * lc.square().mean()
+    loss_o.backward()
+    loss_c.backward()
+    assert_close(loss_c, loss_o, what="loss")
+    po = dict(oracle.named_parameters())
+    worst = 0.0
+    for n, p in model.named_parameters():
+        assert p.grad is not None, n
+        e = rel_err(p.grad, po[n].grad)
+        worst = max(worst, e)
+        assert e <= 5 * RTOL, f"grad {n}: rel err {e:.3e}"
+    # running statistics moved identically
+    for n, bbuf in model.named_buffers():
+        assert_close(bbuf.float(), dict(oracle.named_buffers())[n].float(), what=n)
+    return worst
+
+
+def test_model_cfg1_train():
+    _model_parity(1, None)
+
+
+def test_model_cfg1_eval():
+    _model_parity(1, None, train=False)
+
+
+def test_model_multi_pattern_four_attr_cols():
+    _model_parity(1, 16, patterns=3, cols=4)
+
+
+def test_model_cfg2_slice():
+    _model_parity(2, 24)
+
+
+def test_model_cfg3_powerlaw():
+    _model_parity(3, 96)
+
+
+def test_model_cfg5_deep():
+    _model_parity(5, 4)
+
+
+def test_two_graph_batch_equals_separate_graphs():
+    """Graphs in a batch only couple through BatchNorm: in eval mode a 2-graph batch == the 2 graphs alone."""
+    _, model = make_models(1)
+    model.eval()
+    from pert_gnn_kdd23_b200.data import Batch
+    from pert_gnn_kdd23_b200.synthetic import make_data_list
+
+    dl = make_data_list(1, 2)
+    both = Batch.from_data_list(dl).to("cuda")
+    g_both, _ = model(*forward_args(both))
+    for i in range(2):
+        one = Batch.from_data_list([dl[i]]).to("cuda")
+        g_one, _ = model(*forward_args(one))
+        assert_close(g_one, g_both[i:i + 1], rtol=1e-5)
