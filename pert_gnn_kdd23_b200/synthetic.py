@@ -14,7 +14,7 @@ SURVEY.md section 8d defines:
   reference's train loop rebuilds on the host every step (pert_gnn.py:220-230).
 
 DAG law: n nodes on L levels, node 0 the sole root (level 0); every other node
-gets one parent drawn uniformly from the previous level (so min-depth == level);
+gets one parent drawn uniformly from the previous level (so every node is reachable);
 the remaining m-(n-1) edges are uniform (lower level -> strictly higher level)
 pairs, no duplicates; node ids (except the root) and the edge order are
 shuffled -- sorting is part of the measured collation.
@@ -99,16 +99,35 @@ def random_dag(rng, n, m, L):
     return np.stack([src[order], dst[order]]).astype(np.int64), level
 
 
-def _node_depth(level):
-    # reference quirk (misc.py:166-175,215): depth/max truncated to long -> {0,1}
-    mx = max(int(level.max()), 1)
-    return (level.astype(np.float64) / mx).astype(np.int64).reshape(-1, 1)
+def bfs_min_depth(edge_index, n, root=0):
+    """Min hop depth from ``root`` over out-edges (what misc.py:59-63 computes); -1 if unreachable."""
+    depth = np.full(n, -1, dtype=np.int64)
+    depth[root] = 0
+    src, dst = edge_index
+    frontier = np.zeros(n, dtype=bool)
+    frontier[root] = True
+    d = 0
+    while frontier.any():
+        nxt = np.zeros(n, dtype=bool)
+        nxt[dst[frontier[src]]] = True
+        nxt &= depth < 0
+        d += 1
+        depth[nxt] = d
+        frontier = nxt
+    return depth
+
+
+def _node_depth(depth):
+    # reference quirk (misc.py:159-175,215): unreachable -> 0, depth/max truncated to long -> {0,1}
+    d = np.where(depth < 0, 0, depth).astype(np.float64)
+    mx = d.max() if d.max() > 0 else 1.0
+    return (d / mx).astype(np.int64).reshape(-1, 1)
 
 
 def make_graph(rng, n, m, L, patterns=1, edge_attr_cols=2):
     """One reference-schema ``Data``: disjoint union of ``patterns`` runtime-pattern
     DAGs (pert_gnn.py:134-173)."""
-    eis, levels, pnn, rtp = [], [], [], []
+    eis, levels, depths, pnn, rtp = [], [], [], [], []
     probs = rng.random(patterns) + 0.1
     probs = probs / probs.sum()
     off = 0
@@ -118,6 +137,7 @@ def make_graph(rng, n, m, L, patterns=1, edge_attr_cols=2):
         ei, lv = random_dag(rng, np_, mp_, L)
         eis.append(ei + off)
         levels.append(lv)
+        depths.append(bfs_min_depth(ei, np_, 0))
         pnn.append(np.full((np_, 1), float(np_), dtype=np.float32))
         rtp.append(np.full((np_, 1), float(probs[p]), dtype=np.float32))
         off += np_
@@ -139,13 +159,14 @@ def make_graph(rng, n, m, L, patterns=1, edge_attr_cols=2):
         edge_index=torch.from_numpy(edge_index),
         edge_attr=torch.from_numpy(ea),
         cat_X=torch.from_numpy(rng.integers(0, N_MS, size=(nn_, 1))),
-        node_depth=torch.from_numpy(np.concatenate([_node_depth(l) for l in levels])),
+        node_depth=torch.from_numpy(np.concatenate([_node_depth(d) for d in depths])),
         pattern_num_nodes=torch.from_numpy(np.concatenate(pnn)),
         pattern_probs=torch.from_numpy(probs.astype(np.float32).reshape(-1, 1)),
         entry_id=torch.from_numpy(rng.integers(0, N_ENTRY, size=1)),
         y=torch.tensor(int(rng.integers(1, 5000)), dtype=torch.long),
         rt_probs=torch.from_numpy(np.concatenate(rtp)),
         level=torch.from_numpy(level),
+        min_depth=torch.from_numpy(np.concatenate(depths)),
     )
 
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import index_oracle, model_oracle
-from tests.helpers import RTOL, assert_close, forward_args, make_batch, make_models, rel_err
+from tests.helpers import RTOL, assert_close, assert_grads_close, forward_args, make_batch, make_models, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -69,7 +69,12 @@ def test_graph_ptr_and_min_depth():
     assert np.array_equal(gp.cpu().numpy(), b.ptr.numpy().astype(np.int32))
     roots = b.ptr[:-1].to(torch.int32).cuda()          # node 0 of every graph is its root
     d = min_depth(gp, gi, roots).cpu().numpy()
-    assert np.array_equal(d, b.level.numpy().astype(np.int32))      # generator: min-depth == level
+    assert np.array_equal(d, b.min_depth.numpy().astype(np.int32))
+    for g in range(B):                                   # DFS restatement, graph by graph
+        lo, hi = int(b.ptr[g]), int(b.ptr[g + 1])
+        m = (b.edge_index[0] >= lo) & (b.edge_index[0] < hi)
+        ref = index_oracle.dfs_min_depth((b.edge_index[:, m] - lo).numpy(), hi - lo, 0)
+        assert np.array_equal(d[lo:hi], ref), g
     # against the DFS restatement graph by graph, incl. unreachable nodes (root != 0)
     g0 = slice(int(b.ptr[0]), int(b.ptr[1]))
     ei = b.edge_index[:, (b.edge_index[0] < b.ptr[1])]
@@ -200,8 +205,7 @@ def test_tconv_layer_fwd_bwd(H):
     assert_close(xc.grad, xo.grad, what="dx")
     assert_close(ifc.grad, ifo.grad, what="d if_emb")
     assert_close(rpc.grad, rpo.grad, what="d rpc_emb")
-    for (n, pc), (_, po) in zip(cc.named_parameters(), oc.named_parameters()):
-        assert_close(pc.grad, po.grad, what=f"d {n}")
+    assert_grads_close(cc.named_parameters(), oc.named_parameters(), RTOL)
 
 
 def test_tconv_generic_edge_features_and_no_edge_dim():
@@ -225,8 +229,7 @@ def test_tconv_generic_edge_features_and_no_edge_dim():
         yc.square().sum().backward()
         assert_close(yc, yo, what="generic conv")
         assert_close(xc.grad, xo.grad, what="generic conv dx")
-        for (n, pc), (_, po) in zip(cc.named_parameters(), oc.named_parameters()):
-            assert_close(pc.grad, po.grad, what=f"generic d {n}")
+        assert_grads_close(cc.named_parameters(), oc.named_parameters(), RTOL)
 
 
 # ------------------------------------------------------------------ batch norm, pool
@@ -305,17 +308,10 @@ def _model_parity(cfg, ng, patterns=1, cols=2, train=True, seed=0):
     loss_o.backward()
     loss_c.backward()
     assert_close(loss_c, loss_o, what="loss")
-    po = dict(oracle.named_parameters())
-    worst = 0.0
-    for n, p in model.named_parameters():
-        assert p.grad is not None, n
-        e = rel_err(p.grad, po[n].grad)
-        worst = max(worst, e)
-        assert e <= 5 * RTOL, f"grad {n}: rel err {e:.3e}"
+    assert_grads_close(model.named_parameters(), oracle.named_parameters(), RTOL, n_convs=len(model.convs))
     # running statistics moved identically
     for n, bbuf in model.named_buffers():
         assert_close(bbuf.float(), dict(oracle.named_buffers())[n].float(), what=n)
-    return worst
 
 
 def test_model_cfg1_train():
