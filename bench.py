@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- call-graph DAGs/sec (forward + backward + optimizer step) on B200, per the driver contract.
+
+  python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # reference-semantics CPU path (oracle) on host cores
+
+Workload (BASELINE.json configs[1]): Alibaba-trace-shaped synthetic batch, 256 DAGs x 200 nodes / 600 edges,
+64-dim, num_layers=3 (3 TransformerConv + 2 BN), fp32, per GPU (weak scaling for N > 1: every rank trains on
+its own 256-graph shard, ONE NCCL all-reduce of the flat gradient buffer per step).
+
+JSON line keys beyond the base contract:
+  roofline      dominant kernel of the step, algorithmic bytes / CUDA-event time inside the timed region
+  scatter_max   the BASELINE metric kernel ([E,64] -> [N,64] segment-max) timed alone, L2 flushed between launches
+  kernels       per-kernel in-step times (ms per step) for the instrumented launches
+  cpu_baseline  the oracle (torch restatement of the reference's PyG 2.4.0 ops) timed on this box's host cores
+  e2e           the reference's own loop body (pert_gnn.py:219-250) around the drop-in model: pinned host batch ->
+                .to(device) -> zero_grad -> forward -> pinball loss -> backward -> Adam.step -> float(loss)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "call-graph DAGs/sec (fwd+bwd)"
+N_ROT = 8  # distinct resident batches the timed loop rotates over
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def make_batches(cfg, rank, count):
+    from pert_gnn_kdd23_b200.data import Batch
+    from pert_gnn_kdd23_b200.synthetic import make_data_list
+
+    return [Batch.from_data_list(make_data_list(cfg, seed=1000 + cfg + 7919 * rank + 131 * r)) for r in range(count)]
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path.  torch_geometric is not installable here, so this is the
+    oracle port (oracle/model_oracle.py: op-for-op torch restatement of PyG 2.4.0 eager) on all host cores."""
+    if rank != 0:
+        return
+    from oracle.model_oracle import OracleSAGEDeterministic, torch_quantile_loss
+    from pert_gnn_kdd23_b200.synthetic import CONFIGS, model_args
+    from pert_gnn_kdd23_b200.train import model_inputs
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = args.cfg
+    torch.manual_seed(0)
+    model = OracleSAGEDeterministic(*model_args(cfg))
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+    batches = make_batches(cfg, 0, 2)
+    B = batches[0].num_graphs
+
+    def step(b):
+        opt.zero_grad()
+        g, _ = model(*model_inputs(b))
+        loss = torch_quantile_loss(b.y.float(), g.flatten(), 0.5)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for i in range(args.warmup):
+        step(batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(batches[i % 2])
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    c = CONFIGS[cfg]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "DAGs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg{cfg}: {B} DAGs x {c['nodes']} nodes/{c['edges']} edges, {c['hidden']}-dim, "
+                               f"num_layers={c['num_layers']}", "global_batch": B},
+        "cpu_baseline": {"value": val, "unit": "DAGs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full train steps (fwd+bwd+Adam) of the {B}-graph batch; torch "
+                                   "restatement of the reference's PyG 2.4.0 eager ops (PyG itself not installable)"},
+        "e2e": {"value": val, "unit": "DAGs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ CUDA arm
+def cpu_baseline(cfg, budget_s=25.0):
+    from oracle.model_oracle import OracleSAGEDeterministic, torch_quantile_loss
+    from pert_gnn_kdd23_b200.synthetic import model_args
+    from pert_gnn_kdd23_b200.train import model_inputs
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = OracleSAGEDeterministic(*model_args(cfg))
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+    b = make_batches(cfg, 0, 1)[0]
+    B = b.num_graphs
+
+    def step():
+        opt.zero_grad()
+        g, _ = model(*model_inputs(b))
+        loss = torch_quantile_loss(b.y.float(), g.flatten(), 0.5)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    step()
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 10 and (time.perf_counter() - t_start) < budget_s:
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": B / med, "unit": "DAGs/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} full train steps (fwd+bwd+Adam) of the same {B}-graph cfg{cfg} batch, median; "
+                      "oracle = torch restatement of the reference's PyG 2.4.0 eager ops"}
+
+
+def scatter_max_bench(batch_dev, H, peak_gbs, iters=60):
+    """BASELINE metric kernel: segment-max of msg[E,H] (CSR order) -> out[N,H], L2 flushed between launches."""
+    from pert_gnn_kdd23_b200 import _lib
+    from pert_gnn_kdd23_b200.index import build_index
+
+    N, E = batch_dev.x.size(0), batch_dev.edge_index.size(1)
+    gi = build_index(batch_dev.edge_index, N)
+    msg = torch.randn(E, H, device="cuda")
+    out = torch.empty(N, H, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream()
+
+    def launch():
+        _lib.call("pert_segment_reduce_fwd", msg.data_ptr(), gi.rowptr.data_ptr(), None, out.data_ptr(), N, H, 1,
+                  st.cuda_stream)
+
+    res = {}
+    for mode in ("cold", "warm"):
+        ts = []
+        for i in range(iters + 5):
+            if mode == "cold":
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            launch()
+            e1.record(st)
+            e1.synchronize()
+            if i >= 5:
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+        res[mode] = statistics.median(ts)
+    bytes_alg = 4 * E * H + 4 * (N + 1) + 4 * N * H
+    ach = bytes_alg / res["cold"] / 1e9
+    return {"kernel": "k_segreduce<max> [E,H]->[N,H]", "bound": "hbm", "achieved": ach, "peak": peak_gbs,
+            "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None, "algorithmic_bytes": bytes_alg,
+            "us_cold": res["cold"] * 1e6, "us_warm": res["warm"] * 1e6,
+            "achieved_warm": bytes_alg / res["warm"] / 1e9, "shape": {"E": E, "N": N, "H": H}}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from pert_gnn_kdd23_b200 import ops
+    from pert_gnn_kdd23_b200.model import SAGEDeterministic
+    from pert_gnn_kdd23_b200.synthetic import CONFIGS, model_args
+    from pert_gnn_kdd23_b200.train import (DataParallel, FlatParams, FusedAdam, model_inputs, torch_quantile_loss,
+                                           train_step)
+
+    assert torch.cuda.is_available(), "bench.py (CUDA arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = args.cfg
+    c = CONFIGS[cfg]
+    H = c["hidden"]
+    peak, peak_kind = _peaks()
+
+    host_batches = [b.pin_memory() for b in make_batches(cfg, rank, N_ROT)]
+    dev_batches = [b.to(dev) for b in host_batches]
+    B = host_batches[0].num_graphs
+    Nn, Ee = host_batches[0].x.size(0), host_batches[0].edge_index.size(1)
+    h2d = host_batches[0].h2d_bytes
+
+    torch.manual_seed(0)
+    model = SAGEDeterministic(*model_args(cfg)).to(dev)
+    fp = FlatParams(model)
+    opt = FusedAdam(fp, lr=3e-4)
+    dp = DataParallel(fp) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only arm: inputs resident in HBM -------------------------------------------------
+    for i in range(args.warmup):
+        train_step(model, opt, dev_batches[i % N_ROT], 0.5, dp)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.TIMERS.clear()
+    ops.TIMING["on"] = True
+    l0 = ops.LAUNCHES["n"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        loss = train_step(model, opt, dev_batches[i % N_ROT], 0.5, dp)
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ops.TIMING["on"] = False
+    launches = ops.LAUNCHES["n"] - l0
+    secs = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+    kern = ops.collect_timers()
+    if world > 1:
+        t = torch.tensor([secs], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t)
+    value = world * B * args.steps / secs
+
+    # ---- end-to-end arm: the reference's loop body with host buffers ------------------------------
+    model2 = SAGEDeterministic(*model_args(cfg)).to(dev)
+    model2.load_state_dict(model.state_dict())
+    opt2 = torch.optim.Adam(model2.parameters(), lr=3e-4)
+    if world > 1:
+        fp2 = None
+
+    def e2e_step(hb):
+        data = hb.to(dev, non_blocking=True)
+        opt2.zero_grad()
+        gp, _ = model2(*model_inputs(data))
+        l = torch_quantile_loss(data.y.float(), gp.flatten(), 0.5)
+        l.backward()
+        if world > 1:
+            for p in model2.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+                    p.grad.div_(world)
+        opt2.step()
+        return float(l)                       # D2H read of the step's result, like pert_gnn.py:248
+
+    for i in range(args.warmup):
+        e2e_step(host_batches[i % N_ROT])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(host_batches[i % N_ROT])
+    e1.record()
+    barrier()
+    secs2 = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([secs2], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs2 = float(t)
+    e2e_val = world * B * args.steps / secs2
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant instrumented kernel (bytes model: DESIGN.md section 4) -----------
+    n_convs = len(model.convs)
+    alg = {
+        "tconv_fwd": 16 * Nn * H + 12 * Ee + 4 * (Nn + 1) + 4 * Ee,
+        "tconv_bwd": (4 * Nn * H * 4 + 12 * Ee + 4 * (Nn + 1) + 8 * Ee) + (4 * Nn * H * 4 + 12 * Ee + 4 * (Nn + 1) + 8 * Ee),
+    }
+    kernels = {}
+    for name, (tot_ms, cnt) in kern.items():
+        kernels[name] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": cnt / args.steps,
+                         "us_per_launch": 1e3 * tot_ms / max(cnt, 1)}
+    roof = None
+    cand = [k for k in kernels if k in alg]
+    if cand:
+        top = max(cand, key=lambda k: kernels[k]["ms_per_step"])
+        ach = alg[top] / (kernels[top]["us_per_launch"] * 1e-6) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_kind, "algorithmic_bytes": alg[top],
+                "us_per_launch": kernels[top]["us_per_launch"],
+                "share_of_step": kernels[top]["ms_per_step"] / (1e3 * secs / args.steps)}
+    smx = scatter_max_bench(dev_batches[0], H, peak)
+    base = cpu_baseline(cfg) if (world == 1 and not args.no_cpu_baseline) else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "DAGs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg{cfg}: {B} DAGs x {c['nodes']} nodes/{c['edges']} edges per GPU, {H}-dim, "
+                               f"num_layers={c['num_layers']} ({n_convs} TransformerConv), fwd+bwd+Adam",
+                   "global_batch": world * B, "nodes_per_gpu": Nn, "edges_per_gpu": Ee,
+                   "parallelism": f"dp{world}",
+                   "l2": f"rotating {N_ROT} distinct resident batches; ~{(n_convs * 8 * Nn * H * 4) >> 20} MB of "
+                         "activations written+read per step (> 126 MB L2 for cfg2+): no explicit flush in the step "
+                         "loop; scatter_max is timed with an explicit 512 MB L2 flush"},
+        "roofline": roof, "scatter_max": smx, "kernels": kernels, "cpu_baseline": base,
+        "e2e": {"value": e2e_val, "unit": "DAGs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": 1e3 * secs2 / args.steps,
+                "path": "pert_gnn.py loop body: Batch.to(device) from pinned host slab, zero_grad, forward, pinball "
+                        "loss, backward, torch.optim.Adam.step, float(loss)"},
+        "gpu_launches": launches, "wall_s": t_wall, "clocks": clocks, "final_loss": float(loss),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cfg", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    run_b200(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

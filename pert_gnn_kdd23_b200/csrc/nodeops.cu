@@ -422,13 +422,16 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   p[i] = pi - (lr / bc1) * (mi / denom);
 }
 
+inline bool al16(const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; }
+
 }  // namespace
 
 extern "C" {
 
 int pert_embedding_fwd(const float* table, int n_rows, const int64_t* ids, int id_stride, float* out, int ld_out,
                        long long N, int H, int accumulate, int* status, void* stream) {
-  if (N < 0 || H <= 0 || H % 4 || ld_out % 4 || !table || !out || n_rows <= 0) return PERT_ERR_BADARG;
+  if (N < 0 || H <= 0 || H % 4 || ld_out % 4 || !table || !out || n_rows <= 0 || !al16(table) || !al16(out))
+    return PERT_ERR_BADARG;
   if (N == 0) return PERT_OK;
   long long total = N * (H / 4);
   k_embedding_fwd<<<pert_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(table, n_rows, ids, id_stride, out,
@@ -439,7 +442,7 @@ int pert_embedding_fwd(const float* table, int n_rows, const int64_t* ids, int i
 
 int pert_embedding_bwd(const float* dy, int ld_dy, const int64_t* ids, int id_stride, float* dtable, int n_rows,
                        long long N, int H, void* stream) {
-  if (N < 0 || H <= 0 || H % 4 || ld_dy % 4 || !dy || !dtable) return PERT_ERR_BADARG;
+  if (N < 0 || H <= 0 || H % 4 || ld_dy % 4 || !dy || !dtable || !al16(dy) || !al16(dtable)) return PERT_ERR_BADARG;
   if (N == 0) return PERT_OK;
   long long total = N * (H / 4);
   k_embedding_bwd<<<pert_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, ld_dy, ids, id_stride, dtable,
@@ -470,6 +473,7 @@ int pert_bn_fwd(const float* x, int ld_x, const float* gamma, const float* beta,
                 long long workspace_bytes, void* stream) {
   if (N < 0 || H <= 0 || H % 4 || H > 1024 || ld_x % 4 || ld_y % 4 || !x || !gamma || !beta || !mean || !rstd || !y)
     return PERT_ERR_BADARG;
+  if (!al16(x) || !al16(gamma) || !al16(beta) || !al16(mean) || !al16(rstd) || !al16(y)) return PERT_ERR_BADARG;
   if (N == 0) return PERT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (training) {
@@ -504,6 +508,8 @@ int pert_bn_bwd(const float* dy, int ld_dy, const float* y, int ld_y, const floa
     return PERT_ERR_BADARG;
   if (relu && !y) return PERT_ERR_BADARG;
   if (ld_dy % 4 || ld_x % 4 || ld_dx % 4 || (relu && ld_y % 4)) return PERT_ERR_BADARG;
+  if (!al16(dy) || !al16(y) || !al16(x) || !al16(mean) || !al16(rstd) || !al16(gamma) || !al16(dx) || !al16(sums))
+    return PERT_ERR_BADARG;
   if (N == 0) return PERT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * H, st);
@@ -527,7 +533,9 @@ int pert_bn_bwd(const float* dy, int ld_dy, const float* y, int ld_y, const floa
 int pert_pool_fwd(const float* x, int ld, const float* probs, const float* pnn, const int64_t* batch,
                   const float* w_local, const float* b_local, float* local, float* pool, long long N, long long B,
                   int H, int* status, void* stream) {
-  if (N < 0 || B < 0 || !x || !probs || !pnn || !batch || !pool || ld % 4) return PERT_ERR_BADARG;
+  if (N < 0 || B < 0 || !x || !probs || !pnn || !batch || !pool || ld % 4 || !al16(x) || !al16(w_local) ||
+      !al16(pool))
+    return PERT_ERR_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (B > 0) {
     cudaError_t e = cudaMemsetAsync(pool, 0, sizeof(float) * B * H, st);
@@ -550,7 +558,9 @@ int pert_pool_fwd(const float* x, int ld, const float* probs, const float* pnn, 
 int pert_pool_bwd(const float* dpool, const float* dlocal, const float* x, int ld, const float* probs,
                   const float* pnn, const int64_t* batch, const float* w_local, float* dx, int ld_dx,
                   float* dw_local, float* db_local, long long N, long long B, int H, void* stream) {
-  if (N < 0 || !probs || !pnn || !batch || !dx || ld % 4 || ld_dx % 4) return PERT_ERR_BADARG;
+  if (N < 0 || !probs || !pnn || !batch || !dx || ld % 4 || ld_dx % 4 || !al16(dpool) || !al16(x) ||
+      !al16(w_local) || !al16(dx))
+    return PERT_ERR_BADARG;
   if (dlocal && (!x || !w_local)) return PERT_ERR_BADARG;
   if (N == 0) return PERT_OK;
   int rc = dispatch_h(H, [&](auto lpr, auto vpl) {

@@ -14,6 +14,35 @@ from ._lib import call, ptr, stream
 # launches issued through the C-ABI (bench.py reports it as `gpu_launches`)
 LAUNCHES = {"n": 0}
 
+# optional CUDA-event timing of selected launches on the launching stream (bench.py roofline)
+TIMING = {"on": False}
+TIMERS = {}
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if TIMING["on"]:
+            self.e1.record()
+            TIMERS.setdefault(self.name, []).append((self.e0, self.e1))
+
+
+def collect_timers():
+    """name -> (total ms, count); call after a device synchronize."""
+    out = {}
+    for name, evs in TIMERS.items():
+        out[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+    return out
+
 
 def _need_cuda(*ts):
     for t in ts:
@@ -39,8 +68,9 @@ def gemm_nt_raw(A, B, bias, out, relu=False, accumulate=False):
     _, lda, a_cb, a_cbs, M, K = _blocked(A)
     _, ldc, c_cb, c_cbs, M2, Nc = _blocked(out)
     assert M == M2 and B.size(0) == Nc and B.size(1) == K, (A.shape, B.shape, out.shape)
-    call("pert_gemm_nt", ptr(A), lda, a_cb, a_cbs, ptr(B), B.stride(0), ptr(bias), ptr(out), ldc, c_cb, c_cbs,
-         M, Nc, K, int(relu), int(accumulate), stream())
+    with _timed("gemm_nt" if M >= 4096 else "gemm_nt_small"):
+        call("pert_gemm_nt", ptr(A), lda, a_cb, a_cbs, ptr(B), B.stride(0), ptr(bias), ptr(out), ldc, c_cb, c_cbs,
+             M, Nc, K, int(relu), int(accumulate), stream())
     LAUNCHES["n"] += 1
     return out
 
@@ -50,8 +80,9 @@ def gemm_tn_raw(A, B, out):
     _, lda, a_cb, a_cbs, R, Mc = _blocked(A)
     _, ldb, b_cb, b_cbs, R2, Nc = _blocked(B)
     assert R == R2 and out.shape == (Mc, Nc) and out.is_contiguous()
-    call("pert_gemm_tn", ptr(A), lda, a_cb, a_cbs, ptr(B), ldb, b_cb, b_cbs, ptr(out), out.stride(0), R, Mc, Nc,
-         stream())
+    with _timed("gemm_tn" if R >= 4096 else "gemm_tn_small"):
+        call("pert_gemm_tn", ptr(A), lda, a_cb, a_cbs, ptr(B), ldb, b_cb, b_cbs, ptr(out), out.stride(0), R, Mc,
+             Nc, stream())
     LAUNCHES["n"] += 1
     return out
 
@@ -212,9 +243,10 @@ class _TConvFn(torch.autograd.Function):
         alpha = torch.empty(max(index.E, 1), device=planes.device, dtype=torch.float32)
         q, k, v = planes[0], planes[1], planes[2]
         s = planes[3] if P_ == 4 else None
-        call("pert_tconv_fwd", ptr(q), ptr(k), ptr(v), ptr(s), H, ptr(index.rowptr), ptr(index.csr_src),
-             ptr(index.csr_if) if has_e else None, ptr(index.csr_rpc) if has_e else None,
-             ptr(t_if), ptr(t_rpc), ptr(out), H, ptr(alpha), N, H, stream())
+        with _timed("tconv_fwd"):
+            call("pert_tconv_fwd", ptr(q), ptr(k), ptr(v), ptr(s), H, ptr(index.rowptr), ptr(index.csr_src),
+                 ptr(index.csr_if) if has_e else None, ptr(index.csr_rpc) if has_e else None,
+                 ptr(t_if), ptr(t_rpc), ptr(out), H, ptr(alpha), N, H, stream())
         LAUNCHES["n"] += 1
         ctx.index = index
         ctx.has_e = has_e
@@ -233,11 +265,13 @@ class _TConvFn(torch.autograd.Function):
         if ctx.has_e:
             dt_if = torch.zeros_like(t_if)
             dt_rpc = torch.zeros_like(t_rpc)
-        call("pert_tconv_bwd", ptr(g), g.stride(0), ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), H,
-             ptr(index.rowptr), ptr(index.csr_src), ptr(index.csr_if) if ctx.has_e else None,
-             ptr(index.csr_rpc) if ctx.has_e else None, ptr(index.colptr), ptr(index.csc_pos), ptr(index.csc_dst),
-             ptr(t_if), ptr(t_rpc), ptr(alpha), ptr(dplanes[0]), ptr(dplanes[1]), ptr(dplanes[2]), H, ptr(dsp),
-             ptr(dt_if), ptr(dt_rpc), t_rpc.size(0) if ctx.has_e else 0, N, H, stream())
+        with _timed("tconv_bwd"):
+            call("pert_tconv_bwd", ptr(g), g.stride(0), ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), H,
+                 ptr(index.rowptr), ptr(index.csr_src), ptr(index.csr_if) if ctx.has_e else None,
+                 ptr(index.csr_rpc) if ctx.has_e else None, ptr(index.colptr), ptr(index.csc_pos),
+                 ptr(index.csc_dst), ptr(t_if), ptr(t_rpc), ptr(alpha), ptr(dplanes[0]), ptr(dplanes[1]),
+                 ptr(dplanes[2]), H, ptr(dsp), ptr(dt_if), ptr(dt_rpc), t_rpc.size(0) if ctx.has_e else 0, N, H,
+                 stream())
         LAUNCHES["n"] += 2
         if P_ == 4:
             dplanes[3].copy_(g)

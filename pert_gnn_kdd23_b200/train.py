@@ -1,0 +1,116 @@
+"""Train / eval step mirroring reference pert_gnn.py:191-193 (pinball loss), :213-251 (train), :254-294 (test),
+plus the data-parallel wrapper the reference lacks (shard independent graphs over GPUs, ONE
+flat-buffer gradient all-reduce per step).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+
+
+def torch_quantile_loss(y_test, y_hat, tau):
+    """reference pert_gnn.py:191-193."""
+    e = y_test - y_hat
+    return torch.mean(torch.maximum(tau * e, (tau - 1) * e))
+
+
+def model_inputs(data):
+    """Argument tuple of SAGEDeterministic.forward from a Batch (pert_gnn.py:233-243); the per-node pattern
+    probability ``rt_probs`` is precomputed at collation instead of rebuilt on the host every step (:220-230)."""
+    probs = data.rt_probs if "rt_probs" in data else data.pattern_probs
+    return (data.x, data.cat_X, data.edge_index, data.edge_attr, data.pattern_num_nodes, probs, data.entry_id,
+            data.batch)
+
+
+class FlatParams:
+    """All parameters (and their gradients) of a module as views into two flat fp32 buffers, so that the
+    gradient all-reduce and the Adam update are ONE collective and ONE kernel (payload <= 4.8 MB, latency-bound)."""
+
+    def __init__(self, module):
+        params = [p for p in module.parameters() if p.requires_grad]
+        al = lambda k: (k + 63) // 64 * 64          # every parameter starts on a 256-byte boundary (float4 / TMA)
+        n = sum(al(p.numel()) for p in params)
+        dev = params[0].device
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += al(k)
+        self.params = params
+        self.numel = n
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+class FusedAdam:
+    """torch.optim.Adam(params, lr) semantics (reference pert_gnn.py:343) in one kernel over FlatParams."""
+
+    def __init__(self, flat: FlatParams, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.fp = flat
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(flat.flat)
+        self.v = torch.zeros_like(flat.flat)
+        self.t = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.fp.zero_grad()
+
+    def step(self, grad_scale=1.0):
+        self.t += 1
+        _lib.call("pert_adam_step", _lib.ptr(self.fp.flat), _lib.ptr(self.fp.grad), _lib.ptr(self.m),
+                  _lib.ptr(self.v), self.fp.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t,
+                  float(grad_scale), _lib.stream())
+        ops.LAUNCHES["n"] += 1
+
+
+class DataParallel:
+    """One process per GPU; each rank owns a shard of the graphs; gradients are averaged with a single
+    all-reduce of the flat gradient buffer (NCCL over NVLink on the box, gloo in the CPU tests).
+    BatchNorm statistics stay per-replica (like DDP); parity claims are per shard."""
+
+    def __init__(self, flat: FlatParams, group=None):
+        self.fp = flat
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def all_reduce_grads(self):
+        if self.world > 1:
+            dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.group)
+        return 1.0 / self.world
+
+
+def train_step(model, optimizer, data, tau=0.5, dp: DataParallel | None = None):
+    """One iteration of the loop body of reference pert_gnn.py:231-247 on a device-resident Batch.
+    Returns the (device) loss tensor; no host sync."""
+    optimizer.zero_grad()
+    global_pred, _ = model(*model_inputs(data))
+    loss = torch_quantile_loss(data.y.float(), global_pred.flatten(), tau)
+    loss.backward()
+    if isinstance(optimizer, FusedAdam):
+        scale = dp.all_reduce_grads() if dp is not None else 1.0
+        optimizer.step(grad_scale=scale)
+    else:
+        if dp is not None:
+            s = dp.all_reduce_grads()
+            if s != 1.0:
+                dp.fp.grad.mul_(s)
+        optimizer.step()
+    return loss
+
+
+@torch.no_grad()
+def eval_step(model, data, tau=0.5):
+    """Loop body of reference pert_gnn.py:260-289: returns device sums (mae, mape, quantile loss * B)."""
+    global_pred, _ = model(*model_inputs(data))
+    pred = global_pred.flatten()
+    mae = (pred - data.y).abs().sum()
+    mape = ((pred - data.y).abs() / data.y).sum()
+    q = torch_quantile_loss(data.y.float(), pred, tau) * data.y.shape[0]
+    return mae, mape, q
