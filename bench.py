@@ -233,8 +233,10 @@ def run_b200(args, rank, world, local_rank):
     from pert_gnn_kdd23_b200 import ops
     from pert_gnn_kdd23_b200.model import SAGEDeterministic
     from pert_gnn_kdd23_b200.synthetic import CONFIGS, model_args
-    from pert_gnn_kdd23_b200.train import (DataParallel, FlatParams, FusedAdam, model_inputs, torch_quantile_loss,
-                                           train_step)
+    from pert_gnn_kdd23_b200.train import (DataParallel, FlatParams, FusedAdam, fused_train_step, model_inputs,
+                                           torch_quantile_loss)
+
+    train_step = fused_train_step
 
     assert torch.cuda.is_available(), "bench.py (CUDA arm) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
@@ -329,6 +331,27 @@ def run_b200(args, rank, world, local_rank):
         secs2 = float(t)
     e2e_val = world * B * args.steps / secs2
 
+    # ---- end-to-end through the fused public API: pinned host batch -> device -> fused_train_step -> loss.item()
+    def e2e_fused_step(hb):
+        data = hb.to(dev, non_blocking=True)
+        return float(train_step(model, opt, data, 0.5, dp))
+
+    for i in range(args.warmup):
+        e2e_fused_step(host_batches[i % N_ROT])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        e2e_fused_step(host_batches[i % N_ROT])
+    e1.record()
+    barrier()
+    secs3 = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([secs3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs3 = float(t)
+    e2e_fused_val = world * B * args.steps / secs3
+
     if rank != 0:
         return
     # ---- roofline of the dominant instrumented kernel (bytes model: DESIGN.md section 4) -----------
@@ -368,6 +391,10 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_step": 1e3 * secs2 / args.steps,
                 "path": "pert_gnn.py loop body: Batch.to(device) from pinned host slab, zero_grad, forward, pinball "
                         "loss, backward, torch.optim.Adam.step, float(loss)"},
+        "e2e_fused": {"value": e2e_fused_val, "unit": "DAGs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                      "ms_per_step": 1e3 * secs3 / args.steps,
+                      "path": "Batch.to(device) from pinned host slab + train.fused_train_step (engine fwd, pinball "
+                              "kernel, engine bwd, fused Adam) + float(loss)"},
         "gpu_launches": launches, "wall_s": t_wall, "clocks": clocks, "final_loss": float(loss),
     }
     print(json.dumps(line), flush=True)

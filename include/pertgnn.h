@@ -144,6 +144,56 @@ int pert_pinball_loss(const int64_t* y, const float* yhat, float tau, long long 
 int pert_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, long long step, float grad_scale, void* stream);
 
+/* ---- whole-model step engine --------------------------------------------------------------------------
+ * SAGEDeterministic.forward (model.py:76-114) and its backward as one call each: the same kernels as above,
+ * issued back-to-back from C++ (no interpreter between launches).  Parameters live in ONE flat fp32 buffer in
+ * the reference's own tensor shapes; PertModelDesc gives the offset (in floats, each 16-byte aligned) of every
+ * tensor, named after the reference's state_dict keys.  Gradients go to a second flat buffer with the same
+ * offsets and are ACCUMULATED (+=), like autograd.  The workspace holds packed operands, saved activations and
+ * temporaries; its first pert_model_packed_bytes() bytes must be zero when first used (padding columns). */
+#define PERT_MAX_CONVS 8
+#define PERT_MAX_CAT 4
+typedef struct PertModelDesc {
+  int32_t F;        /* in_channels of the model (raw node features, 9)             model.py:13  */
+  int32_t H;        /* hidden_channels                                              model.py:18  */
+  int32_t n_convs;  /* max(2, num_layers)                                           model.py:24-52 */
+  int32_t n_cat;    /* len(cat_dims)                                                model.py:57-60 */
+  int32_t cat_rows[PERT_MAX_CAT];
+  int32_t n_entry, n_if, n_rpc; /* rows of entry_embeds / interface_embeds / rpctype_embeds  model.py:63-67 */
+  int32_t k0;       /* padded input width of conv 0: round_up(F + H, 8)                          */
+  float bn_eps, bn_momentum;
+  long long off_cat[PERT_MAX_CAT];                 /* cat_embedding.{i}.weight [rows,H] */
+  long long off_entry, off_if, off_rpc;            /* *_embeds.weight                   */
+  long long off_wq[PERT_MAX_CONVS], off_bq[PERT_MAX_CONVS]; /* convs.{l}.lin_query.{weight [H,Din],bias} */
+  long long off_wk[PERT_MAX_CONVS], off_bk[PERT_MAX_CONVS]; /* lin_key   */
+  long long off_wv[PERT_MAX_CONVS], off_bv[PERT_MAX_CONVS]; /* lin_value */
+  long long off_ws[PERT_MAX_CONVS], off_bs[PERT_MAX_CONVS]; /* lin_skip  */
+  long long off_we[PERT_MAX_CONVS];                         /* lin_edge.weight [H,2H] */
+  long long off_bn_g[PERT_MAX_CONVS], off_bn_b[PERT_MAX_CONVS]; /* bns.{l}.weight / bias */
+  long long off_local_w, off_local_b;              /* local_linear   [1,H],[1]  */
+  long long off_g1_w, off_g1_b;                    /* global_linear1 [H,2H],[H] */
+  long long off_g2_w, off_g2_b;                    /* global_linear2 [1,H],[1]  */
+} PertModelDesc;
+
+long long pert_model_workspace_bytes(const PertModelDesc* desc, long long N, long long E, long long B);
+long long pert_model_packed_bytes(const PertModelDesc* desc);
+/* bn_running: [n_convs-1][2][H] (running_mean | running_var), bn_nbt: [n_convs-1] int64 (either may be NULL in
+ * training mode); index arrays from pert_build_index (built with edge_attr); probs/pnn [N] fp32.
+ * Outputs: global_pred [B], local_pred [N] (NULL to skip). */
+int pert_model_forward(const PertModelDesc* desc, const float* params, float* bn_running, long long* bn_nbt,
+                       const float* x, const int64_t* cat_X, const int64_t* entry_id, const float* probs,
+                       const float* pnn, const int64_t* batch, long long N, long long E, long long B,
+                       const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, void* workspace,
+                       long long workspace_bytes, int training, float* global_pred, float* local_pred, int* status,
+                       void* stream);
+/* Must follow pert_model_forward on the same workspace.  d_global [B], d_local [N] or NULL. */
+int pert_model_backward(const PertModelDesc* desc, const float* params, float* grads, const int64_t* cat_X,
+                        const int64_t* entry_id, const float* probs, const float* pnn, const int64_t* batch,
+                        long long N, long long E, long long B, const int* rowptr, const int* csr_src,
+                        const int* csr_if, const int* csr_rpc, const int* colptr, const int* csc_pos,
+                        const int* csc_dst, void* workspace, long long workspace_bytes, int training,
+                        const float* d_global, const float* d_local, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,11 @@ SIGNATURES = {
     "pert_relu_bwd": (I, [P, P, LL, P]),
     "pert_pinball_loss": (I, [P, P, F, LL, F, P, P, P]),
     "pert_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, LL, F, P]),
+    # whole-model engine (first argument: const PertModelDesc*, see engine.py)
+    "pert_model_workspace_bytes": (LL, [P, LL, LL, LL]),
+    "pert_model_packed_bytes": (LL, [P]),
+    "pert_model_forward": (I, [P, P, P, P, P, P, P, P, P, P, LL, LL, LL, P, P, P, P, P, LL, I, P, P, P, P]),
+    "pert_model_backward": (I, [P, P, P, P, P, P, P, P, LL, LL, LL, P, P, P, P, P, P, P, P, LL, I, P, P, P]),
 }
 
 _lib = None

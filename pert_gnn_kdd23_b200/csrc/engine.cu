@@ -1,0 +1,499 @@
+// Whole-model step engine: SAGEDeterministic forward / backward (reference model.py:76-114 and its autograd
+// backward, driven by pert_gnn.py:233-247) as ONE C call each.  The Python-orchestrated path issues ~130 launches
+// per step through ctypes + autograd (~4.4 ms of host time at cfg2, 2x the GPU time); here the same kernels are
+// issued back-to-back from C++ so the GPU, not the interpreter, bounds the step.
+//
+// Parameters stay in the reference's layout (one flat fp32 buffer + offsets, PertModelDesc); a small pack kernel
+// per layer builds the fused operands each step (W4 = [Wq;Wk;Wv;Ws] with conv-0 columns permuted/padded to the
+// [cat_embeds | x | pad] input layout, W4^T for the data gradient, the two halves of lin_edge and their transposes)
+// and an unpack kernel scatters the packed gradients back (+=) into the flat gradient buffer.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace {
+
+// ------------------------------------------------------------------ grouped small GEMM (heads, edge tables)
+struct SmallGemm {
+  const float* A;     // A(m,k) = A[m*sam + k*sak]
+  const float* B;     // B(k,n) = B[k*sbk + n*sbn];  nullptr => all ones
+  const float* bias;  // [N] or null
+  const float* mask;  // same shape/ld as C: result *= (mask > 0)   (ReLU backward) or null
+  float* C;           // C[m*ldc + n]
+  int M, N, K;
+  int sam, sak, sbk, sbn, ldc;
+  int relu, accumulate, ksplit;
+};
+#define SG_MAX 12
+struct SmallGemmBatch {
+  SmallGemm p[SG_MAX];
+  int count;
+};
+constexpr int SG_BM = 32, SG_BN = 64, SG_BK = 16;
+
+__global__ void __launch_bounds__(256) k_small_gemm(SmallGemmBatch batch) {
+  const SmallGemm& g = batch.p[blockIdx.y];
+  const int tiles_m = (g.M + SG_BM - 1) / SG_BM, tiles_n = (g.N + SG_BN - 1) / SG_BN;
+  const int ks = g.ksplit > 0 ? g.ksplit : 1;
+  int t = blockIdx.x;
+  if (t >= tiles_m * tiles_n * ks) return;
+  const int kpart = t % ks;
+  t /= ks;
+  const int m0 = (t / tiles_n) * SG_BM, n0 = (t % tiles_n) * SG_BN;
+  const int klen = (g.K + ks - 1) / ks;
+  const int kbeg = kpart * klen, kend = min(g.K, kbeg + klen);
+  __shared__ float As[SG_BK][SG_BM + 1];
+  __shared__ float Bs[SG_BK][SG_BN + 1];
+  const int tid = threadIdx.x;
+  const int ty = tid / 16, tx = tid % 16;  // 16x16 threads: 2 rows x 4 cols each
+  float acc[2][4] = {};
+  for (int k0 = kbeg; k0 < kend; k0 += SG_BK) {
+    for (int x = tid; x < SG_BM * SG_BK; x += 256) {
+      // pick the index that is contiguous in memory as the fast thread index
+      int mm, kk;
+      if (g.sak == 1) { kk = x % SG_BK; mm = x / SG_BK; } else { mm = x % SG_BM; kk = x / SG_BM; }
+      int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < g.M && k < kend) ? __ldg(g.A + (size_t)m * g.sam + (size_t)k * g.sak) : 0.f;
+    }
+    for (int x = tid; x < SG_BN * SG_BK; x += 256) {
+      int nn, kk;
+      if (g.sbk == 1) { kk = x % SG_BK; nn = x / SG_BK; } else { nn = x % SG_BN; kk = x / SG_BN; }
+      int n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if (n < g.N && k < kend) v = g.B ? __ldg(g.B + (size_t)k * g.sbk + (size_t)n * g.sbn) : 1.f;
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float b = Bs[kk][tx * 4 + j];
+        acc[0][j] = fmaf(a0, b, acc[0][j]);
+        acc[1][j] = fmaf(a1, b, acc[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int m = m0 + ty * 2 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias && kpart == 0) v += __ldg(g.bias + n);
+      float* c = g.C + (size_t)m * g.ldc + n;
+      if (ks > 1) {
+        atomicAdd(c, v);  // split-K: C pre-zeroed / accumulating, no relu/mask
+      } else {
+        if (g.relu) v = fmaxf(v, 0.f);
+        if (g.mask && !(g.mask[(size_t)m * g.ldc + n] > 0.f)) v = 0.f;
+        *c = g.accumulate ? (*c + v) : v;
+      }
+    }
+  }
+}
+
+int launch_small(const SmallGemmBatch& b, cudaStream_t st) {
+  int maxt = 1;
+  for (int i = 0; i < b.count; ++i) {
+    const SmallGemm& g = b.p[i];
+    int ks = g.ksplit > 0 ? g.ksplit : 1;
+    int t = ((g.M + SG_BM - 1) / SG_BM) * ((g.N + SG_BN - 1) / SG_BN) * ks;
+    if (t > maxt) maxt = t;
+  }
+  k_small_gemm<<<dim3(maxt, b.count), 256, 0, st>>>(b);
+  return 0;
+}
+SmallGemm sg(const float* A, int sam, int sak, const float* B, int sbk, int sbn, const float* bias, float* C,
+             int ldc, int M, int N, int K, int relu = 0, int accumulate = 0, int ksplit = 1,
+             const float* mask = nullptr) {
+  SmallGemm g;
+  g.A = A; g.B = B; g.bias = bias; g.mask = mask; g.C = C; g.M = M; g.N = N; g.K = K;
+  g.sam = sam; g.sak = sak; g.sbk = sbk; g.sbn = sbn; g.ldc = ldc;
+  g.relu = relu; g.accumulate = accumulate; g.ksplit = ksplit;
+  return g;
+}
+
+// ------------------------------------------------------------------ parameter pack / gradient unpack
+struct Seg {
+  long long src;  // offset (floats) into the flat parameter (or gradient) buffer
+  long long dst;  // offset (floats) into the packed workspace
+  int rows, cols, src_ld, dst_ld;
+  int transpose;  // dst[c*dst_ld + r] = src[r*src_ld + c]
+};
+#define SEG_MAX 40
+struct SegList {
+  Seg s[SEG_MAX];
+  int count;
+};
+__global__ void k_pack(const float* __restrict__ params, float* __restrict__ packed, SegList L) {
+  const Seg& s = L.s[blockIdx.y];
+  int n = s.rows * s.cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int r = i / s.cols, c = i - r * s.cols;
+    float v = params[s.src + (size_t)r * s.src_ld + c];
+    if (s.transpose) packed[s.dst + (size_t)c * s.dst_ld + r] = v;
+    else packed[s.dst + (size_t)r * s.dst_ld + c] = v;
+  }
+}
+// grads[src...] += packed_grad[dst...]   (non-transposed segments only)
+__global__ void k_unpack(float* __restrict__ grads, const float* __restrict__ packed, SegList L) {
+  const Seg& s = L.s[blockIdx.y];
+  if (s.transpose) return;
+  int n = s.rows * s.cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int r = i / s.cols, c = i - r * s.cols;
+    grads[s.src + (size_t)r * s.src_ld + c] += packed[s.dst + (size_t)r * s.dst_ld + c];
+  }
+}
+
+// z[b, 0:H] = pool[b]; z[b, H:2H] = entry_table[entry_id[b]]
+__global__ void k_head_concat(const float* __restrict__ pool, const float* __restrict__ table, int n_rows,
+                              const int64_t* __restrict__ ids, float* __restrict__ z, int B, int H, int* status) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 2 * H) return;
+  int b = i / (2 * H), c = i - b * 2 * H;
+  float v;
+  if (c < H) v = pool[(size_t)b * H + c];
+  else {
+    int64_t r = ids[b];
+    if (r < 0 || r >= n_rows) {
+      if (status) atomicExch(status, PERT_ERR_RANGE);
+      r = 0;
+    }
+    v = table[(size_t)r * H + (c - H)];
+  }
+  z[i] = v;
+}
+
+inline long long al64(long long n) { return (n + 63) / 64 * 64; }
+
+struct Ws {
+  // packed parameters (zero-initialised region: pads must stay 0)
+  float *w4[PERT_MAX_CONVS], *b4[PERT_MAX_CONVS], *w4t[PERT_MAX_CONVS];
+  float *weA[PERT_MAX_CONVS], *weB[PERT_MAX_CONVS], *weAt[PERT_MAX_CONVS], *weBt[PERT_MAX_CONVS];
+  // packed gradients + table gradients (zeroed at the start of every backward, one memset)
+  float* gzero_begin;
+  float *dw4[PERT_MAX_CONVS], *db4[PERT_MAX_CONVS], *dweA[PERT_MAX_CONVS], *dweB[PERT_MAX_CONVS];
+  float *dt_if[PERT_MAX_CONVS], *dt_rpc[PERT_MAX_CONVS];
+  float* gzero_end;
+  // forward state
+  float *t_if[PERT_MAX_CONVS], *t_rpc[PERT_MAX_CONVS];
+  float *x[PERT_MAX_CONVS], *planes[PERT_MAX_CONVS], *out[PERT_MAX_CONVS], *alpha[PERT_MAX_CONVS];
+  float* bn_stats[PERT_MAX_CONVS];
+  float *bn_part, *pool, *z, *h1;
+  // backward temporaries
+  float *dplanes, *dx, *dsp, *sums, *dpool, *dzent, *dh1;
+  long long total;  // floats
+  long long packed_floats;
+};
+
+int k_of(const PertModelDesc* d, int l) { return l == 0 ? d->k0 : d->H; }
+
+Ws carve(const PertModelDesc* d, long long N, long long E, long long B, float* base) {
+  Ws w;
+  memset(&w, 0, sizeof(w));
+  long long off = 0;
+  auto take = [&](long long n) {
+    float* p = base ? base + off : nullptr;
+    off += al64(n > 0 ? n : 1);
+    return p;
+  };
+  const int H = d->H, L = d->n_convs;
+  for (int l = 0; l < L; ++l) {
+    int K = k_of(d, l);
+    w.w4[l] = take(4LL * H * K);
+    w.b4[l] = take(4LL * H);
+    w.w4t[l] = take(4LL * H * K);
+    w.weA[l] = take((long long)H * H);
+    w.weB[l] = take((long long)H * H);
+    w.weAt[l] = take((long long)H * H);
+    w.weBt[l] = take((long long)H * H);
+  }
+  w.packed_floats = off;
+  w.gzero_begin = base ? base + off : nullptr;
+  for (int l = 0; l < L; ++l) {
+    int K = k_of(d, l);
+    w.dw4[l] = take(4LL * H * K);
+    w.db4[l] = take(4LL * H);
+    w.dweA[l] = take((long long)H * H);
+    w.dweB[l] = take((long long)H * H);
+    w.dt_if[l] = take((long long)d->n_if * H);
+    w.dt_rpc[l] = take((long long)d->n_rpc * H);
+  }
+  w.gzero_end = base ? base + off : nullptr;
+  for (int l = 0; l < L; ++l) {
+    int K = k_of(d, l);
+    w.t_if[l] = take((long long)d->n_if * H);
+    w.t_rpc[l] = take((long long)d->n_rpc * H);
+    if (l == 0) w.x[l] = take(N * K);
+    w.planes[l] = take(4LL * N * H);
+    w.out[l] = take(N * H);
+    if (l + 1 < L) w.x[l + 1] = take(N * H);
+    w.alpha[l] = take(E);
+    w.bn_stats[l] = take(2LL * H);
+  }
+  w.bn_part = take(pert_bn_workspace_bytes(N, H) / 4 + 16);
+  w.pool = take(B * H);
+  w.z = take(B * 2 * H);
+  w.h1 = take(B * H);
+  w.dplanes = take(4LL * N * H);
+  int kmax = d->k0 > H ? d->k0 : H;
+  w.dx = take(N * kmax);
+  w.dsp = take(E);
+  w.sums = take(2LL * H);
+  w.dpool = take(B * H);
+  w.dzent = take(B * H);
+  w.dh1 = take(B * H);
+  w.total = off;
+  return w;
+}
+
+// segment list of conv layer l: weights -> W4 / W4^T (conv 0: columns permuted to [emb | x | pad]), biases,
+// lin_edge halves and their transposes
+SegList layer_segs(const PertModelDesc* d, const Ws& w, float* base, int l) {
+  SegList S;
+  S.count = 0;
+  const int H = d->H, F = d->F, K = k_of(d, l);
+  const int Din = (l == 0) ? F + H : H;
+  auto add = [&](long long src, float* dst, int rows, int cols, int src_ld, int dst_ld, int tr) {
+    Seg& s = S.s[S.count++];
+    s.src = src; s.dst = dst - base; s.rows = rows; s.cols = cols; s.src_ld = src_ld; s.dst_ld = dst_ld;
+    s.transpose = tr;
+  };
+  const long long* wq[4] = {&d->off_wq[l], &d->off_wk[l], &d->off_wv[l], &d->off_ws[l]};
+  const long long* bq[4] = {&d->off_bq[l], &d->off_bk[l], &d->off_bv[l], &d->off_bs[l]};
+  for (int p = 0; p < 4; ++p) {
+    float* dstw = w.w4[l] + (size_t)p * H * K;  // rows p*H..
+    float* dstt = w.w4t[l] + (size_t)p * H;     // W4^T [K, 4H]: column block p
+    if (l == 0) {
+      // reference input order [x(F) | emb(H)] -> internal [emb(H) | x(F) | pad]
+      add(*wq[p] + F, dstw, H, H, Din, K, 0);          // emb columns -> cols 0..H
+      add(*wq[p], dstw + H, H, F, Din, K, 0);          // x columns   -> cols H..H+F
+      add(*wq[p] + F, dstt, H, H, Din, 4 * H, 1);
+      add(*wq[p], dstt + (size_t)H * 4 * H, H, F, Din, 4 * H, 1);
+    } else {
+      add(*wq[p], dstw, H, H, Din, K, 0);
+      add(*wq[p], dstt, H, H, Din, 4 * H, 1);
+    }
+    add(*bq[p], w.b4[l] + (size_t)p * H, 1, H, H, H, 0);
+  }
+  add(d->off_we[l], w.weA[l], H, H, 2 * H, H, 0);
+  add(d->off_we[l] + H, w.weB[l], H, H, 2 * H, H, 0);
+  add(d->off_we[l], w.weAt[l], H, H, 2 * H, H, 1);
+  add(d->off_we[l] + H, w.weBt[l], H, H, 2 * H, H, 1);
+  return S;
+}
+// same list but pointing at the packed-gradient buffers (for k_unpack)
+SegList layer_grad_segs(const PertModelDesc* d, const Ws& w, float* base, int l) {
+  SegList S = layer_segs(d, w, base, l);
+  // remap dst from parameter pack to gradient pack (same relative layout inside each buffer)
+  for (int i = 0; i < S.count; ++i) {
+    Seg& s = S.s[i];
+    if (s.transpose) continue;
+    float* p = base + s.dst;
+    const int H = d->H, K = k_of(d, l);
+    if (p >= w.w4[l] && p < w.w4[l] + 4LL * H * K) s.dst = (w.dw4[l] + (p - w.w4[l])) - base;
+    else if (p >= w.b4[l] && p < w.b4[l] + 4LL * H) s.dst = (w.db4[l] + (p - w.b4[l])) - base;
+    else if (p == w.weA[l]) s.dst = w.dweA[l] - base;
+    else if (p == w.weB[l]) s.dst = w.dweB[l] - base;
+  }
+  return S;
+}
+
+int check_desc(const PertModelDesc* d) {
+  if (!d) return PERT_ERR_BADARG;
+  if (d->n_convs < 2 || d->n_convs > PERT_MAX_CONVS || d->n_cat < 1 || d->n_cat > PERT_MAX_CAT) return PERT_ERR_BADARG;
+  if (d->H <= 0 || d->F <= 0 || d->k0 < d->F + d->H || d->k0 % 4) return PERT_ERR_BADARG;
+  if (!pert_tconv_supported_width(d->H)) return PERT_ERR_UNSUPPORTED;
+  return PERT_OK;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+long long pert_model_workspace_bytes(const PertModelDesc* d, long long N, long long E, long long B) {
+  if (check_desc(d) || N < 0 || E < 0 || B < 0) return PERT_ERR_BADARG;
+  Ws w = carve(d, N, E, B, nullptr);
+  return w.total * 4;
+}
+long long pert_model_packed_bytes(const PertModelDesc* d) {
+  if (check_desc(d)) return PERT_ERR_BADARG;
+  Ws w = carve(d, 0, 0, 0, nullptr);
+  return w.packed_floats * 4;
+}
+
+int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_running, long long* bn_nbt,
+                       const float* x, const int64_t* cat_X, const int64_t* entry_id, const float* probs,
+                       const float* pnn, const int64_t* batch, long long N, long long E, long long B,
+                       const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, void* workspace,
+                       long long workspace_bytes, int training, float* global_pred, float* local_pred, int* status,
+                       void* stream) {
+  TRY(check_desc(d));
+  if (!params || !x || !cat_X || !entry_id || !probs || !pnn || !batch || !rowptr || !workspace || !global_pred)
+    return PERT_ERR_BADARG;
+  if (E > 0 && (!csr_src || !csr_if || !csr_rpc)) return PERT_ERR_BADARG;
+  float* base = (float*)workspace;
+  Ws w = carve(d, N, E, B, base);
+  if (workspace_bytes < w.total * 4) return PERT_ERR_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = d->H, L = d->n_convs;
+  // 1. pack parameters (one launch per layer) and build the edge tables of all layers (one grouped launch each <=6)
+  for (int l = 0; l < L; ++l) {
+    SegList S = layer_segs(d, w, base, l);
+    k_pack<<<dim3(8, S.count), 256, 0, st>>>(params, base, S);
+  }
+  {
+    SmallGemmBatch gb;
+    gb.count = 0;
+    for (int l = 0; l < L; ++l) {
+      // T_if = if_emb . WeA^T ;  T_rpc = rpc_emb . WeB^T      (B(k,n) = WeA[n,k])
+      gb.p[gb.count++] = sg(params + d->off_if, H, 1, w.weA[l], 1, H, nullptr, w.t_if[l], H, d->n_if, H, H);
+      gb.p[gb.count++] = sg(params + d->off_rpc, H, 1, w.weB[l], 1, H, nullptr, w.t_rpc[l], H, d->n_rpc, H, H);
+      if (gb.count + 2 > SG_MAX || l == L - 1) {
+        launch_small(gb, st);
+        gb.count = 0;
+      }
+    }
+  }
+  // 2. prologue: X0 = [sum_i cat_emb_i[cat_X[:,i]] | x | 0]
+  for (int i = 0; i < d->n_cat; ++i)
+    TRY(pert_embedding_fwd(params + d->off_cat[i], d->cat_rows[i], cat_X + i, d->n_cat, w.x[0], d->k0, N, H, i > 0,
+                           status, st));
+  TRY(pert_copy_cols(x, d->F, w.x[0], d->k0, H, N, st));
+  // 3. conv stack
+  for (int l = 0; l < L; ++l) {
+    const int K = k_of(d, l);
+    TRY(pert_gemm_nt(w.x[l], K, 0, 0, w.w4[l], K, w.b4[l], w.planes[l], H, H, N * (long long)H, N, 4 * H, K, 0, 0, st));
+    float* pl = w.planes[l];
+    TRY(pert_tconv_fwd(pl, pl + N * H, pl + 2 * N * H, pl + 3 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, w.t_if[l],
+                       w.t_rpc[l], w.out[l], H, w.alpha[l], N, H, st));
+    if (l + 1 < L) {
+      float* rm = bn_running ? bn_running + (size_t)l * 2 * H : nullptr;
+      float* rv = rm ? rm + H : nullptr;
+      TRY(pert_bn_fwd(w.out[l], H, params + d->off_bn_g[l], params + d->off_bn_b[l], rm, rv,
+                      (training && bn_nbt) ? bn_nbt + l : nullptr, d->bn_eps, d->bn_momentum, training, 1,
+                      w.bn_stats[l], w.bn_stats[l] + H, w.x[l + 1], H, N, H, w.bn_part,
+                      pert_bn_workspace_bytes(N, H), st));
+    }
+  }
+  // 4. local head + weighted add-pool, global head
+  TRY(pert_pool_fwd(w.out[L - 1], H, probs, pnn, batch, params + d->off_local_w, params + d->off_local_b, local_pred,
+                    w.pool, N, B, H, status, st));
+  if (B > 0) {
+    k_head_concat<<<pert_cdiv(B * 2 * H, 256), 256, 0, st>>>(w.pool, params + d->off_entry, d->n_entry, entry_id, w.z,
+                                                            (int)B, H, status);
+    SmallGemmBatch g1;
+    g1.count = 1;
+    g1.p[0] = sg(w.z, 2 * H, 1, params + d->off_g1_w, 1, 2 * H, params + d->off_g1_b, w.h1, H, (int)B, H, 2 * H, 1);
+    launch_small(g1, st);
+    SmallGemmBatch g2;
+    g2.count = 1;
+    g2.p[0] = sg(w.h1, H, 1, params + d->off_g2_w, 1, H, params + d->off_g2_b, global_pred, 1, (int)B, 1, H);
+    launch_small(g2, st);
+  }
+  PERT_LAUNCH_CHECK();
+  return PERT_OK;
+}
+
+// d_global [B] = dL/d global_pred, d_local [N] or NULL.  grads: flat buffer, same offsets as params, accumulated (+=).
+int pert_model_backward(const PertModelDesc* d, const float* params, float* grads, const int64_t* cat_X,
+                        const int64_t* entry_id, const float* probs, const float* pnn, const int64_t* batch,
+                        long long N, long long E, long long B, const int* rowptr, const int* csr_src,
+                        const int* csr_if, const int* csr_rpc, const int* colptr, const int* csc_pos,
+                        const int* csc_dst, void* workspace, long long workspace_bytes, int training,
+                        const float* d_global, const float* d_local, void* stream) {
+  TRY(check_desc(d));
+  if (!params || !grads || !cat_X || !entry_id || !probs || !pnn || !batch || !rowptr || !colptr || !workspace ||
+      !d_global)
+    return PERT_ERR_BADARG;
+  float* base = (float*)workspace;
+  Ws w = carve(d, N, E, B, base);
+  if (workspace_bytes < w.total * 4) return PERT_ERR_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = d->H, L = d->n_convs;
+  cudaError_t e = cudaMemsetAsync(w.gzero_begin, 0, (size_t)(w.gzero_end - w.gzero_begin) * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  // ---- global head backward
+  if (B > 0) {
+    SmallGemmBatch g;
+    g.count = 0;
+    // dh1 = (d_global (x) W2) * (h1 > 0)
+    g.p[g.count++] = sg(d_global, 1, 1, params + d->off_g2_w, H, 1, nullptr, w.dh1, H, (int)B, H, 1, 0, 0, 1, w.h1);
+    // dW2[0,:] += d_global^T h1 ;  db2 += sum d_global
+    g.p[g.count++] = sg(d_global, 0, 1, w.h1, H, 1, nullptr, grads + d->off_g2_w, H, 1, H, (int)B, 0, 1);
+    g.p[g.count++] = sg(d_global, 0, 1, nullptr, 0, 0, nullptr, grads + d->off_g2_b, 1, 1, 1, (int)B, 0, 1);
+    launch_small(g, st);
+    g.count = 0;
+    // dpool = dh1 . W1[:, :H] ; dzent = dh1 . W1[:, H:]      (B(k,n) = W1[k, n (+H)])
+    g.p[g.count++] = sg(w.dh1, H, 1, params + d->off_g1_w, 2 * H, 1, nullptr, w.dpool, H, (int)B, H, H);
+    g.p[g.count++] = sg(w.dh1, H, 1, params + d->off_g1_w + H, 2 * H, 1, nullptr, w.dzent, H, (int)B, H, H);
+    // dW1 += dh1^T . z  ([H,2H]);  db1 += sum_b dh1
+    g.p[g.count++] = sg(w.dh1, 1, H, w.z, 2 * H, 1, nullptr, grads + d->off_g1_w, 2 * H, H, 2 * H, (int)B, 0, 1);
+    g.p[g.count++] = sg(w.dh1, 1, H, nullptr, 0, 0, nullptr, grads + d->off_g1_b, 1, H, 1, (int)B, 0, 1);
+    launch_small(g, st);
+    TRY(pert_embedding_bwd(w.dzent, H, entry_id, 1, grads + d->off_entry, d->n_entry, B, H, st));
+  }
+  // ---- pool / local head backward: g = dL/d out[L-1], written straight into the skip plane of dplanes
+  float* dq = w.dplanes;
+  float* dk = dq + N * H;
+  float* dv = dk + N * H;
+  float* dskip = dv + N * H;
+  TRY(pert_pool_bwd(B > 0 ? w.dpool : nullptr, d_local, w.out[L - 1], H, probs, pnn, batch, params + d->off_local_w,
+                    dskip, H, grads + d->off_local_w, grads + d->off_local_b, N, B, H, st));
+  for (int l = L - 1; l >= 0; --l) {
+    const int K = k_of(d, l);
+    float* pl = w.planes[l];
+    TRY(pert_tconv_bwd(dskip, H, pl, pl + N * H, pl + 2 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos,
+                       csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.dt_if[l], w.dt_rpc[l],
+                       d->n_rpc, N, H, st));
+    // weight / bias gradients of the fused node linear (packed), data gradient
+    TRY(pert_gemm_tn(w.dplanes, H, H, N * (long long)H, w.x[l], K, 0, 0, w.dw4[l], K, N, 4 * H, K, st));
+    TRY(pert_colsum(w.dplanes, H, H, N * (long long)H, w.db4[l], N, 4 * H, st));
+    TRY(pert_gemm_nt(w.dplanes, H, H, N * (long long)H, w.w4t[l], 4 * H, nullptr, w.dx, K, 0, 0, N, K, 4 * H, 0, 0, st));
+    if (l > 0) {
+      // BN(+ReLU) backward of layer l-1: dx (grad wrt x[l]) -> g of conv l-1, into the skip plane
+      TRY(pert_bn_bwd(w.dx, K, w.x[l], H, w.out[l - 1], H, w.bn_stats[l - 1], w.bn_stats[l - 1] + H,
+                      params + d->off_bn_g[l - 1], 1, training, dskip, H, grads + d->off_bn_g[l - 1],
+                      grads + d->off_bn_b[l - 1], w.sums, N, H, st));
+    }
+  }
+  // ---- categorical embedding gradients from dX0[:, 0:H]
+  for (int i = 0; i < d->n_cat; ++i)
+    TRY(pert_embedding_bwd(w.dx, d->k0, cat_X + i, d->n_cat, grads + d->off_cat[i], d->cat_rows[i], N, H, st));
+  // ---- edge tables: dWeA = dT_if^T . if_emb ; d if_emb += dT_if . WeA   (and the rpc halves), all layers grouped
+  {
+    SmallGemmBatch gb;
+    gb.count = 0;
+    for (int l = 0; l < L; ++l) {
+      int ks_if = d->n_if >= 512 ? 8 : 1, ks_rpc = 1;
+      gb.p[gb.count++] = sg(w.dt_if[l], 1, H, params + d->off_if, H, 1, nullptr, w.dweA[l], H, H, H, d->n_if, 0, 1, ks_if);
+      gb.p[gb.count++] = sg(w.dt_rpc[l], 1, H, params + d->off_rpc, H, 1, nullptr, w.dweB[l], H, H, H, d->n_rpc, 0, 1, ks_rpc);
+      gb.p[gb.count++] = sg(w.dt_if[l], H, 1, w.weA[l], H, 1, nullptr, grads + d->off_if, H, d->n_if, H, H, 0, 1);
+      gb.p[gb.count++] = sg(w.dt_rpc[l], H, 1, w.weB[l], H, 1, nullptr, grads + d->off_rpc, H, d->n_rpc, H, H, 0, 1);
+      // accumulating into the same embedding-gradient rows from several layers must be serialised: one launch per layer
+      launch_small(gb, st);
+      gb.count = 0;
+    }
+  }
+  for (int l = 0; l < L; ++l) {
+    SegList S = layer_grad_segs(d, w, base, l);
+    k_unpack<<<dim3(8, S.count), 256, 0, st>>>(grads, base, S);
+  }
+  PERT_LAUNCH_CHECK();
+  return PERT_OK;
+}
+
+}  // extern "C"

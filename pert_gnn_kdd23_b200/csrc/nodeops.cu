@@ -101,10 +101,12 @@ __global__ void __launch_bounds__(256) k_bn_partial(const float* __restrict__ x,
 __global__ void k_bn_finalize(const float* __restrict__ part, int chunks, long long N, int H, float eps,
                               float momentum, float* __restrict__ mean, float* __restrict__ rstd,
                               float* running_mean, float* running_var, long long* num_batches_tracked) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per column: lanes stride over the chunk partials, then a shuffle tree of Chan merges
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= H) return;
   float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
-  for (int k = 0; k < chunks; ++k) {
+  for (int k = lane; k < chunks; k += 32) {
     float n_b = (float)min((long long)BN_ROWS, N - (long long)k * BN_ROWS);
     float mean_b = part[((size_t)k * 2 + 0) * H + c], m2_b = part[((size_t)k * 2 + 1) * H + c];
     float n = n_a + n_b, delta = mean_b - mean_a;
@@ -112,6 +114,20 @@ __global__ void k_bn_finalize(const float* __restrict__ part, int chunks, long l
     m2_a += m2_b + delta * delta * (n_a * n_b / n);
     n_a = n;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float n_b = __shfl_xor_sync(0xffffffffu, n_a, o);
+    float mean_b = __shfl_xor_sync(0xffffffffu, mean_a, o);
+    float m2_b = __shfl_xor_sync(0xffffffffu, m2_a, o);
+    float n = n_a + n_b;
+    if (n > 0.f) {
+      float delta = mean_b - mean_a;
+      mean_a += delta * (n_b / n);
+      m2_a += m2_b + delta * delta * (n_a * n_b / n);
+    }
+    n_a = n;
+  }
+  if (lane != 0) return;
   float var = m2_a / (float)N;  // biased, used to normalise
   mean[c] = mean_a;
   rstd[c] = 1.0f / sqrtf(var + eps);  // exact 1/sqrt (rsqrtf is ~2 ulp off ATen)
@@ -488,7 +504,7 @@ int pert_bn_fwd(const float* x, int ld_x, const float* gamma, const float* beta,
     if (smem > 48 * 1024) return PERT_ERR_UNSUPPORTED;
     float* part = (float*)workspace;
     k_bn_partial<<<chunks, threads, smem, st>>>(x, ld_x, N, H, part);
-    k_bn_finalize<<<pert_cdiv(H, 128), 128, 0, st>>>(part, chunks, N, H, eps, momentum, mean, rstd, running_mean,
+    k_bn_finalize<<<pert_cdiv((long long)H * 32, 128), 128, 0, st>>>(part, chunks, N, H, eps, momentum, mean, rstd, running_mean,
                                                     running_var, num_batches_tracked);
   } else {
     if (!running_mean || !running_var) return PERT_ERR_BADARG;

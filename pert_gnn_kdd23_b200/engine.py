@@ -1,0 +1,186 @@
+"""Python side of the whole-model step engine (csrc/engine.cu): builds the ``PertModelDesc`` from a
+``SAGEDeterministic`` module, owns the workspace, and exposes
+  * ``Engine.forward`` / ``Engine.backward``  -- raw calls (no autograd), used by the fused train step;
+  * ``engine_forward``                        -- a single autograd.Function for ``model.forward`` (drop-in path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from .index import GraphIndex
+
+MAX_CONVS, MAX_CAT = 8, 4
+LL = C.c_longlong
+
+
+class PertModelDesc(C.Structure):
+    _fields_ = [
+        ("F", C.c_int32), ("H", C.c_int32), ("n_convs", C.c_int32), ("n_cat", C.c_int32),
+        ("cat_rows", C.c_int32 * MAX_CAT), ("n_entry", C.c_int32), ("n_if", C.c_int32), ("n_rpc", C.c_int32),
+        ("k0", C.c_int32), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("off_cat", LL * MAX_CAT), ("off_entry", LL), ("off_if", LL), ("off_rpc", LL),
+        ("off_wq", LL * MAX_CONVS), ("off_bq", LL * MAX_CONVS), ("off_wk", LL * MAX_CONVS), ("off_bk", LL * MAX_CONVS),
+        ("off_wv", LL * MAX_CONVS), ("off_bv", LL * MAX_CONVS), ("off_ws", LL * MAX_CONVS), ("off_bs", LL * MAX_CONVS),
+        ("off_we", LL * MAX_CONVS), ("off_bn_g", LL * MAX_CONVS), ("off_bn_b", LL * MAX_CONVS),
+        ("off_local_w", LL), ("off_local_b", LL), ("off_g1_w", LL), ("off_g1_b", LL), ("off_g2_w", LL),
+        ("off_g2_b", LL),
+    ]
+
+
+def _bind():
+    return _lib.lib()
+
+
+class Engine:
+    """Owns flat parameters / gradients / BN buffers of one model replica and the engine workspace."""
+
+    # launches per call (for the gpu_launches accounting of bench.py)
+    def __init__(self, model, flat=None):
+        from .train import FlatParams
+
+        self.model = model
+        self.fp = flat if flat is not None else FlatParams(model)
+        self.lib = _bind()
+        dev = self.fp.flat.device
+        H = model.hidden_channels
+        n_convs = len(model.convs)
+        assert n_convs <= MAX_CONVS and len(model.cat_embedding) <= MAX_CAT
+        # BN running statistics as one flat buffer; the module buffers become views of it
+        n_bn = n_convs - 1
+        self.bn_running = torch.empty(n_bn, 2, H, device=dev, dtype=torch.float32)
+        self.bn_nbt = torch.zeros(n_bn, device=dev, dtype=torch.int64)
+        for l, bn in enumerate(model.bns):
+            self.bn_running[l, 0].copy_(bn.running_mean)
+            self.bn_running[l, 1].copy_(bn.running_var)
+            self.bn_nbt[l] = bn.num_batches_tracked
+            bn._buffers["running_mean"] = self.bn_running[l, 0]
+            bn._buffers["running_var"] = self.bn_running[l, 1]
+            bn._buffers["num_batches_tracked"] = self.bn_nbt[l]
+        d = PertModelDesc()
+        d.F, d.H, d.n_convs, d.n_cat = model.in_channels, H, n_convs, len(model.cat_embedding)
+        d.n_entry = model.entry_embeds.num_embeddings
+        d.n_if = model.interface_embeds.num_embeddings
+        d.n_rpc = model.rpctype_embeds.num_embeddings
+        d.k0 = (model.in_channels + H + 7) // 8 * 8
+        d.bn_eps = model.bns[0].eps
+        d.bn_momentum = model.bns[0].momentum if model.bns[0].momentum is not None else 0.0
+        base = self.fp.flat.data_ptr()
+
+        def off(p):
+            o = p.data_ptr() - base
+            assert o % 16 == 0 and 0 <= o < self.fp.flat.numel() * 4, "parameter is not an aligned view of the flat buffer"
+            return o // 4
+
+        for i, e in enumerate(model.cat_embedding):
+            d.cat_rows[i] = e.num_embeddings
+            d.off_cat[i] = off(e.weight)
+        d.off_entry, d.off_if, d.off_rpc = off(model.entry_embeds.weight), off(model.interface_embeds.weight), \
+            off(model.rpctype_embeds.weight)
+        for l, c in enumerate(model.convs):
+            d.off_wq[l], d.off_bq[l] = off(c.lin_query.weight), off(c.lin_query.bias)
+            d.off_wk[l], d.off_bk[l] = off(c.lin_key.weight), off(c.lin_key.bias)
+            d.off_wv[l], d.off_bv[l] = off(c.lin_value.weight), off(c.lin_value.bias)
+            d.off_ws[l], d.off_bs[l] = off(c.lin_skip.weight), off(c.lin_skip.bias)
+            d.off_we[l] = off(c.lin_edge.weight)
+        for l, bn in enumerate(model.bns):
+            d.off_bn_g[l], d.off_bn_b[l] = off(bn.weight), off(bn.bias)
+        d.off_local_w, d.off_local_b = off(model.local_linear.weight), off(model.local_linear.bias)
+        d.off_g1_w, d.off_g1_b = off(model.global_linear1.weight), off(model.global_linear1.bias)
+        d.off_g2_w, d.off_g2_b = off(model.global_linear2.weight), off(model.global_linear2.bias)
+        self.desc = d
+        self.n_convs = n_convs
+        self.ws = None
+        self.ws_key = (0, 0, 0)
+        self._saved = None
+
+    # ------------------------------------------------------------------------------------------
+    def _workspace(self, N, E, B):
+        if self.ws is None or N > self.ws_key[0] or E > self.ws_key[1] or B > self.ws_key[2]:
+            key = (max(N, self.ws_key[0]), max(E, self.ws_key[1]), max(B, self.ws_key[2]))
+            nbytes = self.lib.pert_model_workspace_bytes(C.byref(self.desc), *key)
+            if nbytes < 0:
+                _lib.check(int(nbytes), "pert_model_workspace_bytes")
+            self.ws = torch.zeros(nbytes // 4, device=self.fp.flat.device, dtype=torch.float32)
+            self.ws_key = key
+        return self.ws
+
+    def launches_forward(self):
+        L = self.n_convs
+        return L + (L + 5) // 6 + self.desc.n_cat + 1 + L * 2 + (L - 1) * 3 + 1 + 3
+
+    def launches_backward(self):
+        L = self.n_convs
+        return 2 + 1 + 1 + L * 5 + (L - 1) * 2 + self.desc.n_cat + L + L
+
+    def forward(self, x, cat_X, entry_id, probs, pnn, batch, index: GraphIndex, training):
+        """-> (global_pred [B,1], local_pred [N,1]); keeps what backward needs in the workspace."""
+        N, E, B = x.size(0), index.E, entry_id.numel()
+        ws = self._workspace(N, E, B)
+        dev = x.device
+        x = x.contiguous().float()
+        cat_X = cat_X.contiguous()
+        entry_id = entry_id.contiguous().reshape(-1)
+        probs = probs.reshape(-1).contiguous().float()
+        pnn = pnn.reshape(-1).contiguous().float()
+        batch = batch.contiguous()
+        gpred = torch.empty(B, 1, device=dev, dtype=torch.float32)
+        lpred = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        p = _lib.ptr
+        rc = self.lib.pert_model_forward(
+            C.byref(self.desc), p(self.fp.flat), p(self.bn_running), p(self.bn_nbt), p(x), p(cat_X), p(entry_id),
+            p(probs), p(pnn), p(batch), N, E, B, p(index.rowptr), p(index.csr_src), p(index.csr_if), p(index.csr_rpc),
+            p(ws), ws.numel() * 4, int(training), p(gpred), p(lpred), p(index.status), _lib.stream())
+        _lib.check(rc, "pert_model_forward")
+        ops.LAUNCHES["n"] += self.launches_forward()
+        self._saved = (x, cat_X, entry_id, probs, pnn, batch, index, bool(training), N, E, B)
+        return gpred, lpred
+
+    def backward(self, d_global, d_local=None, grads=None):
+        """Accumulates (+=) parameter gradients into ``grads`` (default: the flat gradient buffer)."""
+        x, cat_X, entry_id, probs, pnn, batch, index, training, N, E, B = self._saved
+        grads = self.fp.grad if grads is None else grads
+        d_global = d_global.reshape(-1).contiguous().float()
+        if d_local is not None:
+            d_local = d_local.reshape(-1).contiguous().float()
+        p = _lib.ptr
+        ws = self.ws
+        rc = self.lib.pert_model_backward(
+            C.byref(self.desc), p(self.fp.flat), p(grads), p(cat_X), p(entry_id), p(probs), p(pnn), p(batch), N, E, B,
+            p(index.rowptr), p(index.csr_src), p(index.csr_if), p(index.csr_rpc), p(index.colptr), p(index.csc_pos),
+            p(index.csc_dst), p(ws), ws.numel() * 4, int(training), p(d_global), p(d_local), _lib.stream())
+        _lib.check(rc, "pert_model_backward")
+        ops.LAUNCHES["n"] += self.launches_backward()
+
+
+class _EngineFn(torch.autograd.Function):
+    """model.forward as ONE autograd node: inputs are the parameters (so autograd routes their gradients),
+    outputs (global_pred, local_pred)."""
+
+    @staticmethod
+    def forward(ctx, engine, x, cat_X, entry_id, probs, pnn, batch, index, training, *params):
+        g, l = engine.forward(x, cat_X, entry_id, probs, pnn, batch, index, training)
+        ctx.engine = engine
+        ctx.token = engine._saved
+        return g, l
+
+    @staticmethod
+    def backward(ctx, dg, dl):
+        eng = ctx.engine
+        if eng._saved is not ctx.token:
+            raise RuntimeError("engine workspace was overwritten by a later forward before this backward ran "
+                               "(one in-flight forward per model replica)")
+        gbuf = torch.zeros_like(eng.fp.flat)
+        eng.backward(dg, dl, grads=gbuf)
+        base = eng.fp.flat.data_ptr()
+        outs = []
+        for p in eng.fp.params:
+            o = (p.data_ptr() - base) // 4
+            outs.append(gbuf[o:o + p.numel()].view_as(p))
+        return (None,) * 9 + tuple(outs)
+
+
+def engine_forward(engine, x, cat_X, entry_id, probs, pnn, batch, index, training):
+    return _EngineFn.apply(engine, x, cat_X, entry_id, probs, pnn, batch, index, training, *engine.fp.params)

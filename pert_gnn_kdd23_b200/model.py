@@ -39,6 +39,24 @@ class SAGEDeterministic(torch.nn.Module):
         self.interface_embeds = torch.nn.Embedding(interface_id_max + 1, H)
         self.rpctype_embeds = torch.nn.Embedding(rpctype_id_max + 1, H)
         self.edge_linear = Linear(-1, 2 * H)   # lazy + unused in the reference forward (model.py:68): no params
+        # True: whole forward/backward issued by the C++ step engine (csrc/engine.cu); False: one autograd
+        # Function per operator (ops.py).  Same kernels, same results; the engine removes the interpreter gaps.
+        self.use_engine = True
+        self._engine = None
+
+    def engine(self, flat=None):
+        """The step engine of this replica (created on first use; re-created if the parameters moved)."""
+        eng = self._engine
+        if eng is not None and flat is None:
+            p0 = next(self.parameters())
+            lo = eng.fp.flat.data_ptr()
+            if lo <= p0.data_ptr() < lo + eng.fp.flat.numel() * 4:
+                return eng
+        from .engine import Engine
+        from .train import FlatParams
+
+        self._engine = Engine(self, flat if flat is not None else FlatParams(self, bind_grads=False))
+        return self._engine
 
     def reset_parameters(self):
         for conv in self.convs:
@@ -53,6 +71,11 @@ class SAGEDeterministic(torch.nn.Module):
         if index is None:
             index = cached_index(edge_index, N, edge_attr, self.interface_embeds.num_embeddings,
                                  self.rpctype_embeds.num_embeddings)
+        if self.use_engine and (self.dropout == 0 or not self.training):
+            from .engine import engine_forward
+
+            return engine_forward(self.engine(), x, cat_X, entry_id, pattern_probs, pattern_num_nodes, batch, index,
+                                  self.training)
         # prologue (model.py:87-90): internal layout [cat_embeds | x | pad]; conv 0 weights permuted to match
         h = ops.embed_concat(x, cat_X, [e.weight for e in self.cat_embedding])
         pad = h.size(1) - (Fin + H)

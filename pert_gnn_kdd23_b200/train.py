@@ -28,7 +28,7 @@ class FlatParams:
     """All parameters (and their gradients) of a module as views into two flat fp32 buffers, so that the
     gradient all-reduce and the Adam update are ONE collective and ONE kernel (payload <= 4.8 MB, latency-bound)."""
 
-    def __init__(self, module):
+    def __init__(self, module, bind_grads=True):
         params = [p for p in module.parameters() if p.requires_grad]
         al = lambda k: (k + 63) // 64 * 64          # every parameter starts on a 256-byte boundary (float4 / TMA)
         n = sum(al(p.numel()) for p in params)
@@ -40,7 +40,8 @@ class FlatParams:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
-            p.grad = self.grad[off:off + k].view_as(p)
+            if bind_grads:
+                p.grad = self.grad[off:off + k].view_as(p)
             off += al(k)
         self.params = params
         self.numel = n
@@ -102,6 +103,33 @@ def train_step(model, optimizer, data, tau=0.5, dp: DataParallel | None = None):
             if s != 1.0:
                 dp.fp.grad.mul_(s)
         optimizer.step()
+    return loss
+
+
+def fused_train_step(model, optimizer: FusedAdam, data, tau=0.5, dp: DataParallel | None = None, index=None):
+    """Same step as ``train_step`` but without autograd: engine forward -> pinball loss + its gradient (one
+    kernel) -> engine backward into the flat gradient buffer -> (all-reduce) -> fused Adam.  5 C calls per step.
+    Returns the device loss tensor [1]."""
+    from .index import cached_index
+
+    eng = model.engine(optimizer.fp) if (model._engine is None or model._engine.fp is not optimizer.fp) \
+        else model._engine
+    x, cat_X, edge_index, edge_attr, pnn, probs, entry_id, batch = model_inputs(data)
+    if index is None:
+        index = cached_index(edge_index, x.size(0), edge_attr, model.interface_embeds.num_embeddings,
+                             model.rpctype_embeds.num_embeddings)
+    optimizer.zero_grad()
+    with torch.no_grad():
+        gpred, _ = eng.forward(x, cat_X, entry_id, probs, pnn, batch, index, model.training)
+        B = gpred.size(0)
+        loss = torch.empty(1, device=gpred.device, dtype=torch.float32)
+        dy = torch.empty(B, device=gpred.device, dtype=torch.float32)
+        _lib.call("pert_pinball_loss", _lib.ptr(data.y), _lib.ptr(gpred), float(tau), B, 1.0, _lib.ptr(loss),
+                  _lib.ptr(dy), _lib.stream())
+        ops.LAUNCHES["n"] += 1
+        eng.backward(dy, None)
+        scale = dp.all_reduce_grads() if dp is not None else 1.0
+        optimizer.step(grad_scale=scale)
     return loss
 
 
