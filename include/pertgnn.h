@@ -74,18 +74,21 @@ int pert_segment_reduce_bwd(const float* dout, const float* msg, const float* ou
  * root_weight) -- reference model.py:26-51 (construction), :100,:104 (calls).  q,k,v,s: [N,H] planes with
  * row stride ld (s = lin_skip(x), may be NULL); t_if [n_if,H], t_rpc [n_rpc,H] = embedding tables already
  * multiplied by the two halves of lin_edge.weight (NULL,NULL = no edge features).  out [N,H];
- * alpha [E] (CSR order) is saved for backward.  H in {4,8,16,32,64,96,128,192,256}. */
+ * alpha [E] (CSR order) is saved for backward.  H in {4,8,16,32,64,96,128,192,256}.
+ * E = number of edges, B_hint = number of graphs in the batch (0 if unknown): only used to size the shared-memory
+ * node tiles of the staged kernels (csrc/tconv_tile.cu); n_rpc = rows of t_rpc. */
 int pert_tconv_supported_width(int H);
 int pert_tconv_fwd(const float* q, const float* k, const float* v, const float* s, int ld, const int* rowptr,
                    const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if, const float* t_rpc,
-                   float* out, int ld_out, float* alpha, long long N, int H, void* stream);
+                   float* out, int ld_out, float* alpha, int n_rpc, long long N, long long E, long long B_hint, int H,
+                   void* stream);
 /* g = dL/dout [N,H] (stride ld_g).  Writes dq,dk,dv [N,H] (stride ld_d), dsp [E] scratch; ACCUMULATES
  * (+=, atomics) into dt_if [n_if,H] and dt_rpc [n_rpc,H] (caller zeroes them once per step). */
 int pert_tconv_bwd(const float* g, int ld_g, const float* q, const float* k, const float* v, int ld,
                    const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr,
                    const int* csc_pos, const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha,
                    float* dq, float* dk, float* dv, int ld_d, float* dsp, float* dt_if, float* dt_rpc, int n_rpc,
-                   long long N, int H, void* stream);
+                   long long N, long long E, long long B_hint, int H, void* stream);
 
 /* ---- dense linears (exact fp32) --------------------------------------------------------------------
  * Replace torch_geometric.nn.Linear / the lin_* of TransformerConv (model.py:26-55,105,110-112).

@@ -26,8 +26,9 @@ SIGNATURES = {
     "pert_segment_reduce_fwd": (I, [P, P, P, P, LL, I, I, P]),
     "pert_segment_reduce_bwd": (I, [P, P, P, P, P, P, LL, I, I, P]),
     "pert_tconv_supported_width": (I, [I]),
-    "pert_tconv_fwd": (I, [P, P, P, P, I, P, P, P, P, P, P, P, I, P, LL, I, P]),
-    "pert_tconv_bwd": (I, [P, I, P, P, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, I, LL, I, P]),
+    "pert_tconv_fwd": (I, [P, P, P, P, I, P, P, P, P, P, P, P, I, P, I, LL, LL, LL, I, P]),
+    "pert_tconv_bwd": (I, [P, I, P, P, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, I, LL, LL, LL, I,
+                           P]),
     "pert_gemm_nt": (I, [P, I, I, LL, P, I, P, P, I, I, LL, LL, I, I, I, I, P]),
     "pert_gemm_tn": (I, [P, I, I, LL, P, I, I, LL, P, I, LL, I, I, P]),
     "pert_colsum": (I, [P, I, I, LL, P, LL, I, P]),

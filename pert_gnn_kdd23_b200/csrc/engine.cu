@@ -379,7 +379,7 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
     TRY(pert_gemm_nt(w.x[l], K, 0, 0, w.w4[l], K, w.b4[l], w.planes[l], H, H, N * (long long)H, N, 4 * H, K, 0, 0, st));
     float* pl = w.planes[l];
     TRY(pert_tconv_fwd(pl, pl + N * H, pl + 2 * N * H, pl + 3 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, w.t_if[l],
-                       w.t_rpc[l], w.out[l], H, w.alpha[l], N, H, st));
+                       w.t_rpc[l], w.out[l], H, w.alpha[l], d->n_rpc, N, E, B, H, st));
     if (l + 1 < L) {
       float* rm = bn_running ? bn_running + (size_t)l * 2 * H : nullptr;
       float* rv = rm ? rm + H : nullptr;
@@ -458,7 +458,7 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
     float* pl = w.planes[l];
     TRY(pert_tconv_bwd(dskip, H, pl, pl + N * H, pl + 2 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos,
                        csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.dt_if[l], w.dt_rpc[l],
-                       d->n_rpc, N, H, st));
+                       d->n_rpc, N, E, B, H, st));
     // weight / bias gradients of the fused node linear (packed), data gradient
     TRY(pert_gemm_tn(w.dplanes, H, H, N * (long long)H, w.x[l], K, 0, 0, w.dw4[l], K, N, 4 * H, K, st));
     TRY(pert_colsum(w.dplanes, H, H, N * (long long)H, w.db4[l], N, 4 * H, st));

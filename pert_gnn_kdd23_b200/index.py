@@ -20,7 +20,7 @@ _CHECK = os.environ.get("PERT_CHECK_INDICES", "0") == "1"
 
 class GraphIndex:
     __slots__ = ("N", "E", "rowptr", "perm", "csr_src", "csr_if", "csr_rpc", "colptr", "csc_pos",
-                 "csc_dst", "status", "has_attr", "n_if", "n_rpc", "_buf", "__weakref__")
+                 "csc_dst", "status", "has_attr", "n_if", "n_rpc", "num_graphs", "_buf", "__weakref__")
 
     def check(self):
         """Synchronising validity check of the ids seen while building (debug aid)."""
@@ -57,6 +57,7 @@ def build_index(edge_index, num_nodes, edge_attr=None, n_if=0, n_rpc=0, check=No
     parts = [buf[offs[i]:offs[i] + sizes[i]] for i in range(len(sizes))]
     gi = GraphIndex()
     gi.N, gi.E, gi._buf = N, E, buf
+    gi.num_graphs = 0          # hint for the shared-memory tile size (set by the model: batch size)
     (gi.rowptr, gi.perm, gi.csr_src, gi.csr_if, gi.csr_rpc, gi.colptr, gi.csc_pos, gi.csc_dst, status) = parts
     gi.status = status[:1]
     gi.status.zero_()

@@ -71,6 +71,7 @@ class SAGEDeterministic(torch.nn.Module):
         if index is None:
             index = cached_index(edge_index, N, edge_attr, self.interface_embeds.num_embeddings,
                                  self.rpctype_embeds.num_embeddings)
+        index.num_graphs = entry_id.numel()
         if self.use_engine and (self.dropout == 0 or not self.training):
             from .engine import engine_forward
 

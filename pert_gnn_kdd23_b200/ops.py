@@ -246,7 +246,8 @@ class _TConvFn(torch.autograd.Function):
         with _timed("tconv_fwd"):
             call("pert_tconv_fwd", ptr(q), ptr(k), ptr(v), ptr(s), H, ptr(index.rowptr), ptr(index.csr_src),
                  ptr(index.csr_if) if has_e else None, ptr(index.csr_rpc) if has_e else None,
-                 ptr(t_if), ptr(t_rpc), ptr(out), H, ptr(alpha), N, H, stream())
+                 ptr(t_if), ptr(t_rpc), ptr(out), H, ptr(alpha), t_rpc.size(0) if has_e else 0, N, index.E,
+                 getattr(index, "num_graphs", 0), H, stream())
         LAUNCHES["n"] += 1
         ctx.index = index
         ctx.has_e = has_e
@@ -270,8 +271,8 @@ class _TConvFn(torch.autograd.Function):
                  ptr(index.rowptr), ptr(index.csr_src), ptr(index.csr_if) if ctx.has_e else None,
                  ptr(index.csr_rpc) if ctx.has_e else None, ptr(index.colptr), ptr(index.csc_pos),
                  ptr(index.csc_dst), ptr(t_if), ptr(t_rpc), ptr(alpha), ptr(dplanes[0]), ptr(dplanes[1]),
-                 ptr(dplanes[2]), H, ptr(dsp), ptr(dt_if), ptr(dt_rpc), t_rpc.size(0) if ctx.has_e else 0, N, H,
-                 stream())
+                 ptr(dplanes[2]), H, ptr(dsp), ptr(dt_if), ptr(dt_rpc), t_rpc.size(0) if ctx.has_e else 0, N,
+                 index.E, getattr(index, "num_graphs", 0), H, stream())
         LAUNCHES["n"] += 2
         if P_ == 4:
             dplanes[3].copy_(g)
