@@ -234,6 +234,13 @@ inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
 
+// tensor-core (tcgen05, 3xTF32) kernels of gemm_tc.cu; PERT_ERR_UNSUPPORTED => exact-fp32 SIMT kernels below
+int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, const float* bias,
+                    float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K, int relu,
+                    cudaStream_t st);
+int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, int b_cb,
+                    long long b_cbs, float* C, int ldc, long long R, int Mc, int Nc, cudaStream_t st);
+
 extern "C" {
 
 int pert_gemm_nt(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, const float* bias,
@@ -243,6 +250,15 @@ int pert_gemm_nt(const float* A, int lda, int a_cb, long long a_cbs, const float
   if (a_cb <= 0) a_cb = K;
   if (c_cb <= 0) c_cb = Nc;
   if (M == 0) return PERT_OK;
+  if (!accumulate) {
+    int rt = pert_gemm_nt_tc(A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, M, Nc, K, relu,
+                             (cudaStream_t)stream);
+    if (rt != PERT_ERR_UNSUPPORTED) {
+      if (rt) return rt;
+      PERT_LAUNCH_CHECK();
+      return PERT_OK;
+    }
+  }
   const int vec_a = !(K % 4 || lda % 4 || a_cb % 4 || a_cbs % 4 || !al16(A));
   const int vec_b = !(K % 4 || ldb % 4 || !al16(B));
   Blocked a{lda, a_cb, a_cbs}, c{ldc, c_cb, c_cbs};
@@ -259,6 +275,14 @@ int pert_gemm_tn(const float* A, int lda, int a_cb, long long a_cbs, const float
   if (a_cb <= 0) a_cb = Mc;
   if (b_cb <= 0) b_cb = Nc;
   if (R == 0) return PERT_OK;
+  {
+    int rt = pert_gemm_tn_tc(A, lda, a_cb, a_cbs, B, ldb, b_cb, b_cbs, C, ldc, R, Mc, Nc, (cudaStream_t)stream);
+    if (rt != PERT_ERR_UNSUPPORTED) {
+      if (rt) return rt;
+      PERT_LAUNCH_CHECK();
+      return PERT_OK;
+    }
+  }
   const int vec_a = !(lda % 4 || a_cb % 4 || a_cbs % 4 || !al16(A));
   const int vec_b = !(ldb % 4 || b_cb % 4 || b_cbs % 4 || !al16(B));
   Blocked a{lda, a_cb, a_cbs}, b{ldb, b_cb, b_cbs};

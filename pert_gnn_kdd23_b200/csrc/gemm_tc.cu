@@ -1,0 +1,509 @@
+// Tensor-core path of the dense node linears: tcgen05.mma kind::tf32 with 3xTF32 split accumulation.
+//
+// The linears need fp32-level accuracy (1e-4 after 3-5 layers + BatchNorm), which single-pass TF32 (10-bit
+// mantissa) does not give.  Every fp32 operand x is split exactly into hi = x & 0xffffe000 (a tf32 value) and
+// lo = x - hi; the product is accumulated in fp32 (TMEM) as  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is
+// ~2^-22 relative), three MMAs per K-step on the 5th-generation tensor cores (tests: test_linear_* at 2e-6).
+//
+// Operand staging (validated by csrc/dev/umma_probe*.cu on B200):
+//   A (activations):  thread = row; the row's K-chunk goes global -> registers (16-byte loads) -> split ->
+//       tcgen05.st into TMEM (A-from-TMEM MMA form: lane = row, one 32-bit column per K element).  No smem, no TMA
+//       descriptor; the split is free.  (MN-major smem operands are NOT usable for 32-bit types without the special
+//       128B_BASE32B swizzle -- probed, returns zeros -- so the weight-gradient kernel also feeds A through TMEM and
+//       transposes B while filling shared memory.)
+//   B:  shared memory, no-swizzle K-major canonical layout (8-row x 16-byte core matrices, LBO = 128 B between
+//       K-adjacent core matrices, SBO between N-adjacent), split hi/lo.
+//   D:  fp32 accumulator in TMEM; epilogue tcgen05.ld (lane = row).
+//
+// Both kernels are persistent, one CTA per SM, warp-specialised with mbarrier pipelines (2 stages):
+//   NT (forward / data gradient, C[M,Nc] = A[M,K] . B[Nc,K]^T (+bias)):
+//       warps 0-3 load+split A chunks into TMEM stage s | warp 4 issues the MMAs (one thread) | warps 5-8 drain the
+//       accumulator stage (TMEM -> registers -> +bias -> global) while the next tile is being multiplied.
+//   TN (weight gradient, C[Mc,Nc] += A[R,Mc]^T . B[R,Nc], split over R, REDG.128 accumulation):
+//       warps 0-3 load A columns (coalesced across lanes) into TMEM | warps 4-7 transpose the B chunk into the K-major
+//       smem layout (bank-conflict-free 8x4 patches) | warp 8 issues the MMAs.
+// These GEMMs are HBM-bound (K <= 256): A read once, C written once; the tensor cores only have to keep up.
+#include "common.cuh"
+#include <stdlib.h>
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); base_offset 0, lbo_mode 0, SWIZZLE_NONE
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  // c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+          taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
+
+constexpr int TC_THREADS = 288;  // 4 producer warps + 1 MMA warp + 4 consumer warps
+constexpr int KC = 64;           // K elements per A stage (TMEM columns per hi / lo half)
+constexpr int D_COL = 0;         // accumulator stages at columns 0 and 128
+constexpr int A_COL = 256;       // A stages at 256 + s*128 (hi: +0, lo: +64)
+constexpr int TMEM_COLS = 512;
+
+struct NtArgs {
+  const float* A;
+  int lda, a_cb;
+  long long a_cbs;
+  const float* B;
+  int ldb;
+  const float* bias;
+  float* C;
+  int ldc, c_cb;
+  long long c_cbs;
+  int M, Nc, K, BN, relu;
+};
+
+struct NtBars {
+  uint64_t a_full[2], a_empty[2], d_full[2], d_empty[2];
+};
+
+// grid: (persistent over 128-row tiles, Nc / BN); one CTA per SM
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_nt_tc(NtArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) NtBars bars;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = g.K, BN = g.BN;
+  const int n0 = blockIdx.y * BN;
+  const uint32_t LBO = 128, SBO = (uint32_t)(K / 4) * 128;
+  unsigned char* sBhi = smem;
+  unsigned char* sBlo = smem + (size_t)BN * K * 4;
+  // ---- B (weights) -> smem, split hi/lo, canonical K-major (all threads, once per CTA)
+  const int kq = K / 4;
+  for (int idx = tid; idx < BN * kq; idx += TC_THREADS) {
+    const int n = idx / kq, kc = idx - n * kq;
+    float4 v = f4zero();
+    if (n0 + n < g.Nc) v = ldg4(g.B + (size_t)(n0 + n) * g.ldb + kc * 4);
+    uint4 h, l;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l.x = tf32_lo(v.x, h.x); l.y = tf32_lo(v.y, h.y); l.z = tf32_lo(v.z, h.z); l.w = tf32_lo(v.w, h.w);
+    const size_t off = (size_t)(n >> 3) * SBO + (n & 7) * 16 + (size_t)kc * LBO;
+    *reinterpret_cast<uint4*>(sBhi + off) = h;
+    *reinterpret_cast<uint4*>(sBlo + off) = l;
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.a_full[s], 128);
+      mbar_init(&bars.a_empty[s], 1);
+      mbar_init(&bars.d_full[s], 1);
+      mbar_init(&bars.d_empty[s], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = s_tmem;
+  const int mtiles = (g.M + 127) / 128;
+  const int nchunks = (K + KC - 1) / KC;
+
+  if (warp < 4) {
+    // ================= A producer: global -> registers -> hi/lo -> TMEM stage =================
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    uint32_t stage = 0, ph = 0;
+    for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+      const int row = mt * 128 + tid;
+      const bool rok = row < g.M;
+      const float* arow = g.A + (size_t)(rok ? row : 0) * g.lda;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int k0 = ch * KC;
+        const int kw = min(KC, K - k0);
+        const float* src = arow + (size_t)(k0 / g.a_cb) * g.a_cbs + (k0 % g.a_cb);   // a chunk never straddles blocks
+        float4 va[KC / 4];
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q) va[q] = (rok && q * 4 < kw) ? ldg4(src + q * 4) : f4zero();
+        mbar_wait(&bars.a_empty[stage], ph ^ 1);
+        fence_after();
+        const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
+#pragma unroll
+        for (int grp = 0; grp < KC / 16; ++grp) {
+          if (grp * 16 < kw) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 v = va[grp * 4 + q];
+              hi[q * 4 + 0] = tf32_hi(v.x); lo[q * 4 + 0] = tf32_lo(v.x, hi[q * 4 + 0]);
+              hi[q * 4 + 1] = tf32_hi(v.y); lo[q * 4 + 1] = tf32_lo(v.y, hi[q * 4 + 1]);
+              hi[q * 4 + 2] = tf32_hi(v.z); lo[q * 4 + 2] = tf32_lo(v.z, hi[q * 4 + 2]);
+              hi[q * 4 + 3] = tf32_hi(v.w); lo[q * 4 + 3] = tf32_lo(v.w, hi[q * 4 + 3]);
+            }
+            tmem_st16(t_hi + grp * 16, hi);
+            tmem_st16(t_hi + KC + grp * 16, lo);
+          }
+        }
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&bars.a_full[stage]);
+        stage ^= 1;
+        if (stage == 0) ph ^= 1;
+      }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, BN);
+      const uint32_t bhi0 = smem_u32(sBhi), blo0 = smem_u32(sBlo);
+      uint32_t stage = 0, ph = 0, ds = 0, dph = 0;
+      for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+        mbar_wait(&bars.d_empty[ds], dph ^ 1);
+        fence_after();
+        const uint32_t t_d = tmem + D_COL + ds * 128;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int k0 = ch * KC;
+          const int kw = min(KC, K - k0);
+          mbar_wait(&bars.a_full[stage], ph);
+          fence_after();
+          const uint32_t t_hi = tmem + A_COL + stage * 128;
+          for (int s = 0; s < kw / 8; ++s) {
+            const uint32_t koff = (uint32_t)((k0 >> 3) + s) * 2 * LBO;   // 8 K-elements = two 16-byte core columns
+            const uint64_t bhi = make_desc(bhi0 + koff, LBO, SBO);
+            const uint64_t blo = make_desc(blo0 + koff, LBO, SBO);
+            mma_ts(t_d, t_hi + s * 8, bhi, idesc, (ch | s) ? 1u : 0u);
+            mma_ts(t_d, t_hi + KC + s * 8, bhi, idesc, 1u);
+            mma_ts(t_d, t_hi + s * 8, blo, idesc, 1u);
+          }
+          mma_commit(&bars.a_empty[stage]);
+          stage ^= 1;
+          if (stage == 0) ph ^= 1;
+        }
+        mma_commit(&bars.d_full[ds]);
+        ds ^= 1;
+        if (ds == 0) dph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue: accumulator stage -> registers -> (+bias, relu) -> global =================
+    const int q4 = warp & 3;                       // TMEM lane quarter this warp may access
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    uint32_t ds = 0, dph = 0;
+    for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+      const int row = mt * 128 + q4 * 32 + lane;
+      const bool rok = row < g.M;
+      mbar_wait(&bars.d_full[ds], dph);
+      fence_after();
+      const uint32_t t_d = tmem + lane_off + D_COL + ds * 128;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(t_d + c0, r0);
+        const bool two = c0 + 16 < BN;
+        if (two) tmem_ld16(t_d + c0 + 16, r1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && !two) break;
+          const uint32_t* r = half ? r1 : r0;
+          const int col = n0 + c0 + half * 16;
+          if (rok && col < g.Nc) {
+            float* dst = g.C + (size_t)(col / g.c_cb) * g.c_cbs + (size_t)row * g.ldc + (col % g.c_cb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 o = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                     __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+              if (g.bias) o = f4add(o, ldg4(g.bias + col + q * 4));
+              if (g.relu) o = f4max(o, f4zero());
+              st4(dst + q * 4, o);
+            }
+          }
+        }
+      }
+      fence_before();
+      mbar_arrive(&bars.d_empty[ds]);
+      ds ^= 1;
+      if (ds == 0) dph ^= 1;
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RC = 64;   // reduction rows (nodes) per chunk == K of one pipeline stage
+
+struct TnArgs {
+  const float* A;   // [R, Mc] blocked
+  int lda, a_cb;
+  long long a_cbs;
+  const float* B;   // [R, Nc] plain
+  int ldb;
+  float* C;         // [Mc, Nc], ldc
+  int ldc;
+  int R, Mc, Nc, NcP, rows_per_split;
+};
+struct TnBars {
+  uint64_t full[2], empty[2], done;
+};
+
+// grid: (splits over R, Mc / 128); one CTA per SM
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) TnBars bars;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NcP = g.NcP;
+  const uint32_t LBO = 128, SBO = (RC / 4) * 128;
+  const size_t stage_bytes = (size_t)NcP * RC * 4;      // one of hi / lo
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.full[s], 256);
+      mbar_init(&bars.empty[s], 1);
+    }
+    mbar_init(&bars.done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = s_tmem;
+  const int r_begin = blockIdx.x * g.rows_per_split;
+  const int r_end = min(g.R, r_begin + g.rows_per_split);
+  const int nch = (r_end - r_begin + RC - 1) / RC;
+
+  if (warp < 4) {
+    // ================= A producer: column mcol over RC rows (coalesced across the warp) -> TMEM =================
+    const int mcol = blockIdx.y * 128 + tid;     // this thread's A column == D row
+    const bool mok = mcol < g.Mc;
+    const int mc = mok ? mcol : 0;
+    const float* acol = g.A + (size_t)(mc / g.a_cb) * g.a_cbs + (mc % g.a_cb);
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    uint32_t stage = 0, ph = 0;
+    for (int c = 0; c < nch; ++c) {
+      const int r0 = r_begin + c * RC;
+      const float* p = acol + (size_t)r0 * g.lda;
+      float av[RC];
+#pragma unroll
+      for (int i = 0; i < RC; ++i) av[i] = (mok && r0 + i < r_end) ? __ldg(p + (size_t)i * g.lda) : 0.f;
+      mbar_wait(&bars.empty[stage], ph ^ 1);
+      fence_after();
+      const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
+#pragma unroll
+      for (int grp = 0; grp < RC / 16; ++grp) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          hi[i] = tf32_hi(av[grp * 16 + i]);
+          lo[i] = tf32_lo(av[grp * 16 + i], hi[i]);
+        }
+        tmem_st16(t_hi + grp * 16, hi);
+        tmem_st16(t_hi + RC + grp * 16, lo);
+      }
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&bars.full[stage]);
+      stage ^= 1;
+      if (stage == 0) ph ^= 1;
+    }
+    // ---- epilogue: D -> REDG.128 into C
+    if (nch > 0) {
+      mbar_wait(&bars.done, 0);
+      fence_after();
+      for (int c0 = 0; c0 < NcP; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_off + D_COL + c0, r);
+        tmem_wait_ld();
+        if (mok) {
+          float* dst = g.C + (size_t)mcol * g.ldc + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (c0 + q * 4 < g.Nc)
+              red4(dst + q * 4, make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                            __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ================= B producer: [RC rows, Nc] -> smem stage, K-major (K = row), hi/lo =================
+    // lane -> (n % 8, r % 4): a warp store covers an 8 (n) x 4 (r) patch = 32 distinct banks
+    const int w = warp - 4;
+    const int ln = lane & 7, lr = lane >> 3;
+    const int npatch_n = NcP / 8;
+    uint32_t stage = 0, ph = 0;
+    for (int c = 0; c < nch; ++c) {
+      const int r0 = r_begin + c * RC;
+      mbar_wait(&bars.empty[stage], ph ^ 1);
+      unsigned char* sBhi = smem + (size_t)stage * 2 * stage_bytes;
+      unsigned char* sBlo = sBhi + stage_bytes;
+      for (int rp = w; rp < RC / 4; rp += 4) {          // row patch (4 rows)
+        const int r = rp * 4 + lr;
+        const bool rok = r0 + r < r_end;
+        const float* brow = g.B + (size_t)(r0 + (rok ? r : 0)) * g.ldb;
+        const size_t roff = (size_t)(r >> 2) * LBO + (r & 3) * 4;
+        for (int np = 0; np < npatch_n; ++np) {
+          const int n = np * 8 + ln;
+          const float x = (rok && n < g.Nc) ? __ldg(brow + n) : 0.f;
+          const uint32_t h = tf32_hi(x);
+          const size_t off = (size_t)np * SBO + ln * 16 + roff;
+          *reinterpret_cast<uint32_t*>(sBhi + off) = h;
+          *reinterpret_cast<uint32_t*>(sBlo + off) = tf32_lo(x, h);
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&bars.full[stage]);
+      stage ^= 1;
+      if (stage == 0) ph ^= 1;
+    }
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, NcP);
+      uint32_t stage = 0, ph = 0;
+      for (int c = 0; c < nch; ++c) {
+        mbar_wait(&bars.full[stage], ph);
+        fence_after();
+        const uint32_t bhi0 = smem_u32(smem + (size_t)stage * 2 * stage_bytes);
+        const uint32_t blo0 = bhi0 + (uint32_t)stage_bytes;
+        const uint32_t t_hi = tmem + A_COL + stage * 128;
+#pragma unroll
+        for (int s = 0; s < RC / 8; ++s) {
+          const uint32_t koff = (uint32_t)s * 2 * LBO;
+          const uint64_t bhi = make_desc(bhi0 + koff, LBO, SBO);
+          const uint64_t blo = make_desc(blo0 + koff, LBO, SBO);
+          mma_ts(tmem + D_COL, t_hi + s * 8, bhi, idesc, (c | s) ? 1u : 0u);
+          mma_ts(tmem + D_COL, t_hi + RC + s * 8, bhi, idesc, 1u);
+          mma_ts(tmem + D_COL, t_hi + s * 8, blo, idesc, 1u);
+        }
+        mma_commit(&bars.empty[stage]);
+        stage ^= 1;
+        if (stage == 0) ph ^= 1;
+      }
+      if (nch > 0) mma_commit(&bars.done);
+    }
+    __syncwarp();
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static bool tc_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PERT_GEMM_TC");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+}  // namespace
+
+// Returns PERT_ERR_UNSUPPORTED when the shape / layout is outside what the tensor-core kernels handle (the caller
+// then uses the exact-fp32 SIMT kernels of gemm.cu).
+int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, const float* bias,
+                    float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K, int relu,
+                    cudaStream_t st) {
+  if (!tc_enabled() || M < 1024) return PERT_ERR_UNSUPPORTED;
+  if (a_cb <= 0) { a_cb = K; a_cbs = 0; }
+  if (c_cb <= 0) { c_cb = Nc; c_cbs = 0; }
+  if (K % 8 || K > 1024 || Nc % 16 || lda % 4 || ldb % 4 || ldc % 4 || c_cb % 16 || a_cbs % 4 || c_cbs % 4 ||
+      !al16(A) || !al16(B) || !al16(C) || (bias && !al16(bias)))
+    return PERT_ERR_UNSUPPORTED;
+  if (a_cb < K && a_cb % KC) return PERT_ERR_UNSUPPORTED;   // a K-chunk must not straddle two column blocks
+  // N block: <= 128 accumulator columns per CTA, Nc split into equal multiples of 16
+  int nblk = (Nc + 127) / 128;
+  while (Nc % nblk || (Nc / nblk) % 16) ++nblk;
+  const int BN = Nc / nblk;
+  const size_t smem = (size_t)BN * K * 4 * 2;
+  if (smem > 200 * 1024) return PERT_ERR_UNSUPPORTED;
+  NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu};
+  cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int mtiles = (int)((M + 127) / 128);
+  int gx = PERT_NUM_SMS / nblk;
+  if (gx < 1) gx = 1;
+  if (gx > mtiles) gx = mtiles;
+  k_gemm_nt_tc<<<dim3(gx, nblk), TC_THREADS, smem, st>>>(g);
+  return PERT_OK;
+}
+
+int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, int b_cb,
+                    long long b_cbs, float* C, int ldc, long long R, int Mc, int Nc, cudaStream_t st) {
+  if (!tc_enabled() || R < 4096) return PERT_ERR_UNSUPPORTED;
+  if (a_cb <= 0) { a_cb = Mc; a_cbs = 0; }
+  if (b_cb > 0 && b_cb < Nc) return PERT_ERR_UNSUPPORTED;   // B must be a plain matrix
+  if (Nc % 4 || Nc > 128 || ldc % 4 || !al16(C)) return PERT_ERR_UNSUPPORTED;
+  const int NcP = (Nc + 15) / 16 * 16;
+  const int mblk = (Mc + 127) / 128;
+  int splits = PERT_NUM_SMS / mblk;
+  if (splits < 1) splits = 1;
+  int rps = (int)((R + splits - 1) / splits);
+  rps = (rps + RC - 1) / RC * RC;
+  splits = (int)((R + rps - 1) / rps);
+  const size_t smem = (size_t)NcP * RC * 4 * 2 * 2;
+  TnArgs g{A, lda, a_cb, a_cbs, B, ldb, C, ldc, (int)R, Mc, Nc, NcP, rps};
+  cudaError_t e = cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_gemm_tn_tc<<<dim3(splits, mblk), TC_THREADS, smem, st>>>(g);
+  return PERT_OK;
+}
