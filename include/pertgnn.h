@@ -99,8 +99,10 @@ int pert_tconv_bwd(const float* g, int ld_g, const float* q, const float* k, con
 int pert_gemm_nt(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, const float* bias,
                  float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K, int relu, int accumulate,
                  void* stream);
+/* a_colsum (optional, [Mc]): also accumulates a_colsum[m] += sum_r A[r,m] (the bias gradient of the same linear,
+ * fused into the producer of the tensor-core kernel: A is read once for both). */
 int pert_gemm_tn(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, int b_cb,
-                 long long b_cbs, float* C, int ldc, long long R, int Mc, int Nc, void* stream);
+                 long long b_cbs, float* C, int ldc, float* a_colsum, long long R, int Mc, int Nc, void* stream);
 int pert_colsum(const float* A, int lda, int a_cb, long long a_cbs, float* out, long long R, int Cc, void* stream);
 
 /* ---- embeddings / concat (model.py:87-97,108) -------------------------------------------------------

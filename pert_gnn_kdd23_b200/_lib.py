@@ -30,7 +30,7 @@ SIGNATURES = {
     "pert_tconv_bwd": (I, [P, I, P, P, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, I, LL, LL, LL, I,
                            P]),
     "pert_gemm_nt": (I, [P, I, I, LL, P, I, P, P, I, I, LL, LL, I, I, I, I, P]),
-    "pert_gemm_tn": (I, [P, I, I, LL, P, I, I, LL, P, I, LL, I, I, P]),
+    "pert_gemm_tn": (I, [P, I, I, LL, P, I, I, LL, P, I, P, LL, I, I, P]),
     "pert_colsum": (I, [P, I, I, LL, P, LL, I, P]),
     "pert_embedding_fwd": (I, [P, I, P, I, P, I, LL, I, I, P, P]),
     "pert_embedding_bwd": (I, [P, I, P, I, P, I, LL, I, P]),

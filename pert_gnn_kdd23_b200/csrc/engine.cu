@@ -29,7 +29,8 @@ struct SmallGemmBatch {
   SmallGemm p[SG_MAX];
   int count;
 };
-constexpr int SG_BM = 32, SG_BN = 64, SG_BK = 16;
+// BK = 64: these problems are latency-bound chains of (load -> sync -> fma) steps; fewer, fatter steps
+constexpr int SG_BM = 32, SG_BN = 64, SG_BK = 64;
 
 __global__ void __launch_bounds__(256) k_small_gemm(SmallGemmBatch batch) {
   const SmallGemm& g = batch.p[blockIdx.y];
@@ -460,8 +461,7 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
                        csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.dt_if[l], w.dt_rpc[l],
                        d->n_rpc, N, E, B, H, st));
     // weight / bias gradients of the fused node linear (packed), data gradient
-    TRY(pert_gemm_tn(w.dplanes, H, H, N * (long long)H, w.x[l], K, 0, 0, w.dw4[l], K, N, 4 * H, K, st));
-    TRY(pert_colsum(w.dplanes, H, H, N * (long long)H, w.db4[l], N, 4 * H, st));
+    TRY(pert_gemm_tn(w.dplanes, H, H, N * (long long)H, w.x[l], K, 0, 0, w.dw4[l], K, w.db4[l], N, 4 * H, K, st));
     TRY(pert_gemm_nt(w.dplanes, H, H, N * (long long)H, w.w4t[l], 4 * H, nullptr, w.dx, K, 0, 0, N, K, 4 * H, 0, 0, st));
     if (l > 0) {
       // BN(+ReLU) backward of layer l-1: dx (grad wrt x[l]) -> g of conv l-1, into the skip plane

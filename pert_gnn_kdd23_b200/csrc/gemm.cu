@@ -239,7 +239,8 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
                     float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K, int relu,
                     cudaStream_t st);
 int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, int b_cb,
-                    long long b_cbs, float* C, int ldc, long long R, int Mc, int Nc, cudaStream_t st);
+                    long long b_cbs, float* C, int ldc, float* a_colsum, long long R, int Mc, int Nc,
+                    cudaStream_t st);
 
 extern "C" {
 
@@ -270,18 +271,23 @@ int pert_gemm_nt(const float* A, int lda, int a_cb, long long a_cbs, const float
 }
 
 int pert_gemm_tn(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, int b_cb,
-                 long long b_cbs, float* C, int ldc, long long R, int Mc, int Nc, void* stream) {
+                 long long b_cbs, float* C, int ldc, float* a_colsum, long long R, int Mc, int Nc, void* stream) {
   if (R < 0 || Mc <= 0 || Nc <= 0 || !A || !B || !C) return PERT_ERR_BADARG;
   if (a_cb <= 0) a_cb = Mc;
   if (b_cb <= 0) b_cb = Nc;
   if (R == 0) return PERT_OK;
   {
-    int rt = pert_gemm_tn_tc(A, lda, a_cb, a_cbs, B, ldb, b_cb, b_cbs, C, ldc, R, Mc, Nc, (cudaStream_t)stream);
+    int rt = pert_gemm_tn_tc(A, lda, a_cb, a_cbs, B, ldb, b_cb, b_cbs, C, ldc, a_colsum, R, Mc, Nc,
+                             (cudaStream_t)stream);
     if (rt != PERT_ERR_UNSUPPORTED) {
       if (rt) return rt;
       PERT_LAUNCH_CHECK();
       return PERT_OK;
     }
+  }
+  if (a_colsum) {
+    int rc = pert_colsum(A, lda, a_cb, a_cbs, a_colsum, R, Mc, stream);
+    if (rc) return rc;
   }
   const int vec_a = !(lda % 4 || a_cb % 4 || a_cbs % 4 || !al16(A));
   const int vec_b = !(ldb % 4 || b_cb % 4 || b_cbs % 4 || !al16(B));

@@ -113,7 +113,7 @@ class Engine:
 
     def launches_backward(self):
         L = self.n_convs
-        return 2 + 1 + 1 + L * 5 + (L - 1) * 2 + self.desc.n_cat + L + L
+        return 2 + 1 + 1 + L * 4 + (L - 1) * 2 + self.desc.n_cat + L + L
 
     def forward(self, x, cat_X, entry_id, probs, pnn, batch, index: GraphIndex, training):
         """-> (global_pred [B,1], local_pred [N,1]); keeps what backward needs in the workspace."""

@@ -81,7 +81,7 @@ def gemm_tn_raw(A, B, out):
     _, ldb, b_cb, b_cbs, R2, Nc = _blocked(B)
     assert R == R2 and out.shape == (Mc, Nc) and out.is_contiguous()
     with _timed("gemm_tn" if R >= 4096 else "gemm_tn_small"):
-        call("pert_gemm_tn", ptr(A), lda, a_cb, a_cbs, ptr(B), ldb, b_cb, b_cbs, ptr(out), out.stride(0), R, Mc,
+        call("pert_gemm_tn", ptr(A), lda, a_cb, a_cbs, ptr(B), ldb, b_cb, b_cbs, ptr(out), out.stride(0), None, R, Mc,
              Nc, stream())
     LAUNCHES["n"] += 1
     return out
