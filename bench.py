@@ -189,42 +189,61 @@ def cpu_baseline(cfg, budget_s=25.0):
                       "oracle = torch restatement of the reference's PyG 2.4.0 eager ops"}
 
 
-def scatter_max_bench(batch_dev, H, peak_gbs, iters=60):
-    """BASELINE metric kernel: segment-max of msg[E,H] (CSR order) -> out[N,H], L2 flushed between launches."""
+def scatter_max_bench(batch_dev, H, peak_gbs, iters=40):
+    """BASELINE metric kernel: segment-max of msg[E,H] (CSR order) -> out[N,H].
+
+    Two protocols, both with cold inputs: (a) "single": one launch between two events after a 512 MB L2 flush
+    (includes the ~3-5 us launch / event gap of a lone short kernel); (b) "train": TRAIN back-to-back launches over
+    ROT distinct message/output buffers whose total footprint exceeds L2 (inputs larger than L2, no flush), one
+    event pair around the train, divided by TRAIN -- the per-launch duration once the launch gap is amortised,
+    which is what the ncu gpu__time_duration of the same kernel shows.  `frac` is quoted from (b)."""
     from pert_gnn_kdd23_b200 import _lib
     from pert_gnn_kdd23_b200.index import build_index
 
     N, E = batch_dev.x.size(0), batch_dev.edge_index.size(1)
     gi = build_index(batch_dev.edge_index, N)
-    msg = torch.randn(E, H, device="cuda")
-    out = torch.empty(N, H, device="cuda")
+    bytes_alg = 4 * E * H + 4 * (N + 1) + 4 * N * H
+    ROT = max(4, int(3 * (160 << 20) // max(bytes_alg, 1)) + 1)     # >= 3 x 160 MB of distinct data in rotation
+    TRAIN = 2 * ROT
+    msgs = [torch.randn(E, H, device="cuda") for _ in range(ROT)]
+    outs = [torch.empty(N, H, device="cuda") for _ in range(ROT)]
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream()
 
-    def launch():
-        _lib.call("pert_segment_reduce_fwd", msg.data_ptr(), gi.rowptr.data_ptr(), None, out.data_ptr(), N, H, 1,
-                  st.cuda_stream)
+    def launch(i):
+        _lib.call("pert_segment_reduce_fwd", msgs[i % ROT].data_ptr(), gi.rowptr.data_ptr(), None,
+                  outs[i % ROT].data_ptr(), N, H, 1, st.cuda_stream)
 
-    res = {}
-    for mode in ("cold", "warm"):
-        ts = []
-        for i in range(iters + 5):
-            if mode == "cold":
-                flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st)
-            launch()
-            e1.record(st)
-            e1.synchronize()
-            if i >= 5:
-                ts.append(e0.elapsed_time(e1) * 1e-3)
-        res[mode] = statistics.median(ts)
-    bytes_alg = 4 * E * H + 4 * (N + 1) + 4 * N * H
-    ach = bytes_alg / res["cold"] / 1e9
-    return {"kernel": "k_segreduce<max> [E,H]->[N,H]", "bound": "hbm", "achieved": ach, "peak": peak_gbs,
-            "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None, "algorithmic_bytes": bytes_alg,
-            "us_cold": res["cold"] * 1e6, "us_warm": res["warm"] * 1e6,
-            "achieved_warm": bytes_alg / res["warm"] / 1e9, "shape": {"E": E, "N": N, "H": H}}
+    single = []
+    for i in range(iters + 5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        launch(i)
+        e1.record(st)
+        e1.synchronize()
+        if i >= 5:
+            single.append(e0.elapsed_time(e1) * 1e-3)
+    train = []
+    for rep in range(12):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for i in range(TRAIN):
+            launch(i)
+        e1.record(st)
+        e1.synchronize()
+        if rep >= 2:
+            train.append(e0.elapsed_time(e1) * 1e-3 / TRAIN)
+    t_single, t_train = statistics.median(single), statistics.median(train)
+    ach = bytes_alg / t_train / 1e9
+    return {"kernel": "k_segreduce_stream<max> [E,H]->[N,H] (TMA bulk + mbarrier pipeline)", "bound": "hbm",
+            "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None,
+            "algorithmic_bytes": bytes_alg, "us_per_launch": t_train * 1e6,
+            "protocol": f"{TRAIN} back-to-back launches over {ROT} distinct msg/out buffer pairs "
+                        f"({ROT * bytes_alg >> 20} MB > L2), event pair around the train, median of 10",
+            "us_single_launch_after_l2_flush": t_single * 1e6,
+            "achieved_single_launch": bytes_alg / t_single / 1e9, "shape": {"E": E, "N": N, "H": H}}
 
 
 def run_b200(args, rank, world, local_rank):

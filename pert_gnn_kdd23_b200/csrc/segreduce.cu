@@ -148,6 +148,9 @@ int dispatch_w(int H, F&& f) {
 
 }  // namespace
 
+int pert_segreduce_stream(const float* msg, const int* rowptr, float* out, long long N, int H, int op,
+                          cudaStream_t st);
+
 extern "C" {
 
 // op: 0 = sum, 1 = max.  perm may be null (msg already in CSR order).
@@ -157,6 +160,14 @@ int pert_segment_reduce_fwd(const float* msg, const int* rowptr, const int* perm
   if (N == 0) return PERT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = PERT_ERR_UNSUPPORTED;
+  if (!perm) {   // CSR-ordered messages: TMA-pipelined streaming kernel (segreduce_tma.cu)
+    rc = pert_segreduce_stream(msg, rowptr, out, N, H, op, st);
+    if (rc == PERT_OK) {
+      PERT_LAUNCH_CHECK();
+      return PERT_OK;
+    }
+    if (rc != PERT_ERR_UNSUPPORTED) return rc;
+  }
   if ((((uintptr_t)msg | (uintptr_t)out) & 15) == 0) {
     rc = dispatch_w(H, [&](auto lpr, auto vpl) {
       constexpr int LPR = decltype(lpr)::value, VPL = decltype(vpl)::value;
