@@ -1,23 +1,25 @@
 // Shared-memory-staged variant of the fused TransformerConv kernels (see tconv.cu for the math).
 //
-// Why: the per-row gather kernels are bound by L2->SM traffic and latency, not by HBM: every k/v row is fetched
-// once per out-edge (~3x) and L1 catches only ~35-50 % of that (r1 ncu: 19 M instructions, 70 % of issue cycles
-// with no eligible warp, DRAM bytes == algorithmic bytes at 10 % of peak).  Batched call graphs are graph-major:
-// all neighbours of a node live within a few hundred rows of it.  So a CTA takes a TILE of consecutive nodes,
-// pulls the tile's k and v rows (contiguous in the plane layout) into shared memory with two TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx: no per-thread loads, no register staging), stages the tile's CSR index
-// slices next to them, and gathers neighbours from shared memory (~30-cycle latency, 32-bit addressing).
-// Each k/v row is read from L2/HBM once per tile; sources outside the tile (a graph cut by a tile
-// boundary, graphs larger than a tile) fall back to the global gather.  Same semantics, same outputs.
+// Why: the per-row gather kernels are bound by L2->SM traffic, latency and instruction issue, not by HBM: every
+// k/v row is fetched once per out-edge (~3x), L1 catches only ~35-50 % of that, and the predicated 4-edge register
+// blocks cost 19 M instructions per launch at cfg2 (r1 ncu: 70 % of issue cycles without an eligible warp, DRAM at
+// 10 % with bytes == algorithmic bytes).  Batched call graphs are graph-major: all neighbours of a node live within a
+// few hundred rows of it.  So a CTA takes a TILE of consecutive nodes, pulls the tile's two operand planes (k and v
+// forward / target pass, g and q in the source pass -- contiguous in the plane layout) into shared memory with two
+// TMA bulk copies (cp.async.bulk + mbarrier complete_tx: no per-thread loads, no register staging), stages the
+// tile's CSR (or CSC) index slices and per-edge scalars next to them, and walks each node's edges one by one
+// against shared memory (~30-cycle latency, 32-bit addressing, no padding slots), with the one remaining global
+// gather (the interface-table row) prefetched one edge ahead.  Each operand row is read from L2/HBM once per tile;
+// neighbours outside the tile (a graph cut by a tile boundary, graphs larger than a tile) fall back to the global
+// gather.  Same semantics, same outputs as tconv.cu.
 //
-// Tile size (nodes) is chosen by the host so that 2*T*H*4 bytes of k/v tiles (+ indices) fit the smem budget.
+// Tile size (nodes) is chosen by the host so that two CTAs of 512 threads fit one SM; when the batch holds equally
+// sized graphs the tile is a whole number of graphs (no cut edges).
 #include "common.cuh"
-#include <type_traits>
 
 namespace {
 
-constexpr int CHUNK = 4;           // edges processed together (all their rows in flight / in registers)
-constexpr int TILE_THREADS = 256;
+constexpr int TILE_THREADS = 512;
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,100 +50,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-
-template <int VPL>
-struct Row {
-  float4 v[VPL];
-};
-template <int LPR, int VPL>
-__device__ __forceinline__ Row<VPL> grow(const float* __restrict__ base, int ld, int row, int lig) {
-  Row<VPL> r;
-  const float* p = base + (size_t)row * ld + lig * 4;
-#pragma unroll
-  for (int u = 0; u < VPL; ++u) r.v[u] = ldg4(p + u * LPR * 4);
-  return r;
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-template <int LPR, int VPL>
-__device__ __forceinline__ Row<VPL> grow_if(bool pred, const float* __restrict__ base, int ld, int row, int lig) {
-  Row<VPL> r;
-  const float* p = base + (size_t)row * ld + lig * 4;
-#pragma unroll
-  for (int u = 0; u < VPL; ++u) r.v[u] = pred ? ldg4(p + u * LPR * 4) : f4zero();
-  return r;
-}
-// row of a staged tile (shared memory) or, when the node is outside the tile, of the global plane
-template <int LPR, int VPL>
-__device__ __forceinline__ Row<VPL> trow(bool on, const float* s_tile, const float* __restrict__ gbase, int ld, int n0,
-                                         int nt, int node, int lig) {
-  constexpr int H = 4 * LPR * VPL;
-  Row<VPL> r;
-  const unsigned loc = (unsigned)(node - n0);
-  if (loc < (unsigned)nt) {
-    const float* p = s_tile + loc * H + lig * 4;
-#pragma unroll
-    for (int u = 0; u < VPL; ++u) r.v[u] = on ? *reinterpret_cast<const float4*>(p + u * LPR * 4) : f4zero();
-  } else {
-    const float* p = gbase + (size_t)node * ld + lig * 4;
-#pragma unroll
-    for (int u = 0; u < VPL; ++u) r.v[u] = on ? ldg4(p + u * LPR * 4) : f4zero();
-  }
-  return r;
-}
-template <int LPR, int VPL>
-__device__ __forceinline__ void srow(float* __restrict__ base, int ld, int row, int lig, const Row<VPL>& r) {
-  float* p = base + (size_t)row * ld + lig * 4;
-#pragma unroll
-  for (int u = 0; u < VPL; ++u) st4(p + u * LPR * 4, r.v[u]);
-}
-template <int VPL>
-__device__ __forceinline__ Row<VPL> radd(const Row<VPL>& a, const Row<VPL>& b) {
-  Row<VPL> r;
-#pragma unroll
-  for (int u = 0; u < VPL; ++u) r.v[u] = f4add(a.v[u], b.v[u]);
-  return r;
-}
-template <int VPL>
-__device__ __forceinline__ float rdot(const Row<VPL>& a, const Row<VPL>& b) {
-  float s = 0.f;
-#pragma unroll
-  for (int u = 0; u < VPL; ++u) s += f4dot(a.v[u], b.v[u]);
-  return s;
-}
-template <int VPL>
-__device__ __forceinline__ void rfma(float s, const Row<VPL>& a, Row<VPL>& acc) {
-#pragma unroll
-  for (int u = 0; u < VPL; ++u) acc.v[u] = f4fma(s, a.v[u], acc.v[u]);
-}
-template <int VPL>
-__device__ __forceinline__ Row<VPL> rzero() {
-  Row<VPL> r;
-#pragma unroll
-  for (int u = 0; u < VPL; ++u) r.v[u] = f4zero();
-  return r;
-}
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 struct TileArgs {
-  // planes / rows (row stride ld unless noted)
-  const float *q, *k, *v, *s;
-  int ld;
-  const float* g;  // backward: dL/dout
-  int ld_g;
+  const float *q, *k, *v, *s;   // planes, dense rows (ld == H)
+  const float* g;               // backward: dL/dout, dense rows
   const int *rowptr, *csr_src, *csr_if, *csr_rpc;
   const int *colptr, *csc_pos, *csc_dst;
   const float *t_if, *t_rpc;
   int n_rpc;
-  float* out;   // fwd: out rows; bwd_dst: dq rows
-  int ld_out;
-  float *dk, *dv;  // bwd_src
-  float* alpha;    // fwd: written; bwd: read
-  float* dsp;      // bwd_dst: written; bwd_src: read
+  float* out;       // fwd: out rows; bwd_dst: dq rows (dense)
+  float *dk, *dv;   // bwd_src
+  float* alpha;     // fwd: written; bwd: read
+  float* dsp;       // bwd_dst: written; bwd_src: read
   float *dt_if, *dt_rpc;
   int N, tile_nodes, edge_cap;
   float inv_sqrt_c;
 };
 
-// dynamic smem layout, shared by the three kernels (NI int and NF float per-edge arrays, kernel specific):
-//   [bar 16 B][tile A: T*H][tile B: T*H][rpc table: n_rpc*H][rowptr/colptr slice: T+1][NI x ecap ints][NF x ecap floats]
+// dynamic smem layout shared by the three kernels (NA per-edge 4-byte arrays, kernel specific):
+//   [bar 16 B][tile A: T*H][tile B: T*H][rpc table (source pass only): n_rpc*H][row/col ptr slice: T+1][NA x ecap]
 // attribute ids are staged packed: interface id | rpc id << 22
 #define PACK_ID(a, b) ((a) | ((b) << 22))
 #define ID_IF(x) ((x) & 0x3fffff)
@@ -162,7 +95,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base, int T, int H, in
   s.ptr = reinterpret_cast<int*>(f); f += ((T + 1 + 3) / 4) * 4;
   s.e0 = reinterpret_cast<int*>(f); f += ecap;
   s.e1 = reinterpret_cast<int*>(f); f += ecap;
-  s.f0 = f; f += ecap;       // only the first NI+NF arrays are backed by memory (see smem_bytes)
+  s.f0 = f; f += ecap;       // only the first NA arrays are backed by memory (see smem_bytes)
   s.f1 = f;
   return s;
 }
@@ -171,16 +104,10 @@ static size_t smem_bytes(int T, int H, int n_rpc, int ecap, int n_edge_arrays) {
                                (size_t)n_edge_arrays * ecap);
 }
 
-// ============================================================== forward
-template <int LPR, int VPL, bool HAS_E>
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
-  constexpr int H = 4 * LPR * VPL;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int T = a.tile_nodes;
-  const Smem S = carve_smem(smem_raw, T, H, HAS_E ? a.n_rpc : 0, a.edge_cap);
-  const int n0 = blockIdx.x * T;
-  const int nt = min(T, a.N - n0);
-  const int tid = threadIdx.x;
+// stage the two operand tiles + the node-pointer slice; returns after the pointers are visible (tiles: mbar_wait)
+template <int H>
+__device__ __forceinline__ void stage_tiles(const Smem& S, const float* pa, const float* pb, const int* nodeptr,
+                                            int n0, int nt, int tid) {
   if (tid == 0) {
     mbar_init(S.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -188,18 +115,65 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
   __syncthreads();
   if (tid == 0) {
     const uint32_t tile_bytes = (uint32_t)nt * H * 4;
-    const uint32_t rpc_bytes = HAS_E ? (uint32_t)a.n_rpc * H * 4 : 0;
-    mbar_expect_tx(S.bar, 2 * tile_bytes + rpc_bytes);
-    bulk_g2s(S.ta, a.k + (size_t)n0 * a.ld, tile_bytes, S.bar);   // planes are dense: ld == H (checked on host)
-    bulk_g2s(S.tb, a.v + (size_t)n0 * a.ld, tile_bytes, S.bar);
-    if (HAS_E) bulk_g2s(S.rpc, a.t_rpc, rpc_bytes, S.bar);
+    mbar_expect_tx(S.bar, 2 * tile_bytes);
+    bulk_g2s(S.ta, pa + (size_t)n0 * H, tile_bytes, S.bar);
+    bulk_g2s(S.tb, pb + (size_t)n0 * H, tile_bytes, S.bar);
   }
-  // index slices of the tile (coalesced), overlapped with the bulk copies
-  for (int x = tid; x <= nt; x += TILE_THREADS) S.ptr[x] = __ldg(a.rowptr + n0 + x);
+  for (int x = tid; x <= nt; x += TILE_THREADS) S.ptr[x] = __ldg(nodeptr + n0 + x);
   __syncthreads();
+}
+
+// ---------------------------------------------------------------- explicit shared-space accessors (32-bit addresses:
+// keeps the compiler from falling back to generic loads + cluster-address checks inside the edge loops)
+__device__ __forceinline__ float4 lds4s(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int ldsi(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float ldsf(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void stsf(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+template <int LPR>
+__device__ __forceinline__ float gsum_full(float v) {   // butterfly inside each LPR-lane group, whole warp converged
+#pragma unroll
+  for (int off = LPR >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+struct SAddr {   // shared-space byte addresses of the staged arrays
+  uint32_t ta, tb, rpc, ptr, e0, e1, f0, f1;
+};
+__device__ __forceinline__ SAddr saddr_of(const Smem& S) {
+  SAddr s;
+  s.ta = smem_u32(S.ta); s.tb = smem_u32(S.tb); s.rpc = smem_u32(S.rpc); s.ptr = smem_u32(S.ptr);
+  s.e0 = smem_u32(S.e0); s.e1 = smem_u32(S.e1); s.f0 = smem_u32(S.f0); s.f1 = smem_u32(S.f1);
+  return s;
+}
+
+// All lane groups of a warp walk their nodes' edges in lockstep (trip count = the warp's max degree, finished groups
+// contribute zeros), so shuffles use the full mask and no per-group branch divergence bookkeeping is generated.
+
+// ============================================================== forward
+template <int LPR, bool HAS_E>
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
+  constexpr int H = 4 * LPR;
+  constexpr int GPW = 32 / LPR;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int T = a.tile_nodes;
+  const Smem S = carve_smem(smem_raw, T, H, 0, a.edge_cap);
+  const int n0 = blockIdx.x * T;
+  const int nt = min(T, a.N - n0);
+  const int tid = threadIdx.x;
+  stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
   const int e_lo = S.ptr[0];
-  const int ne = S.ptr[nt] - e_lo;
-  const int ne_s = min(ne, a.edge_cap);
+  const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
   for (int x = tid; x < ne_s; x += TILE_THREADS) {
     S.e0[x] = __ldg(a.csr_src + e_lo + x);
     if (HAS_E) S.e1[x] = PACK_ID(__ldg(a.csr_if + e_lo + x), __ldg(a.csr_rpc + e_lo + x));
@@ -207,107 +181,116 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
   __syncthreads();
   mbar_wait(S.bar, 0);
 
+  const SAddr sa = saddr_of(S);
   const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
   constexpr int GPC = TILE_THREADS / LPR;  // lane groups per CTA
-  const int g_in_cta = (tid >> 5) * (32 / LPR) + grp;
-  for (int loc = g_in_cta; loc < nt; loc += GPC) {
+  const float qscale = a.inv_sqrt_c * 1.4426950408889634f;   // logits kept in log2 units: exp(x) = 2^(x*log2 e)
+  const uint32_t lane4 = lig * 16;
+  const int g0 = (tid >> 5) * GPW;          // first group of this warp
+  // q / skip rows of the next node are requested one node ahead
+  int loc = g0 + grp;
+  float4 q_n = f4zero(), s_n = f4zero();
+  if (loc < nt) {
+    q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
+    if (a.s) s_n = ldg4(a.s + (size_t)(n0 + loc) * H + lig * 4);
+  }
+  for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {   // warp-uniform: the warp's first group still has a node
+    const bool valid = loc < nt;
     const int i = n0 + loc;
-    const int p0 = S.ptr[loc], p1 = S.ptr[loc + 1];
-    const Row<VPL> q = grow<LPR, VPL>(a.q, a.ld, i, lig);
-    const Row<VPL> skip = a.s ? grow<LPR, VPL>(a.s, a.ld, i, lig) : rzero<VPL>();
-    const bool staged = (p1 - p0) > CHUNK;
-    Row<VPL> acc = rzero<VPL>();
+    const float4 q = f4scale(qscale, q_n);
+    const float4 skip = s_n;
+    if (loc + GPC < nt) {
+      q_n = ldg4(a.q + (size_t)(i + GPC) * H + lig * 4);
+      if (a.s) s_n = ldg4(a.s + (size_t)(i + GPC) * H + lig * 4);
+    }
+    const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
+    const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
+    const int deg = p1 - p0;
+    const int degmax = __reduce_max_sync(0xffffffffu, deg);
+    float4 acc = f4zero();
     float m = -INFINITY, Z = 0.f;
-    for (int c0 = p0; c0 < p1; c0 += CHUNK) {
-      const int deg = p1 - c0;
-      int j[CHUNK], ia[CHUNK], ib[CHUNK];
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        const bool on = x < deg;
-        const int le = c0 + x - e_lo;           // position inside the staged slice
-        const bool in_s = le < ne_s;
-        j[x] = on ? (in_s ? S.e0[le] : __ldg(a.csr_src + c0 + x)) : n0;
-        ia[x] = (on && HAS_E) ? (in_s ? ID_IF(S.e1[le]) : __ldg(a.csr_if + c0 + x)) : 0;
-        ib[x] = (on && HAS_E) ? (in_s ? ID_RPC(S.e1[le]) : __ldg(a.csr_rpc + c0 + x)) : 0;
-      }
-      Row<VPL> kj[CHUNK], vj[CHUNK], ei[CHUNK];
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        const bool on = x < deg;
-        ei[x] = grow_if<LPR, VPL>(on && HAS_E, a.t_if, H, ia[x], lig);        // global (L1/L2-resident table)
-        kj[x] = trow<LPR, VPL>(on, S.ta, a.k, a.ld, n0, nt, j[x], lig);
-        vj[x] = trow<LPR, VPL>(on, S.tb, a.v, a.ld, n0, nt, j[x], lig);
-      }
-      float s[CHUNK];
-      float m_new = m;
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        if (HAS_E) {
-          const float* pr = S.rpc + ib[x] * H + lig * 4;
-#pragma unroll
-          for (int u = 0; u < VPL; ++u) {
-            const float4 e = f4add(ei[x].v[u], *reinterpret_cast<const float4*>(pr + u * LPR * 4));
-            kj[x].v[u] = f4add(kj[x].v[u], e);
-            vj[x].v[u] = f4add(vj[x].v[u], e);
-          }
+    // software pipeline over edges: ids + table rows of edge t+1 are requested before edge t is consumed
+    int j = n0, id = 0;
+    float4 eif = f4zero(), erp = f4zero();
+    auto fetch = [&](int p, bool on) {
+      j = n0;
+      id = 0;
+      if (on) {
+        const int le = p - e_lo;
+        if (le < ne_s) {
+          j = ldsi(sa.e0 + le * 4);
+          if (HAS_E) id = ldsi(sa.e1 + le * 4);
+        } else {
+          j = __ldg(a.csr_src + p);
+          if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
         }
-        s[x] = group_sum<LPR>(rdot(q, kj[x]), gmask) * a.inv_sqrt_c;
-        if (x < deg) m_new = fmaxf(m_new, s[x]);
       }
-      const float scale = __expf(m - m_new);
-      Z *= scale;
-#pragma unroll
-      for (int u = 0; u < VPL; ++u) acc.v[u] = f4scale(scale, acc.v[u]);
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        const float pz = (x < deg) ? expf(s[x] - m_new) : 0.f;
-        Z += pz;
-        rfma(pz, vj[x], acc);
-        if (lig == 0 && x < deg) a.alpha[c0 + x] = staged ? s[x] : pz;
+      if (HAS_E) {
+        eif = ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4);
+        erp = ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4);
       }
-      m = m_new;
+    };
+    fetch(p0, 0 < deg);
+    for (int t = 0; t < degmax; ++t) {
+      const bool on = t < deg;
+      const int p = p0 + t;
+      const int cj = j;
+      const float4 e = f4add(eif, erp);
+      fetch(p + 1, t + 1 < deg);
+      float4 kk, vv;
+      const unsigned sl = (unsigned)(cj - n0);
+      if (sl < (unsigned)nt) {
+        kk = lds4s(sa.ta + sl * (H * 4) + lane4);
+        vv = lds4s(sa.tb + sl * (H * 4) + lane4);
+      } else {
+        kk = ldg4(a.k + (size_t)cj * H + lig * 4);
+        vv = ldg4(a.v + (size_t)cj * H + lig * 4);
+      }
+      if (HAS_E) {
+        kk = f4add(kk, e);
+        vv = f4add(vv, e);
+      }
+      const float s = gsum_full<LPR>(f4dot(q, kk));
+      if (on && lig == 0) {
+        const int le = p - e_lo;
+        if (le < ne_s) stsf(sa.f0 + le * 4, s);
+        else a.alpha[p] = s;
+      }
+      const float mn = on ? fmaxf(m, s) : m;
+      const float sc = on ? ex2(m - mn) : 1.f;
+      const float pz = on ? ex2(s - mn) : 0.f;
+      Z = fmaf(Z, sc, pz);
+      acc.x = fmaf(pz, vv.x, acc.x * sc);
+      acc.y = fmaf(pz, vv.y, acc.y * sc);
+      acc.z = fmaf(pz, vv.z, acc.z * sc);
+      acc.w = fmaf(pz, vv.w, acc.w * sc);
+      m = mn;
     }
     const float invZ = 1.0f / (Z + 1e-16f);
-#pragma unroll
-    for (int u = 0; u < VPL; ++u) acc.v[u] = f4scale(invZ, acc.v[u]);
-    srow<LPR, VPL>(a.out, a.ld_out, i, lig, radd(acc, skip));
-    __syncwarp(gmask);
+    if (valid) st4(a.out + (size_t)i * H + lig * 4, f4add(f4scale(invZ, acc), skip));
+    __syncwarp();
     for (int p = p0 + lig; p < p1; p += LPR) {
-      const float v = a.alpha[p];
-      a.alpha[p] = (staged ? expf(v - m) : v) * invZ;
+      const int le = p - e_lo;
+      const float s = (le < ne_s) ? ldsf(sa.f0 + le * 4) : a.alpha[p];
+      a.alpha[p] = ex2(s - m) * invZ;
     }
   }
 }
 
 // ============================================================== backward, target pass (dq, ds)
-template <int LPR, int VPL, bool HAS_E>
+template <int LPR, bool HAS_E>
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
-  constexpr int H = 4 * LPR * VPL;
+  constexpr int H = 4 * LPR;
+  constexpr int GPW = 32 / LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int T = a.tile_nodes;
-  const Smem S = carve_smem(smem_raw, T, H, HAS_E ? a.n_rpc : 0, a.edge_cap);
+  const Smem S = carve_smem(smem_raw, T, H, 0, a.edge_cap);
   const int n0 = blockIdx.x * T;
   const int nt = min(T, a.N - n0);
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    mbar_init(S.bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t tile_bytes = (uint32_t)nt * H * 4;
-    const uint32_t rpc_bytes = HAS_E ? (uint32_t)a.n_rpc * H * 4 : 0;
-    mbar_expect_tx(S.bar, 2 * tile_bytes + rpc_bytes);
-    bulk_g2s(S.ta, a.k + (size_t)n0 * a.ld, tile_bytes, S.bar);
-    bulk_g2s(S.tb, a.v + (size_t)n0 * a.ld, tile_bytes, S.bar);
-    if (HAS_E) bulk_g2s(S.rpc, a.t_rpc, rpc_bytes, S.bar);
-  }
-  for (int x = tid; x <= nt; x += TILE_THREADS) S.ptr[x] = __ldg(a.rowptr + n0 + x);
-  __syncthreads();
+  stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
   const int e_lo = S.ptr[0];
-  const int ne = S.ptr[nt] - e_lo;
-  const int ne_s = min(ne, a.edge_cap);
+  const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
   for (int x = tid; x < ne_s; x += TILE_THREADS) {
     S.e0[x] = __ldg(a.csr_src + e_lo + x);
     S.f0[x] = __ldg(a.alpha + e_lo + x);
@@ -316,117 +299,98 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
   __syncthreads();
   mbar_wait(S.bar, 0);
 
+  const SAddr sa = saddr_of(S);
   const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
   constexpr int GPC = TILE_THREADS / LPR;
-  const int g_in_cta = (tid >> 5) * (32 / LPR) + grp;
-  for (int loc = g_in_cta; loc < nt; loc += GPC) {
+  const uint32_t lane4 = lig * 16;
+  const int g0 = (tid >> 5) * GPW;
+  int loc = g0 + grp;
+  float4 g_n = f4zero();
+  if (loc < nt) g_n = ldg4(a.g + (size_t)(n0 + loc) * H + lig * 4);
+  for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {
+    const bool valid = loc < nt;
     const int i = n0 + loc;
-    const int p0 = S.ptr[loc], p1 = S.ptr[loc + 1];
-    const Row<VPL> g = grow<LPR, VPL>(a.g, a.ld_g, i, lig);
-    Row<VPL> dq = rzero<VPL>();
-    const bool single = (p1 - p0) <= CHUNK;
-    // pass 1: dalpha_t = <g_i, v_j + e_t>, dot = sum alpha_t dalpha_t   (single chunk: everything stays in registers)
+    const float4 g = g_n;
+    if (loc + GPC < nt) g_n = ldg4(a.g + (size_t)(i + GPC) * H + lig * 4);
+    const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
+    const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
+    const int deg = p1 - p0;
+    const int degmax = __reduce_max_sync(0xffffffffu, deg);
+    // one edge record: source row offsets + e = T_if[a] + T_rpc[b]
+    auto edge = [&](int p, bool on, int& j, float& al, float4& e) {
+      j = n0;
+      al = 0.f;
+      int id = 0;
+      if (on) {
+        const int le = p - e_lo;
+        if (le < ne_s) {
+          j = ldsi(sa.e0 + le * 4);
+          al = ldsf(sa.f0 + le * 4);
+          if (HAS_E) id = ldsi(sa.e1 + le * 4);
+        } else {
+          j = __ldg(a.csr_src + p);
+          al = __ldg(a.alpha + p);
+          if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+        }
+      }
+      e = f4zero();
+      if (HAS_E)
+        e = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4), ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4));
+    };
+    // pass 1: dalpha_t = <g_i, v_j + e_t> (staged), dot = sum_t alpha_t dalpha_t
     float dot = 0.f;
-    float da1[CHUNK], al1[CHUNK];
-    Row<VPL> kj1[CHUNK];
-    for (int c0 = p0; c0 < p1; c0 += CHUNK) {
-      const int deg = p1 - c0;
-      int j[CHUNK], ia[CHUNK], ib[CHUNK];
-      float al[CHUNK];
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        const bool on = x < deg;
-        const int le = c0 + x - e_lo;
-        const bool in_s = le < ne_s;
-        j[x] = on ? (in_s ? S.e0[le] : __ldg(a.csr_src + c0 + x)) : n0;
-        al[x] = on ? (in_s ? S.f0[le] : __ldg(a.alpha + c0 + x)) : 0.f;
-        ia[x] = (on && HAS_E) ? (in_s ? ID_IF(S.e1[le]) : __ldg(a.csr_if + c0 + x)) : 0;
-        ib[x] = (on && HAS_E) ? (in_s ? ID_RPC(S.e1[le]) : __ldg(a.csr_rpc + c0 + x)) : 0;
-      }
-      Row<VPL> vj[CHUNK], ei[CHUNK];
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        const bool on = x < deg;
-        ei[x] = grow_if<LPR, VPL>(on && HAS_E, a.t_if, H, ia[x], lig);
-        vj[x] = trow<LPR, VPL>(on, S.tb, a.v, a.ld, n0, nt, j[x], lig);
-        if (single) kj1[x] = trow<LPR, VPL>(on, S.ta, a.k, a.ld, n0, nt, j[x], lig);
-      }
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        if (HAS_E) {
-          const float* pr = S.rpc + ib[x] * H + lig * 4;
-#pragma unroll
-          for (int u = 0; u < VPL; ++u) {
-            const float4 e = f4add(ei[x].v[u], *reinterpret_cast<const float4*>(pr + u * LPR * 4));
-            vj[x].v[u] = f4add(vj[x].v[u], e);
-            if (single) kj1[x].v[u] = f4add(kj1[x].v[u], e);
-          }
-        }
-        const float da = group_sum<LPR>(rdot(g, vj[x]), gmask);
-        dot = fmaf(al[x], da, dot);
-        if (single) {
-          da1[x] = da;
-          al1[x] = al[x];
-        } else if (lig == 0 && x < deg) {
-          a.dsp[c0 + x] = da;     // staged for pass 2
-        }
+    for (int t = 0; t < degmax; ++t) {
+      const bool on = t < deg;
+      const int p = p0 + t;
+      int j;
+      float al;
+      float4 e;
+      edge(p, on, j, al, e);
+      float4 vv;
+      const unsigned sl = (unsigned)(j - n0);
+      if (sl < (unsigned)nt) vv = lds4s(sa.tb + sl * (H * 4) + lane4);
+      else vv = ldg4(a.v + (size_t)j * H + lig * 4);
+      const float da = gsum_full<LPR>(f4dot(g, f4add(vv, e)));
+      dot = fmaf(al, da, dot);
+      if (on && lig == 0) {
+        const int le = p - e_lo;
+        if (le < ne_s) stsf(sa.f1 + le * 4, da);
+        else a.dsp[p] = da;
       }
     }
-    if (single) {
-      const int deg = p1 - p0;
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        const float ds = (x < deg) ? al1[x] * (da1[x] - dot) * a.inv_sqrt_c : 0.f;
-        if (x < deg) rfma(ds, kj1[x], dq);
-        if (lig == 0 && x < deg) a.dsp[p0 + x] = ds;
+    __syncwarp();
+    // pass 2: ds_t = alpha_t (dalpha_t - dot) / sqrt(C);  dq_i = sum_t ds_t (k_j + e_t)
+    float4 dq = f4zero();
+    for (int t = 0; t < degmax; ++t) {
+      const bool on = t < deg;
+      const int p = p0 + t;
+      int j;
+      float al;
+      float4 e;
+      edge(p, on, j, al, e);
+      float4 kk;
+      const unsigned sl = (unsigned)(j - n0);
+      if (sl < (unsigned)nt) kk = lds4s(sa.ta + sl * (H * 4) + lane4);
+      else kk = ldg4(a.k + (size_t)j * H + lig * 4);
+      float da = 0.f;
+      if (on) {
+        const int le = p - e_lo;
+        da = (le < ne_s) ? ldsf(sa.f1 + le * 4) : a.dsp[p];
       }
-    } else {
-      __syncwarp(gmask);
-      for (int c0 = p0; c0 < p1; c0 += CHUNK) {
-        const int deg = p1 - c0;
-        int j[CHUNK], ia[CHUNK], ib[CHUNK];
-        float ds[CHUNK];
-#pragma unroll
-        for (int x = 0; x < CHUNK; ++x) {
-          const bool on = x < deg;
-          const int le = c0 + x - e_lo;
-          const bool in_s = le < ne_s;
-          j[x] = on ? (in_s ? S.e0[le] : __ldg(a.csr_src + c0 + x)) : n0;
-          const float al = on ? (in_s ? S.f0[le] : __ldg(a.alpha + c0 + x)) : 0.f;
-          ds[x] = on ? al * (a.dsp[c0 + x] - dot) * a.inv_sqrt_c : 0.f;
-          ia[x] = (on && HAS_E) ? (in_s ? ID_IF(S.e1[le]) : __ldg(a.csr_if + c0 + x)) : 0;
-          ib[x] = (on && HAS_E) ? (in_s ? ID_RPC(S.e1[le]) : __ldg(a.csr_rpc + c0 + x)) : 0;
-        }
-        Row<VPL> kj[CHUNK], ei[CHUNK];
-#pragma unroll
-        for (int x = 0; x < CHUNK; ++x) {
-          const bool on = x < deg;
-          ei[x] = grow_if<LPR, VPL>(on && HAS_E, a.t_if, H, ia[x], lig);
-          kj[x] = trow<LPR, VPL>(on, S.ta, a.k, a.ld, n0, nt, j[x], lig);
-        }
-        __syncwarp(gmask);
-#pragma unroll
-        for (int x = 0; x < CHUNK; ++x) {
-          if (HAS_E) {
-            const float* pr = S.rpc + ib[x] * H + lig * 4;
-#pragma unroll
-            for (int u = 0; u < VPL; ++u)
-              kj[x].v[u] = f4add(kj[x].v[u], f4add(ei[x].v[u], *reinterpret_cast<const float4*>(pr + u * LPR * 4)));
-          }
-          rfma(ds[x], kj[x], dq);
-          if (lig == 0 && x < deg) a.dsp[c0 + x] = ds[x];
-        }
-      }
+      const float ds = al * (da - dot) * a.inv_sqrt_c;
+      dq = f4fma(ds, f4add(kk, e), dq);
+      __syncwarp();                      // all lanes have read a.dsp[p] (overflow path) before lane 0 rewrites it
+      if (on && lig == 0) a.dsp[p] = ds;
     }
-    srow<LPR, VPL>(a.out, a.ld_out, i, lig, dq);
+    if (valid) st4(a.out + (size_t)i * H + lig * 4, dq);
   }
 }
 
 // ============================================================== backward, source pass (dk, dv, table grads)
-template <int LPR, int VPL, bool HAS_E>
+template <int LPR, bool HAS_E>
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
-  constexpr int H = 4 * LPR * VPL;
+  constexpr int H = 4 * LPR;
+  constexpr int GPW = 32 / LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int T = a.tile_nodes;
   const Smem S = carve_smem(smem_raw, T, H, HAS_E ? a.n_rpc : 0, a.edge_cap);
@@ -434,24 +398,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   const int nt = min(T, a.N - n0);
   const int tid = threadIdx.x;
   float* s_drpc = S.rpc;   // privatised gradient of the rpc-type table (few hot rows), flushed once per CTA
-  if (tid == 0) {
-    mbar_init(S.bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   if (HAS_E)
     for (int x = tid; x < a.n_rpc * H; x += TILE_THREADS) s_drpc[x] = 0.f;
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t tile_bytes = (uint32_t)nt * H * 4;
-    mbar_expect_tx(S.bar, 2 * tile_bytes);
-    bulk_g2s(S.ta, a.g + (size_t)n0 * a.ld_g, tile_bytes, S.bar);   // g and q tiles (targets live in the same graph)
-    bulk_g2s(S.tb, a.q + (size_t)n0 * a.ld, tile_bytes, S.bar);
-  }
-  for (int x = tid; x <= nt; x += TILE_THREADS) S.ptr[x] = __ldg(a.colptr + n0 + x);
-  __syncthreads();
+  stage_tiles<H>(S, a.g, a.q, a.colptr, n0, nt, tid);   // targets of a node's out-edges live in the same graph
   const int c_lo = S.ptr[0];
-  const int ne = S.ptr[nt] - c_lo;
-  const int ne_s = min(ne, a.edge_cap);
+  const int ne_s = min(S.ptr[nt] - c_lo, a.edge_cap);
   // per out-edge (CSC order): target, and through the CSR slot its alpha, ds and attribute ids
   for (int x = tid; x < ne_s; x += TILE_THREADS) {
     const int p = __ldg(a.csc_pos + c_lo + x);
@@ -463,65 +414,60 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   __syncthreads();
   mbar_wait(S.bar, 0);
 
+  const SAddr sa = saddr_of(S);
   const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
   constexpr int GPC = TILE_THREADS / LPR;
-  const int g_in_cta = (tid >> 5) * (32 / LPR) + grp;
-  for (int loc = g_in_cta; loc < nt; loc += GPC) {
+  const uint32_t lane4 = lig * 16;
+  const int g0 = (tid >> 5) * GPW;
+  for (int loc = g0 + grp; g0 + (loc - g0 - grp) < nt; loc += GPC) {
+    const bool valid = loc < nt;
     const int jn = n0 + loc;
-    const int c0n = S.ptr[loc], c1n = S.ptr[loc + 1];
-    Row<VPL> dk = rzero<VPL>(), dv = rzero<VPL>();
-    for (int cc = c0n; cc < c1n; cc += CHUNK) {
-      const int deg = c1n - cc;
-      int i[CHUNK], ia[CHUNK], ib[CHUNK];
-      float al[CHUNK], ds[CHUNK];
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        const bool on = x < deg;
-        const int le = cc + x - c_lo;
+    const int c0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
+    const int c1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
+    const int deg = c1 - c0;
+    const int degmax = __reduce_max_sync(0xffffffffu, deg);
+    float4 dk = f4zero(), dv = f4zero();
+    for (int t = 0; t < degmax; ++t) {
+      const bool on = t < deg;
+      const int c = c0 + t;
+      int i = n0, id = 0;
+      float al = 0.f, ds = 0.f;
+      if (on) {
+        const int le = c - c_lo;
         if (le < ne_s) {
-          i[x] = on ? S.e0[le] : n0;
-          al[x] = on ? S.f0[le] : 0.f;
-          ds[x] = on ? S.f1[le] : 0.f;
-          ia[x] = (on && HAS_E) ? ID_IF(S.e1[le]) : 0;
-          ib[x] = (on && HAS_E) ? ID_RPC(S.e1[le]) : 0;
+          i = ldsi(sa.e0 + le * 4); al = ldsf(sa.f0 + le * 4); ds = ldsf(sa.f1 + le * 4);
+          if (HAS_E) id = ldsi(sa.e1 + le * 4);
         } else {
-          const int p = on ? __ldg(a.csc_pos + cc + x) : 0;
-          i[x] = on ? __ldg(a.csc_dst + cc + x) : n0;
-          al[x] = on ? __ldg(a.alpha + p) : 0.f;
-          ds[x] = on ? __ldg(a.dsp + p) : 0.f;
-          ia[x] = (on && HAS_E) ? __ldg(a.csr_if + p) : 0;
-          ib[x] = (on && HAS_E) ? __ldg(a.csr_rpc + p) : 0;
+          const int p = __ldg(a.csc_pos + c);
+          i = __ldg(a.csc_dst + c); al = __ldg(a.alpha + p); ds = __ldg(a.dsp + p);
+          if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
         }
       }
-      Row<VPL> gi[CHUNK], qi[CHUNK];
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        const bool on = x < deg;
-        gi[x] = trow<LPR, VPL>(on, S.ta, a.g, a.ld_g, n0, nt, i[x], lig);
-        qi[x] = trow<LPR, VPL>(on, S.tb, a.q, a.ld, n0, nt, i[x], lig);
+      float4 gi, qi;
+      const unsigned sl = (unsigned)(i - n0);
+      if (sl < (unsigned)nt) {
+        gi = lds4s(sa.ta + sl * (H * 4) + lane4);
+        qi = lds4s(sa.tb + sl * (H * 4) + lane4);
+      } else {
+        gi = ldg4(a.g + (size_t)i * H + lig * 4);
+        qi = ldg4(a.q + (size_t)i * H + lig * 4);
       }
-#pragma unroll
-      for (int x = 0; x < CHUNK; ++x) {
-        rfma(ds[x], qi[x], dk);
-        rfma(al[x], gi[x], dv);
-        if (HAS_E && x < deg) {
-          float* pif = a.dt_if + (size_t)ia[x] * H + lig * 4;
-          float* prp = s_drpc + ib[x] * H + lig * 4;
-#pragma unroll
-          for (int u = 0; u < VPL; ++u) {
-            float4 de = f4scale(al[x], gi[x].v[u]);
-            de = f4fma(ds[x], qi[x].v[u], de);
-            red4(pif + u * LPR * 4, de);
-            atomicAdd(prp + u * LPR * 4 + 0, de.x);
-            atomicAdd(prp + u * LPR * 4 + 1, de.y);
-            atomicAdd(prp + u * LPR * 4 + 2, de.z);
-            atomicAdd(prp + u * LPR * 4 + 3, de.w);
-          }
-        }
+      dk = f4fma(ds, qi, dk);
+      dv = f4fma(al, gi, dv);
+      if (HAS_E && on) {
+        const float4 de = f4fma(ds, qi, f4scale(al, gi));
+        red4(a.dt_if + (size_t)ID_IF(id) * H + lig * 4, de);
+        float* prp = s_drpc + ID_RPC(id) * H + lig * 4;
+        atomicAdd(prp + 0, de.x);
+        atomicAdd(prp + 1, de.y);
+        atomicAdd(prp + 2, de.z);
+        atomicAdd(prp + 3, de.w);
       }
     }
-    srow<LPR, VPL>(a.dk, a.ld_out, jn, lig, dk);
-    srow<LPR, VPL>(a.dv, a.ld_out, jn, lig, dv);
+    if (valid) {
+      st4(a.dk + (size_t)jn * H + lig * 4, dk);
+      st4(a.dv + (size_t)jn * H + lig * 4, dv);
+    }
   }
   if (HAS_E) {
     __syncthreads();
@@ -529,16 +475,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
       const float v = s_drpc[x];
       if (v != 0.f) atomicAdd(a.dt_rpc + x, v);
     }
-  }
-}
-
-template <typename F>
-int dispatch_tile(int H, F&& f) {
-  switch (H) {
-    case 32: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
-    case 64: return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 1>{});
-    case 128: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 1>{});
-    default: return PERT_ERR_UNSUPPORTED;
   }
 }
 
@@ -552,8 +488,8 @@ struct TileGeom {
 TileGeom tile_geom(int H, int n_rpc, long long N, long long E, long long B, int n_edge_arrays) {
   const double budget2 = 115712.0, budget1 = 231424.0;
   const double deg = N > 0 ? (double)E / (double)N : 1.0;
-  const double per_node = 4.0 * (2.0 * H + 1.0 + n_edge_arrays * deg * 1.03);
-  const double fixed = 64.0 + 4.0 * n_rpc * H + 4.0 * n_edge_arrays * 48.0;
+  const double per_node = 4.0 * (2.0 * H + 1.0 + n_edge_arrays * deg * 1.02);
+  const double fixed = 64.0 + 4.0 * n_rpc * H + 4.0 * n_edge_arrays * 20.0;
   auto fit = [&](double b) { return (long long)((b - fixed) / per_node); };
   long long T = fit(budget2);
   const long long G = (B > 0 && N % B == 0) ? N / B : 0;   // uniform graph size, if any
@@ -561,7 +497,7 @@ TileGeom tile_geom(int H, int n_rpc, long long N, long long E, long long B, int 
   if (G > 0 && G <= T) T = T / G * G;
   if (T > N) T = N;
   if (T < 1) T = 1;
-  int ecap = (int)(deg * 1.03 * (double)T) + 48;
+  int ecap = (int)(deg * 1.02 * (double)T) + 20;
   ecap = (ecap + 3) / 4 * 4;
   TileGeom g{(int)T, ecap, smem_bytes((int)T, H, n_rpc, ecap, n_edge_arrays)};
   return g;
@@ -573,6 +509,47 @@ int set_smem(K kernel, size_t bytes) {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+template <int LPR>
+int launch_fwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, cudaStream_t st) {
+  constexpr int H = 4 * LPR;
+  const TileGeom g = tile_geom(H, 0, N, E, B, 3);   // src, packed ids, logit staging
+  TileArgs a = a0;
+  a.tile_nodes = g.T;
+  a.edge_cap = g.ecap;
+  const int grid = pert_cdiv(N, g.T);
+  int rc;
+  if (has_e) {
+    if ((rc = set_smem(k_tile_fwd<LPR, true>, g.bytes))) return rc;
+    k_tile_fwd<LPR, true><<<grid, TILE_THREADS, g.bytes, st>>>(a);
+  } else {
+    if ((rc = set_smem(k_tile_fwd<LPR, false>, g.bytes))) return rc;
+    k_tile_fwd<LPR, false><<<grid, TILE_THREADS, g.bytes, st>>>(a);
+  }
+  return PERT_OK;
+}
+template <int LPR>
+int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, cudaStream_t st) {
+  constexpr int H = 4 * LPR;
+  const TileGeom gd = tile_geom(H, 0, N, E, B, 4);                      // src, ids, alpha, dalpha staging
+  const TileGeom gs = tile_geom(H, has_e ? a0.n_rpc : 0, N, E, B, 4);   // dst, ids, alpha, ds
+  TileArgs ad = a0, as = a0;
+  ad.tile_nodes = gd.T; ad.edge_cap = gd.ecap;
+  as.tile_nodes = gs.T; as.edge_cap = gs.ecap;
+  int rc;
+  if (has_e) {
+    if ((rc = set_smem(k_tile_bwd_dst<LPR, true>, gd.bytes))) return rc;
+    if ((rc = set_smem(k_tile_bwd_src<LPR, true>, gs.bytes))) return rc;
+    k_tile_bwd_dst<LPR, true><<<pert_cdiv(N, gd.T), TILE_THREADS, gd.bytes, st>>>(ad);
+    k_tile_bwd_src<LPR, true><<<pert_cdiv(N, gs.T), TILE_THREADS, gs.bytes, st>>>(as);
+  } else {
+    if ((rc = set_smem(k_tile_bwd_dst<LPR, false>, gd.bytes))) return rc;
+    if ((rc = set_smem(k_tile_bwd_src<LPR, false>, gs.bytes))) return rc;
+    k_tile_bwd_dst<LPR, false><<<pert_cdiv(N, gd.T), TILE_THREADS, gd.bytes, st>>>(ad);
+    k_tile_bwd_src<LPR, false><<<pert_cdiv(N, gs.T), TILE_THREADS, gs.bytes, st>>>(as);
+  }
+  return PERT_OK;
+}
+
 }  // namespace
 
 // Entry points used by tconv.cu's C-ABI functions: return PERT_ERR_UNSUPPORTED when the tile path does not apply
@@ -581,26 +558,19 @@ int pert_tile_fwd(const float* q, const float* k, const float* v, const float* s
                   const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if, const float* t_rpc,
                   int n_rpc, float* out, int ld_out, float* alpha, long long N, long long E, long long B, int H,
                   cudaStream_t st) {
-  if (ld != H || (t_if && ((size_t)n_rpc * H * 4 > 16 * 1024 || n_rpc > 1023))) return PERT_ERR_UNSUPPORTED;
-  return dispatch_tile(H, [&](auto lpr, auto vpl) {
-    constexpr int LPR = decltype(lpr)::value, VPL = decltype(vpl)::value;
-    const TileGeom g = tile_geom(H, t_if ? n_rpc : 0, N, E, B, 2);
-    TileArgs a{};
-    a.q = q; a.k = k; a.v = v; a.s = s; a.ld = ld;
-    a.rowptr = rowptr; a.csr_src = csr_src; a.csr_if = csr_if; a.csr_rpc = csr_rpc;
-    a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc; a.out = out; a.ld_out = ld_out; a.alpha = alpha;
-    a.N = (int)N; a.tile_nodes = g.T; a.edge_cap = g.ecap; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
-    const int grid = pert_cdiv(N, g.T);
-    int rc;
-    if (t_if) {
-      if ((rc = set_smem(k_tile_fwd<LPR, VPL, true>, g.bytes))) return rc;
-      k_tile_fwd<LPR, VPL, true><<<grid, TILE_THREADS, g.bytes, st>>>(a);
-    } else {
-      if ((rc = set_smem(k_tile_fwd<LPR, VPL, false>, g.bytes))) return rc;
-      k_tile_fwd<LPR, VPL, false><<<grid, TILE_THREADS, g.bytes, st>>>(a);
-    }
-    return PERT_OK;
-  });
+  if (ld != H || ld_out != H || (t_if && ((size_t)n_rpc * H * 4 > 16 * 1024 || n_rpc > 1023)))
+    return PERT_ERR_UNSUPPORTED;
+  TileArgs a{};
+  a.q = q; a.k = k; a.v = v; a.s = s;
+  a.rowptr = rowptr; a.csr_src = csr_src; a.csr_if = csr_if; a.csr_rpc = csr_rpc;
+  a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc; a.out = out; a.alpha = alpha;
+  a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
+  switch (H) {
+    case 32: return launch_fwd<8>(a, N, E, B, t_if != nullptr, st);
+    case 64: return launch_fwd<16>(a, N, E, B, t_if != nullptr, st);
+    case 128: return launch_fwd<32>(a, N, E, B, t_if != nullptr, st);
+    default: return PERT_ERR_UNSUPPORTED;
+  }
 }
 
 int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, const float* v, int ld, const int* rowptr,
@@ -608,35 +578,20 @@ int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, con
                   const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha, float* dq, float* dk,
                   float* dv, int ld_d, float* dsp, float* dt_if, float* dt_rpc, int n_rpc, long long N, long long E,
                   long long B, int H, cudaStream_t st) {
-  if (ld != H || ld_g != H || (t_if && ((size_t)n_rpc * H * 4 > 16 * 1024 || n_rpc > 1023)))
+  if (ld != H || ld_g != H || ld_d != H || (t_if && ((size_t)n_rpc * H * 4 > 16 * 1024 || n_rpc > 1023)))
     return PERT_ERR_UNSUPPORTED;
-  return dispatch_tile(H, [&](auto lpr, auto vpl) {
-    constexpr int LPR = decltype(lpr)::value, VPL = decltype(vpl)::value;
-    const TileGeom gd = tile_geom(H, t_if ? n_rpc : 0, N, E, B, 3);   // target pass: src, ids, alpha
-    const TileGeom gs = tile_geom(H, t_if ? n_rpc : 0, N, E, B, 4);   // source pass: dst, ids, alpha, ds
-    TileArgs a{};
-    a.q = q; a.k = k; a.v = v; a.ld = ld; a.g = g_; a.ld_g = ld_g;
-    a.rowptr = rowptr; a.csr_src = csr_src; a.csr_if = csr_if; a.csr_rpc = csr_rpc;
-    a.colptr = colptr; a.csc_pos = csc_pos; a.csc_dst = csc_dst;
-    a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc;
-    a.out = dq; a.ld_out = ld_d; a.dk = dk; a.dv = dv; a.alpha = const_cast<float*>(alpha); a.dsp = dsp;
-    a.dt_if = dt_if; a.dt_rpc = dt_rpc;
-    a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
-    TileArgs ad = a, as = a;
-    ad.tile_nodes = gd.T; ad.edge_cap = gd.ecap;
-    as.tile_nodes = gs.T; as.edge_cap = gs.ecap;
-    int rc;
-    if (t_if) {
-      if ((rc = set_smem(k_tile_bwd_dst<LPR, VPL, true>, gd.bytes))) return rc;
-      if ((rc = set_smem(k_tile_bwd_src<LPR, VPL, true>, gs.bytes))) return rc;
-      k_tile_bwd_dst<LPR, VPL, true><<<pert_cdiv(N, gd.T), TILE_THREADS, gd.bytes, st>>>(ad);
-      k_tile_bwd_src<LPR, VPL, true><<<pert_cdiv(N, gs.T), TILE_THREADS, gs.bytes, st>>>(as);
-    } else {
-      if ((rc = set_smem(k_tile_bwd_dst<LPR, VPL, false>, gd.bytes))) return rc;
-      if ((rc = set_smem(k_tile_bwd_src<LPR, VPL, false>, gs.bytes))) return rc;
-      k_tile_bwd_dst<LPR, VPL, false><<<pert_cdiv(N, gd.T), TILE_THREADS, gd.bytes, st>>>(ad);
-      k_tile_bwd_src<LPR, VPL, false><<<pert_cdiv(N, gs.T), TILE_THREADS, gs.bytes, st>>>(as);
-    }
-    return PERT_OK;
-  });
+  TileArgs a{};
+  a.q = q; a.k = k; a.v = v; a.g = g_;
+  a.rowptr = rowptr; a.csr_src = csr_src; a.csr_if = csr_if; a.csr_rpc = csr_rpc;
+  a.colptr = colptr; a.csc_pos = csc_pos; a.csc_dst = csc_dst;
+  a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc;
+  a.out = dq; a.dk = dk; a.dv = dv; a.alpha = const_cast<float*>(alpha); a.dsp = dsp;
+  a.dt_if = dt_if; a.dt_rpc = dt_rpc;
+  a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
+  switch (H) {
+    case 32: return launch_bwd<8>(a, N, E, B, t_if != nullptr, st);
+    case 64: return launch_bwd<16>(a, N, E, B, t_if != nullptr, st);
+    case 128: return launch_bwd<32>(a, N, E, B, t_if != nullptr, st);
+    default: return PERT_ERR_UNSUPPORTED;
+  }
 }

@@ -346,7 +346,10 @@ def test_fused_train_step_matches_oracle_adam_step():
         # Adam normalises the update: structurally-zero gradients (pure rounding noise) move by +-lr on both sides
         if n.endswith("lin_key.bias") or (n.endswith("lin_skip.bias") and not n.startswith("convs.1.")):
             continue
-        assert_close(p, po[n], rtol=2e-4, what=f"param {n} after 3 steps")
+        # Adam divides by sqrt(v): gradient rounding noise (atomics order, 3xTF32 vs fp32) is amplified to a
+        # fraction of lr per step on small-gradient weights -> loose bound here; the optimiser arithmetic itself is
+        # pinned exactly by test_fused_adam_matches_torch_adam, the gradients by the *_train parity tests.
+        assert_close(p, po[n], rtol=2e-3, what=f"param {n} after 3 steps")
     for n, bbuf in model.named_buffers():
         if n.endswith("running_mean"):
             continue    # absorbs the +-lr random walk of the zero-gradient lin_skip.bias feeding the BatchNorm
@@ -387,3 +390,25 @@ def test_two_graph_batch_equals_separate_graphs():
         one = Batch.from_data_list([dl[i]]).to("cuda")
         g_one, _ = model(*forward_args(one))
         assert_close(g_one, g_both[i:i + 1], rtol=1e-5)
+
+
+def test_fused_adam_matches_torch_adam():
+    """pert_adam_step over a flat buffer == torch.optim.Adam given identical gradients (5 steps, with grad_scale)."""
+    from pert_gnn_kdd23_b200.train import FlatParams, FusedAdam
+
+    torch.manual_seed(0)
+    lin_c = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 3)).cuda()
+    lin_o = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 3))
+    lin_o.load_state_dict({k: v.cpu() for k, v in lin_c.state_dict().items()})
+    fp = FlatParams(lin_c)
+    opt_c = FusedAdam(fp, lr=1e-2)
+    opt_o = torch.optim.Adam(lin_o.parameters(), lr=1e-2)
+    for step in range(5):
+        for pc, po in zip(lin_c.parameters(), lin_o.parameters()):
+            g = torch.randn_like(po)
+            po.grad = g.clone()
+            pc.grad.copy_(2.0 * g.cuda())          # FusedAdam is asked to rescale by 0.5 (data-parallel averaging)
+        opt_o.step()
+        opt_c.step(grad_scale=0.5)
+    for pc, po in zip(lin_c.parameters(), lin_o.parameters()):
+        assert_close(pc, po, rtol=1e-5, what="adam param")
