@@ -185,19 +185,28 @@ long long pert_model_packed_bytes(const PertModelDesc* desc);
 /* bn_running: [n_convs-1][2][H] (running_mean | running_var), bn_nbt: [n_convs-1] int64 (either may be NULL in
  * training mode); index arrays from pert_build_index (built with edge_attr); probs/pnn [N] fp32.
  * Outputs: global_pred [B], local_pred [N] (NULL to skip). */
+/* Optional measurement probe: the engine records the two caller-created cudaEvent_t around ONE kernel family of ONE
+ * layer, on the launching stream (bench.py: in-step duration of the dominant kernel).  kernel: 1 = fused conv forward,
+ * 2 = fused conv backward (target + source pass), 3 = node-linear forward GEMM, 4 = weight-gradient GEMM,
+ * 5 = data-gradient GEMM.  NULL = no probe. */
+typedef struct PertProbe {
+  int32_t kernel, layer;
+  void* ev_start;
+  void* ev_stop;
+} PertProbe;
 int pert_model_forward(const PertModelDesc* desc, const float* params, float* bn_running, long long* bn_nbt,
                        const float* x, const int64_t* cat_X, const int64_t* entry_id, const float* probs,
                        const float* pnn, const int64_t* batch, long long N, long long E, long long B,
                        const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, void* workspace,
                        long long workspace_bytes, int training, float* global_pred, float* local_pred, int* status,
-                       void* stream);
+                       const PertProbe* probe, void* stream);
 /* Must follow pert_model_forward on the same workspace.  d_global [B], d_local [N] or NULL. */
 int pert_model_backward(const PertModelDesc* desc, const float* params, float* grads, const int64_t* cat_X,
                         const int64_t* entry_id, const float* probs, const float* pnn, const int64_t* batch,
                         long long N, long long E, long long B, const int* rowptr, const int* csr_src,
                         const int* csr_if, const int* csr_rpc, const int* colptr, const int* csc_pos,
                         const int* csc_dst, void* workspace, long long workspace_bytes, int training,
-                        const float* d_global, const float* d_local, void* stream);
+                        const float* d_global, const float* d_local, const PertProbe* probe, void* stream);
 
 #ifdef __cplusplus
 }

@@ -315,6 +315,17 @@ int check_desc(const PertModelDesc* d) {
   return PERT_OK;
 }
 
+#define PROBE_START(kid, lay)                                                              \
+  do {                                                                                     \
+    if (probe && probe->kernel == (kid) && probe->layer == (lay) && probe->ev_start)       \
+      cudaEventRecord((cudaEvent_t)probe->ev_start, st);                                   \
+  } while (0)
+#define PROBE_STOP(kid, lay)                                                               \
+  do {                                                                                     \
+    if (probe && probe->kernel == (kid) && probe->layer == (lay) && probe->ev_stop)        \
+      cudaEventRecord((cudaEvent_t)probe->ev_stop, st);                                    \
+  } while (0)
+
 #define TRY(expr)            \
   do {                       \
     int rc__ = (expr);       \
@@ -341,7 +352,7 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
                        const float* pnn, const int64_t* batch, long long N, long long E, long long B,
                        const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, void* workspace,
                        long long workspace_bytes, int training, float* global_pred, float* local_pred, int* status,
-                       void* stream) {
+                       const PertProbe* probe, void* stream) {
   TRY(check_desc(d));
   if (!params || !x || !cat_X || !entry_id || !probs || !pnn || !batch || !rowptr || !workspace || !global_pred)
     return PERT_ERR_BADARG;
@@ -377,10 +388,14 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
   // 3. conv stack
   for (int l = 0; l < L; ++l) {
     const int K = k_of(d, l);
+    PROBE_START(3, l);
     TRY(pert_gemm_nt(w.x[l], K, 0, 0, w.w4[l], K, w.b4[l], w.planes[l], H, H, N * (long long)H, N, 4 * H, K, 0, 0, st));
+    PROBE_STOP(3, l);
     float* pl = w.planes[l];
+    PROBE_START(1, l);
     TRY(pert_tconv_fwd(pl, pl + N * H, pl + 2 * N * H, pl + 3 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, w.t_if[l],
                        w.t_rpc[l], w.out[l], H, w.alpha[l], d->n_rpc, N, E, B, H, st));
+    PROBE_STOP(1, l);
     if (l + 1 < L) {
       float* rm = bn_running ? bn_running + (size_t)l * 2 * H : nullptr;
       float* rv = rm ? rm + H : nullptr;
@@ -415,7 +430,7 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
                         long long N, long long E, long long B, const int* rowptr, const int* csr_src,
                         const int* csr_if, const int* csr_rpc, const int* colptr, const int* csc_pos,
                         const int* csc_dst, void* workspace, long long workspace_bytes, int training,
-                        const float* d_global, const float* d_local, void* stream) {
+                        const float* d_global, const float* d_local, const PertProbe* probe, void* stream) {
   TRY(check_desc(d));
   if (!params || !grads || !cat_X || !entry_id || !probs || !pnn || !batch || !rowptr || !colptr || !workspace ||
       !d_global)
@@ -457,12 +472,18 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
   for (int l = L - 1; l >= 0; --l) {
     const int K = k_of(d, l);
     float* pl = w.planes[l];
+    PROBE_START(2, l);
     TRY(pert_tconv_bwd(dskip, H, pl, pl + N * H, pl + 2 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos,
                        csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.dt_if[l], w.dt_rpc[l],
                        d->n_rpc, N, E, B, H, st));
+    PROBE_STOP(2, l);
     // weight / bias gradients of the fused node linear (packed), data gradient
+    PROBE_START(4, l);
     TRY(pert_gemm_tn(w.dplanes, H, H, N * (long long)H, w.x[l], K, 0, 0, w.dw4[l], K, w.db4[l], N, 4 * H, K, st));
+    PROBE_STOP(4, l);
+    PROBE_START(5, l);
     TRY(pert_gemm_nt(w.dplanes, H, H, N * (long long)H, w.w4t[l], 4 * H, nullptr, w.dx, K, 0, 0, N, K, 4 * H, 0, 0, st));
+    PROBE_STOP(5, l);
     if (l > 0) {
       // BN(+ReLU) backward of layer l-1: dx (grad wrt x[l]) -> g of conv l-1, into the skip plane
       TRY(pert_bn_bwd(w.dx, K, w.x[l], H, w.out[l - 1], H, w.bn_stats[l - 1], w.bn_stats[l - 1] + H,

@@ -34,6 +34,49 @@ def _bind():
     return _lib.lib()
 
 
+class PertProbe(C.Structure):
+    """Measurement probe (include/pertgnn.h): two CUDA events recorded around one kernel family of one layer."""
+    _fields_ = [("kernel", C.c_int32), ("layer", C.c_int32), ("ev_start", C.c_void_p), ("ev_stop", C.c_void_p)]
+
+    KERNELS = {"tconv_fwd": 1, "tconv_bwd": 2, "gemm_fwd": 3, "gemm_wgrad": 4, "gemm_dgrad": 5}
+    _rt = None
+
+    @classmethod
+    def _cudart(cls):
+        if cls._rt is None:
+            import glob
+            import os
+
+            cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*")) + \
+                glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+            if not cands:
+                import nvidia.cuda_runtime as _n   # pip layout
+
+                cands = glob.glob(os.path.join(os.path.dirname(_n.__file__), "lib", "libcudart.so*"))
+            cls._rt = C.CDLL(sorted(cands)[0])
+            cls._rt.cudaEventCreate.argtypes = [C.POINTER(C.c_void_p)]
+            cls._rt.cudaEventElapsedTime.argtypes = [C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+            cls._rt.cudaEventDestroy.argtypes = [C.c_void_p]
+        return cls._rt
+
+    @classmethod
+    def create(cls, kernel, layer):
+        rt = cls._cudart()
+        a, b = C.c_void_p(), C.c_void_p()
+        assert rt.cudaEventCreate(C.byref(a)) == 0 and rt.cudaEventCreate(C.byref(b)) == 0
+        return cls(cls.KERNELS[kernel], layer, a, b)
+
+    def elapsed_ms(self):
+        ms = C.c_float()
+        rc = self._cudart().cudaEventElapsedTime(C.byref(ms), self.ev_start, self.ev_stop)
+        return ms.value if rc == 0 else float("nan")
+
+    def destroy(self):
+        rt = self._cudart()
+        rt.cudaEventDestroy(self.ev_start)
+        rt.cudaEventDestroy(self.ev_stop)
+
+
 class Engine:
     """Owns flat parameters / gradients / BN buffers of one model replica and the engine workspace."""
 
@@ -115,7 +158,7 @@ class Engine:
         L = self.n_convs
         return 2 + 1 + 1 + L * 4 + (L - 1) * 2 + self.desc.n_cat + L + L
 
-    def forward(self, x, cat_X, entry_id, probs, pnn, batch, index: GraphIndex, training):
+    def forward(self, x, cat_X, entry_id, probs, pnn, batch, index: GraphIndex, training, probe=None):
         """-> (global_pred [B,1], local_pred [N,1]); keeps what backward needs in the workspace."""
         N, E, B = x.size(0), index.E, entry_id.numel()
         ws = self._workspace(N, E, B)
@@ -132,13 +175,14 @@ class Engine:
         rc = self.lib.pert_model_forward(
             C.byref(self.desc), p(self.fp.flat), p(self.bn_running), p(self.bn_nbt), p(x), p(cat_X), p(entry_id),
             p(probs), p(pnn), p(batch), N, E, B, p(index.rowptr), p(index.csr_src), p(index.csr_if), p(index.csr_rpc),
-            p(ws), ws.numel() * 4, int(training), p(gpred), p(lpred), p(index.status), _lib.stream())
+            p(ws), ws.numel() * 4, int(training), p(gpred), p(lpred), p(index.status),
+            C.byref(probe) if probe is not None else None, _lib.stream())
         _lib.check(rc, "pert_model_forward")
         ops.LAUNCHES["n"] += self.launches_forward()
         self._saved = (x, cat_X, entry_id, probs, pnn, batch, index, bool(training), N, E, B)
         return gpred, lpred
 
-    def backward(self, d_global, d_local=None, grads=None):
+    def backward(self, d_global, d_local=None, grads=None, probe=None):
         """Accumulates (+=) parameter gradients into ``grads`` (default: the flat gradient buffer)."""
         x, cat_X, entry_id, probs, pnn, batch, index, training, N, E, B = self._saved
         grads = self.fp.grad if grads is None else grads
@@ -150,7 +194,8 @@ class Engine:
         rc = self.lib.pert_model_backward(
             C.byref(self.desc), p(self.fp.flat), p(grads), p(cat_X), p(entry_id), p(probs), p(pnn), p(batch), N, E, B,
             p(index.rowptr), p(index.csr_src), p(index.csr_if), p(index.csr_rpc), p(index.colptr), p(index.csc_pos),
-            p(index.csc_dst), p(ws), ws.numel() * 4, int(training), p(d_global), p(d_local), _lib.stream())
+            p(index.csc_dst), p(ws), ws.numel() * 4, int(training), p(d_global), p(d_local),
+            C.byref(probe) if probe is not None else None, _lib.stream())
         _lib.check(rc, "pert_model_backward")
         ops.LAUNCHES["n"] += self.launches_backward()
 

@@ -106,7 +106,8 @@ def train_step(model, optimizer, data, tau=0.5, dp: DataParallel | None = None):
     return loss
 
 
-def fused_train_step(model, optimizer: FusedAdam, data, tau=0.5, dp: DataParallel | None = None, index=None):
+def fused_train_step(model, optimizer: FusedAdam, data, tau=0.5, dp: DataParallel | None = None, index=None,
+                     probe=None):
     """Same step as ``train_step`` but without autograd: engine forward -> pinball loss + its gradient (one
     kernel) -> engine backward into the flat gradient buffer -> (all-reduce) -> fused Adam.  5 C calls per step.
     Returns the device loss tensor [1]."""
@@ -120,14 +121,14 @@ def fused_train_step(model, optimizer: FusedAdam, data, tau=0.5, dp: DataParalle
                              model.rpctype_embeds.num_embeddings)
     optimizer.zero_grad()
     with torch.no_grad():
-        gpred, _ = eng.forward(x, cat_X, entry_id, probs, pnn, batch, index, model.training)
+        gpred, _ = eng.forward(x, cat_X, entry_id, probs, pnn, batch, index, model.training, probe=probe)
         B = gpred.size(0)
         loss = torch.empty(1, device=gpred.device, dtype=torch.float32)
         dy = torch.empty(B, device=gpred.device, dtype=torch.float32)
         _lib.call("pert_pinball_loss", _lib.ptr(data.y), _lib.ptr(gpred), float(tau), B, 1.0, _lib.ptr(loss),
                   _lib.ptr(dy), _lib.stream())
         ops.LAUNCHES["n"] += 1
-        eng.backward(dy, None)
+        eng.backward(dy, None, probe=probe)
         scale = dp.all_reduce_grads() if dp is not None else 1.0
         optimizer.step(grad_scale=scale)
     return loss
