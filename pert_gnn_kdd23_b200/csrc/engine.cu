@@ -49,20 +49,40 @@ __global__ void __launch_bounds__(256) k_small_gemm(SmallGemmBatch batch) {
   const int ty = tid / 16, tx = tid % 16;  // 16x16 threads: 2 rows x 4 cols each
   float acc[2][4] = {};
   for (int k0 = kbeg; k0 < kend; k0 += SG_BK) {
-    for (int x = tid; x < SG_BM * SG_BK; x += 256) {
-      // pick the index that is contiguous in memory as the fast thread index
-      int mm, kk;
+    // all global loads of the step are issued before the first shared-memory store (the compiler cannot hoist
+    // loads over possibly-aliasing stores: a load->store loop would serialise 24 DRAM/L2 latencies per step)
+    float ra[SG_BM * SG_BK / 256], rb[SG_BN * SG_BK / 256];
+#pragma unroll
+    for (int u = 0; u < SG_BM * SG_BK / 256; ++u) {
+      const int x = tid + u * 256;
+      int mm, kk;   // the index that is contiguous in memory is the fast thread index
       if (g.sak == 1) { kk = x % SG_BK; mm = x / SG_BK; } else { mm = x % SG_BM; kk = x / SG_BM; }
-      int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < g.M && k < kend) ? __ldg(g.A + (size_t)m * g.sam + (size_t)k * g.sak) : 0.f;
+      const int m = m0 + mm, k = k0 + kk;
+      ra[u] = (m < g.M && k < kend) ? __ldg(g.A + (size_t)m * g.sam + (size_t)k * g.sak) : 0.f;
     }
-    for (int x = tid; x < SG_BN * SG_BK; x += 256) {
+#pragma unroll
+    for (int u = 0; u < SG_BN * SG_BK / 256; ++u) {
+      const int x = tid + u * 256;
       int nn, kk;
       if (g.sbk == 1) { kk = x % SG_BK; nn = x / SG_BK; } else { nn = x % SG_BN; kk = x / SG_BN; }
-      int n = n0 + nn, k = k0 + kk;
+      const int n = n0 + nn, k = k0 + kk;
       float v = 0.f;
       if (n < g.N && k < kend) v = g.B ? __ldg(g.B + (size_t)k * g.sbk + (size_t)n * g.sbn) : 1.f;
-      Bs[kk][nn] = v;
+      rb[u] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < SG_BM * SG_BK / 256; ++u) {
+      const int x = tid + u * 256;
+      int mm, kk;
+      if (g.sak == 1) { kk = x % SG_BK; mm = x / SG_BK; } else { mm = x % SG_BM; kk = x / SG_BM; }
+      As[kk][mm] = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < SG_BN * SG_BK / 256; ++u) {
+      const int x = tid + u * 256;
+      int nn, kk;
+      if (g.sbk == 1) { kk = x % SG_BK; nn = x / SG_BK; } else { nn = x % SG_BN; kk = x / SG_BN; }
+      Bs[kk][nn] = rb[u];
     }
     __syncthreads();
 #pragma unroll

@@ -70,7 +70,16 @@ __global__ void __launch_bounds__(256) k_bn_partial(const float* __restrict__ x,
   float* s_mean = sm + rl_n * H; // [H]
   float4 s = f4zero();
   if (rl < rl_n)
-    for (int r = rl; r < rows; r += rl_n) s = f4add(s, ldg4(x + (size_t)(r0 + r) * ld + cl * 4));
+    for (int rb = rl; rb < rows; rb += 8 * rl_n) {   // 8 independent row loads in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = rb + u * rl_n;
+        v[u] = (r < rows) ? ldg4(x + (size_t)(r0 + r) * ld + cl * 4) : f4zero();
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = f4add(s, v[u]);
+    }
   if (rl < rl_n) st4(s_red + rl * H + cl * 4, s);
   __syncthreads();
   if (threadIdx.x < H) {
@@ -82,10 +91,19 @@ __global__ void __launch_bounds__(256) k_bn_partial(const float* __restrict__ x,
   float4 mu = (rl < rl_n) ? ld4(s_mean + cl * 4) : f4zero();
   float4 q = f4zero();
   if (rl < rl_n)
-    for (int r = rl; r < rows; r += rl_n) {
-      float4 v = ldg4(x + (size_t)(r0 + r) * ld + cl * 4);
-      float dx = v.x - mu.x, dy = v.y - mu.y, dz = v.z - mu.z, dw = v.w - mu.w;
-      q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+    for (int rb = rl; rb < rows; rb += 8 * rl_n) {
+      float4 vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = rb + u * rl_n;
+        vv[u] = (r < rows) ? ldg4(x + (size_t)(r0 + r) * ld + cl * 4) : mu;   // mu => contributes 0
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 v = vv[u];
+        float dx = v.x - mu.x, dy = v.y - mu.y, dz = v.z - mu.z, dw = v.w - mu.w;
+        q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+      }
     }
   __syncthreads();
   if (rl < rl_n) st4(s_red + rl * H + cl * 4, q);
@@ -184,17 +202,26 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
   float4 s1 = f4zero(), s2 = f4zero();
   if (rl < rl_n) {
     const float4 mu = ldg4(mean + cl * 4), rs = ldg4(rstd + cl * 4);
-    for (int r = rl; r < rows; r += rl_n) {
-      float4 g = ldg4(dy + (size_t)(r0 + r) * ld_dy + cl * 4);
-      if (relu) {
-        float4 yy = ldg4(y + (size_t)(r0 + r) * ld_y + cl * 4);
+    for (int rb = rl; rb < rows; rb += 4 * rl_n) {   // 4 rows x 3 operands = 12 independent loads in flight
+      float4 gg[4], yy4[4], vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * rl_n;
+        const bool ok = r < rows;
+        gg[u] = ok ? ldg4(dy + (size_t)(r0 + r) * ld_dy + cl * 4) : f4zero();
+        yy4[u] = (ok && relu) ? ldg4(y + (size_t)(r0 + r) * ld_y + cl * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+        vv[u] = ok ? ldg4(x + (size_t)(r0 + r) * ld_x + cl * 4) : mu;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float4 g = gg[u];
+        const float4 yy = yy4[u], v = vv[u];
         g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
         g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+        s1 = f4add(s1, g);
+        s2.x = fmaf(g.x, (v.x - mu.x) * rs.x, s2.x); s2.y = fmaf(g.y, (v.y - mu.y) * rs.y, s2.y);
+        s2.z = fmaf(g.z, (v.z - mu.z) * rs.z, s2.z); s2.w = fmaf(g.w, (v.w - mu.w) * rs.w, s2.w);
       }
-      float4 v = ldg4(x + (size_t)(r0 + r) * ld_x + cl * 4);
-      s1 = f4add(s1, g);
-      s2.x = fmaf(g.x, (v.x - mu.x) * rs.x, s2.x); s2.y = fmaf(g.y, (v.y - mu.y) * rs.y, s2.y);
-      s2.z = fmaf(g.z, (v.z - mu.z) * rs.z, s2.z); s2.w = fmaf(g.w, (v.w - mu.w) * rs.w, s2.w);
     }
     st4(sm + rl * 2 * H + cl * 4, s1);
     st4(sm + rl * 2 * H + H + cl * 4, s2);

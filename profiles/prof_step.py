@@ -8,7 +8,7 @@ import torch
 from pert_gnn_kdd23_b200.data import Batch
 from pert_gnn_kdd23_b200.model import SAGEDeterministic
 from pert_gnn_kdd23_b200.synthetic import make_data_list, model_args
-from pert_gnn_kdd23_b200.train import FlatParams, FusedAdam, train_step
+from pert_gnn_kdd23_b200.train import FlatParams, FusedAdam, fused_train_step as train_step
 
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
