@@ -93,6 +93,27 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
 
+#ifdef PERT_TC_TRACE
+__device__ long long g_trace[4][32][4];   // [role][tile or chunk][event] clock64 stamps of CTA (0,0)
+__device__ unsigned long long g_cta_t[512][2];   // per-CTA globaltimer at entry / exit
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define CTA_T(ev)                                                                                            \
+  do {                                                                                                       \
+    if (threadIdx.x == 0) g_cta_t[blockIdx.y * gridDim.x + blockIdx.x][ev] = gtimer();                      \
+  } while (0)
+#define TRACE(role, it, ev)                                                                                  \
+  do {                                                                                                       \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (it) < 32) g_trace[role][it][ev] = clock64(); \
+  } while (0)
+#else
+#define TRACE(role, it, ev)
+#define CTA_T(ev)
+#endif
+
 constexpr int TC_THREADS = 288;  // 4 producer warps + 1 MMA warp + 4 consumer warps
 constexpr int KC = 64;           // K elements per A stage (TMEM columns per hi / lo half)
 constexpr int D_COL = 0;         // accumulator stages at columns 0 and 128
@@ -122,24 +143,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_nt_tc(NtArgs g) {
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) NtBars bars;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) TRACE(3, 1, 0);
+  CTA_T(0);
   const int K = g.K, BN = g.BN;
   const int n0 = blockIdx.y * BN;
   const uint32_t LBO = 128, SBO = (uint32_t)(K / 4) * 128;
+  const int kq = K / 4;
   unsigned char* sBhi = smem;
   unsigned char* sBlo = smem + (size_t)BN * K * 4;
-  // ---- B (weights) -> smem, split hi/lo, canonical K-major (all threads, once per CTA)
-  const int kq = K / 4;
-  for (int idx = tid; idx < BN * kq; idx += TC_THREADS) {
-    const int n = idx / kq, kc = idx - n * kq;
-    float4 v = f4zero();
-    if (n0 + n < g.Nc) v = ldg4(g.B + (size_t)(n0 + n) * g.ldb + kc * 4);
-    uint4 h, l;
-    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-    l.x = tf32_lo(v.x, h.x); l.y = tf32_lo(v.y, h.y); l.z = tf32_lo(v.z, h.z); l.w = tf32_lo(v.w, h.w);
-    const size_t off = (size_t)(n >> 3) * SBO + (n & 7) * 16 + (size_t)kc * LBO;
-    *reinterpret_cast<uint4*>(sBhi + off) = h;
-    *reinterpret_cast<uint4*>(sBlo + off) = l;
-  }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                  "r"(TMEM_COLS));
@@ -154,11 +165,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_nt_tc(NtArgs g) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  fence_async_smem();
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem = s_tmem;
+  if (tid == 0) TRACE(3, 1, 1);
   const int mtiles = (g.M + 127) / 128;
   const int nchunks = (K + KC - 1) / KC;
 
@@ -172,69 +183,121 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_nt_tc(NtArgs g) {
     unsigned char* stA = smem + (size_t)BN * K * 8;          // 32 KB: 128 rows x 16 chunks of 16 B
     const int c16 = tid & 15, rsub = tid >> 4;               // coalesced phase: chunk within the row, row within a pass of 8
     uint32_t stage = 0, ph = 0;
-    for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+    int tr_i = 0;
+    float4 va[KC / 4], vr[KC / 4];                           // va: loads in flight (next chunk); vr: this thread's row
+    auto issue = [&](int mt, int ch) {
+      const int k0 = ch * KC;
+      const int kw = min(KC, K - k0);
+      const float* base = g.A + (size_t)(k0 / g.a_cb) * g.a_cbs + (k0 % g.a_cb);   // a chunk never straddles blocks
       const int row0 = mt * 128;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int k0 = ch * KC;
-        const int kw = min(KC, K - k0);
-        const float* base = g.A + (size_t)(k0 / g.a_cb) * g.a_cbs + (k0 % g.a_cb);   // a chunk never straddles blocks
-        float4 va[KC / 4];
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int r = it * 8 + rsub;
-          va[it] = (row0 + r < g.M && c16 * 4 < kw) ? ldg4(base + (size_t)(row0 + r) * g.lda + c16 * 4) : f4zero();
+      for (int it = 0; it < 16; ++it) {
+        const int r = it * 8 + rsub;
+        va[it] = (row0 + r < g.M && c16 * 4 < kw) ? ldg4(base + (size_t)(row0 + r) * g.lda + c16 * 4) : f4zero();
+      }
+    };
+    int mt = blockIdx.x, ch = 0;
+    bool have = mt < mtiles;
+    if (have) issue(mt, ch);
+    while (have) {
+      TRACE(0, tr_i, 0);
+      const int kw = min(KC, K - ch * KC);
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // previous chunk's row reads are done
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int r = it * 8 + rsub;
+        *reinterpret_cast<float4*>(stA + r * 256 + (((c16 & 8) | ((c16 ^ r) & 7)) << 4)) = va[it];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      TRACE(0, tr_i, 1);
+      // the next chunk's loads fly while this one is split and written to TMEM
+      // (the shared-memory reads go first: LDS queues in order behind global loads in the memory pipe)
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q)
+        vr[q] = *reinterpret_cast<const float4*>(stA + tid * 256 + (((q & 8) | ((q ^ tid) & 7)) << 4));
+      int nmt = mt, nch = ch + 1;
+      if (nch == nchunks) { nch = 0; nmt += gridDim.x; }
+      const bool nhave = nmt < mtiles;
+      if (nhave) issue(nmt, nch);
+      mbar_wait(&bars.a_empty[stage], ph ^ 1);
+      fence_after();
+      TRACE(0, tr_i, 2);
+      const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
+#pragma unroll
+      for (int grp = 0; grp < KC / 16; ++grp) {
+        if (grp * 16 < kw) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = vr[grp * 4 + q];
+            hi[q * 4 + 0] = tf32_hi(v.x); lo[q * 4 + 0] = tf32_lo(v.x, hi[q * 4 + 0]);
+            hi[q * 4 + 1] = tf32_hi(v.y); lo[q * 4 + 1] = tf32_lo(v.y, hi[q * 4 + 1]);
+            hi[q * 4 + 2] = tf32_hi(v.z); lo[q * 4 + 2] = tf32_lo(v.z, hi[q * 4 + 2]);
+            hi[q * 4 + 3] = tf32_hi(v.w); lo[q * 4 + 3] = tf32_lo(v.w, hi[q * 4 + 3]);
+          }
+          tmem_st16(t_hi + grp * 16, hi);
+          tmem_st16(t_hi + KC + grp * 16, lo);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // previous chunk's row reads are done
+      }
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&bars.a_full[stage]);
+      TRACE(0, tr_i, 3);
+      ++tr_i;
+      stage ^= 1;
+      if (stage == 0) ph ^= 1;
+      mt = nmt; ch = nch; have = nhave;
+    }
+  } else {
+    // ---- B (weights) -> smem, split hi/lo, canonical K-major (warps 4-8, once per CTA, while the A producers already stream)
+    // lane -> (n % 8, kc % 4): a warp's 16-byte stores cover 8 consecutive core-matrix rows (128 contiguous bytes)
+    // per quarter-warp -- conflict-free; (consecutive lanes along kc would all land 128 B apart in the same 4 banks)
+    {
+      const int t = tid - 128, w = t >> 5, nlo = lane & 7, klo = lane >> 3;
+      const int kqb = (kq + 3) / 4, nblk8 = (BN / 8) * kqb;
+      for (int b0 = w; b0 < nblk8; b0 += 8 * 5) {              // 8 independent 16-byte loads in flight per thread
+        float4 v[8];
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int r = it * 8 + rsub;
-          *reinterpret_cast<float4*>(stA + r * 256 + (((c16 & 8) | ((c16 ^ r) & 7)) << 4)) = va[it];
+        for (int u = 0; u < 8; ++u) {
+          const int b = b0 + u * 5;
+          const int n = (b / kqb) * 8 + nlo, kc = (b % kqb) * 4 + klo;
+          v[u] = (b < nblk8 && kc < kq && n0 + n < g.Nc) ? ldg4(g.B + (size_t)(n0 + n) * g.ldb + kc * 4) : f4zero();
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-        for (int q = 0; q < KC / 4; ++q)
-          va[q] = *reinterpret_cast<const float4*>(stA + tid * 256 + (((q & 8) | ((q ^ tid) & 7)) << 4));
-        mbar_wait(&bars.a_empty[stage], ph ^ 1);
-        fence_after();
-        const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
-#pragma unroll
-        for (int grp = 0; grp < KC / 16; ++grp) {
-          if (grp * 16 < kw) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 v = va[grp * 4 + q];
-              hi[q * 4 + 0] = tf32_hi(v.x); lo[q * 4 + 0] = tf32_lo(v.x, hi[q * 4 + 0]);
-              hi[q * 4 + 1] = tf32_hi(v.y); lo[q * 4 + 1] = tf32_lo(v.y, hi[q * 4 + 1]);
-              hi[q * 4 + 2] = tf32_hi(v.z); lo[q * 4 + 2] = tf32_lo(v.z, hi[q * 4 + 2]);
-              hi[q * 4 + 3] = tf32_hi(v.w); lo[q * 4 + 3] = tf32_lo(v.w, hi[q * 4 + 3]);
-            }
-            tmem_st16(t_hi + grp * 16, hi);
-            tmem_st16(t_hi + KC + grp * 16, lo);
+        for (int u = 0; u < 8; ++u) {
+          const int b = b0 + u * 5;
+          const int n = (b / kqb) * 8 + nlo, kc = (b % kqb) * 4 + klo;
+          if (b < nblk8 && kc < kq) {
+            uint4 h, l;
+            h.x = tf32_hi(v[u].x); h.y = tf32_hi(v[u].y); h.z = tf32_hi(v[u].z); h.w = tf32_hi(v[u].w);
+            l.x = tf32_lo(v[u].x, h.x); l.y = tf32_lo(v[u].y, h.y); l.z = tf32_lo(v[u].z, h.z); l.w = tf32_lo(v[u].w, h.w);
+            const size_t off = (size_t)(n >> 3) * SBO + (n & 7) * 16 + (size_t)kc * LBO;
+            *reinterpret_cast<uint4*>(sBhi + off) = h;
+            *reinterpret_cast<uint4*>(sBlo + off) = l;
           }
         }
-        tmem_wait_st();
-        fence_before();
-        mbar_arrive(&bars.a_full[stage]);
-        stage ^= 1;
-        if (stage == 0) ph ^= 1;
       }
     }
-  } else if (warp == 4) {
+    fence_async_smem();                                      // generic-proxy smem writes -> visible to the MMA (async proxy)
+    asm volatile("bar.sync 3, 160;" ::: "memory");
+  if (warp == 4) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, BN);
       const uint32_t bhi0 = smem_u32(sBhi), blo0 = smem_u32(sBlo);
       uint32_t stage = 0, ph = 0, ds = 0, dph = 0;
-      for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+      int tr_i = 0;
+      for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, ++tr_i) {
         mbar_wait(&bars.d_empty[ds], dph ^ 1);
         fence_after();
+        TRACE(1, tr_i, 0);
         const uint32_t t_d = tmem + D_COL + ds * 128;
         for (int ch = 0; ch < nchunks; ++ch) {
           const int k0 = ch * KC;
           const int kw = min(KC, K - k0);
           mbar_wait(&bars.a_full[stage], ph);
           fence_after();
+          TRACE(1, tr_i, 1);
           const uint32_t t_hi = tmem + A_COL + stage * 128;
           for (int s = 0; s < kw / 8; ++s) {
             const uint32_t koff = (uint32_t)((k0 >> 3) + s) * 2 * LBO;   // 8 K-elements = two 16-byte core columns
@@ -249,6 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_nt_tc(NtArgs g) {
           if (stage == 0) ph ^= 1;
         }
         mma_commit(&bars.d_full[ds]);
+        TRACE(1, tr_i, 2);
         ds ^= 1;
         if (ds == 0) dph ^= 1;
       }
@@ -265,12 +329,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_nt_tc(NtArgs g) {
     unsigned char* stD = smem + (size_t)BN * K * 8 + 32 * 1024;
     const int c8 = et & 7, rsub = et >> 3;         // coalesced phase: 16-byte chunk within the 128-byte row, row in a pass of 16
     uint32_t ds = 0, dph = 0;
-    for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+    int tr_i = 0;
+    float4 bv[4];                                  // bias of this thread's 4 columns in each of the <= 4 slabs
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+      const int col = n0 + sl * 32 + c8 * 4;
+      bv[sl] = (g.bias && sl * 32 + c8 * 4 < BN && col < g.Nc) ? ldg4(g.bias + col) : f4zero();
+    }
+    for (int mt = blockIdx.x; mt < mtiles; mt += gridDim.x, ++tr_i) {
       const int row0 = mt * 128;
+      TRACE(2, tr_i, 0);
       mbar_wait(&bars.d_full[ds], dph);
       fence_after();
+      TRACE(2, tr_i, 1);
       const uint32_t t_d = tmem + lane_off + D_COL + ds * 128;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const int c0 = sl * 32;
+        if (c0 >= BN) break;
         uint32_t r0[16], r1[16];
         tmem_ld16(t_d + c0, r0);
         tmem_ld16(t_d + c0 + 16, r1);              // columns >= BN of the 128-column stage are never stored
@@ -286,15 +362,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_nt_tc(NtArgs g) {
         asm volatile("bar.sync 2, 128;" ::: "memory");
         const int col = n0 + c0 + c8 * 4;
         if (c0 + c8 * 4 < BN && col < g.Nc) {
-          float4 bv = f4zero();
-          if (g.bias) bv = ldg4(g.bias + col);
           float* cbase = g.C + (size_t)(col / g.c_cb) * g.c_cbs + (col % g.c_cb);
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 16 + rsub;
             if (row0 + r < g.M) {
               float4 o = *reinterpret_cast<const float4*>(stD + r * 128 + (((c8 ^ r) & 7) << 4));
-              o = f4add(o, bv);
+              o = f4add(o, bv[sl]);
               if (g.relu) o = f4max(o, f4zero());
               st4(cbase + (size_t)(row0 + r) * g.ldc, o);
             }
@@ -303,12 +377,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_nt_tc(NtArgs g) {
       }
       fence_before();
       mbar_arrive(&bars.d_empty[ds]);
+      TRACE(2, tr_i, 2);
       ds ^= 1;
       if (ds == 0) dph ^= 1;
     }
   }
+  }
   fence_before();
   __syncthreads();
+  if (tid == 0) TRACE(3, 1, 2);
+  CTA_T(1);
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
@@ -330,12 +408,15 @@ struct TnBars {
   uint64_t full[2], empty[2], done;
 };
 
-// grid: (splits over R, Mc / 128); one CTA per SM
+// grid: (splits over R, Mc / 128); one CTA per SM.  NPMAX = upper bound of NcP / 8 (register budget of the B producer)
+template <int NPMAX>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) TnBars bars;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) TRACE(3, 1, 0);
+  CTA_T(0);
   const int NcP = g.NcP;
   const uint32_t LBO = 128, SBO = (RC / 4) * 128;
   const size_t stage_bytes = (size_t)NcP * RC * 4;      // one of hi / lo
@@ -356,6 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
   __syncthreads();
   fence_after();
   const uint32_t tmem = s_tmem;
+  if (tid == 0) TRACE(3, 1, 1);
   const int r_begin = blockIdx.x * g.rows_per_split;
   const int r_end = min(g.R, r_begin + g.rows_per_split);
   const int nch = (r_end - r_begin + RC - 1) / RC;
@@ -369,16 +451,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     uint32_t stage = 0, ph = 0;
     float csum = 0.f;
-    for (int c = 0; c < nch; ++c) {
+    // (a register double buffer -- next chunk's loads issued before this chunk is converted -- was measured SLOWER:
+    // the SM's global-load path is the limit here, 256 outstanding 128-byte requests already take ~2500 cycles to issue)
+    float av0[RC];
+    auto loadA = [&](float (&av)[RC], int c) {
       const int r0 = r_begin + c * RC;
       const float* p = acol + (size_t)r0 * g.lda;
-      float av[RC];
 #pragma unroll
       for (int i = 0; i < RC; ++i) av[i] = (mok && r0 + i < r_end) ? __ldg(p + (size_t)i * g.lda) : 0.f;
+    };
+    auto procA = [&](float (&av)[RC], int c) {
+      TRACE(0, c, 0);
 #pragma unroll
       for (int i = 0; i < RC; ++i) csum += av[i];
       mbar_wait(&bars.empty[stage], ph ^ 1);
       fence_after();
+      TRACE(0, c, 1);
       const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
 #pragma unroll
       for (int grp = 0; grp < RC / 16; ++grp) {
@@ -394,14 +482,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
       tmem_wait_st();
       fence_before();
       mbar_arrive(&bars.full[stage]);
+      TRACE(0, c, 2);
       stage ^= 1;
       if (stage == 0) ph ^= 1;
+    };
+    for (int c = 0; c < nch; ++c) {
+      loadA(av0, c);
+      procA(av0, c);
     }
     if (g.colsum && mok && nch > 0) atomicAdd(g.colsum + mcol, csum);
     // ---- epilogue: D -> REDG.128 into C
     if (nch > 0) {
       mbar_wait(&bars.done, 0);
       fence_after();
+      TRACE(3, 0, 0);
       for (int c0 = 0; c0 < NcP; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_off + D_COL + c0, r);
@@ -415,6 +509,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
                                             __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
         }
       }
+      TRACE(3, 0, 1);
     }
   } else if (warp < 8) {
     // ================= B producer: [RC rows, Nc] -> smem stage, K-major (K = row), hi/lo =================
@@ -423,29 +518,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
     const int ln = lane & 7, lr = lane >> 3;
     const int npatch_n = NcP / 8;
     uint32_t stage = 0, ph = 0;
-    for (int c = 0; c < nch; ++c) {
+    // all of this thread's loads of a chunk are issued before anything is stored (a load -> STS loop would serialise
+    // one memory latency per element: the compiler cannot hoist loads over the shared-memory stores)
+    float xv0[RC / 16][NPMAX];
+    auto loadB = [&](float (&xv)[RC / 16][NPMAX], int c) {
       const int r0 = r_begin + c * RC;
-      mbar_wait(&bars.empty[stage], ph ^ 1);
-      unsigned char* sBhi = smem + (size_t)stage * 2 * stage_bytes;
-      unsigned char* sBlo = sBhi + stage_bytes;
-      for (int rp = w; rp < RC / 4; rp += 4) {          // row patch (4 rows)
-        const int r = rp * 4 + lr;
+#pragma unroll
+      for (int i = 0; i < RC / 16; ++i) {
+        const int r = (w + 4 * i) * 4 + lr;
         const bool rok = r0 + r < r_end;
         const float* brow = g.B + (size_t)(r0 + (rok ? r : 0)) * g.ldb;
-        const size_t roff = (size_t)(r >> 2) * LBO + (r & 3) * 4;
-        for (int np = 0; np < npatch_n; ++np) {
+#pragma unroll
+        for (int np = 0; np < NPMAX; ++np) {
           const int n = np * 8 + ln;
-          const float x = (rok && n < g.Nc) ? __ldg(brow + n) : 0.f;
-          const uint32_t h = tf32_hi(x);
-          const size_t off = (size_t)np * SBO + ln * 16 + roff;
-          *reinterpret_cast<uint32_t*>(sBhi + off) = h;
-          *reinterpret_cast<uint32_t*>(sBlo + off) = tf32_lo(x, h);
+          xv[i][np] = (rok && np < npatch_n && n < g.Nc) ? __ldg(brow + n) : 0.f;
+        }
+      }
+    };
+    auto procB = [&](float (&xv)[RC / 16][NPMAX], int c) {
+      TRACE(1, c, 0);
+      mbar_wait(&bars.empty[stage], ph ^ 1);
+      TRACE(1, c, 1);
+      unsigned char* sBhi = smem + (size_t)stage * 2 * stage_bytes;
+      unsigned char* sBlo = sBhi + stage_bytes;
+#pragma unroll
+      for (int i = 0; i < RC / 16; ++i) {
+        const int r = (w + 4 * i) * 4 + lr;
+        const size_t roff = (size_t)(r >> 2) * LBO + (r & 3) * 4;
+#pragma unroll
+        for (int np = 0; np < NPMAX; ++np) {
+          if (np < npatch_n) {
+            const float x = xv[i][np];
+            const uint32_t h = tf32_hi(x);
+            const size_t off = (size_t)np * SBO + ln * 16 + roff;
+            *reinterpret_cast<uint32_t*>(sBhi + off) = h;
+            *reinterpret_cast<uint32_t*>(sBlo + off) = tf32_lo(x, h);
+          }
         }
       }
       fence_async_smem();
       mbar_arrive(&bars.full[stage]);
+      TRACE(1, c, 2);
       stage ^= 1;
       if (stage == 0) ph ^= 1;
+    };
+    for (int c = 0; c < nch; ++c) {
+      loadB(xv0, c);
+      procB(xv0, c);
     }
   } else {
     // ================= MMA issuer =================
@@ -455,6 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
       for (int c = 0; c < nch; ++c) {
         mbar_wait(&bars.full[stage], ph);
         fence_after();
+        TRACE(2, c, 0);
         const uint32_t bhi0 = smem_u32(smem + (size_t)stage * 2 * stage_bytes);
         const uint32_t blo0 = bhi0 + (uint32_t)stage_bytes;
         const uint32_t t_hi = tmem + A_COL + stage * 128;
@@ -468,6 +588,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
           mma_ts(tmem + D_COL, t_hi + s * 8, blo, idesc, 1u);
         }
         mma_commit(&bars.empty[stage]);
+        TRACE(2, c, 1);
         stage ^= 1;
         if (stage == 0) ph ^= 1;
       }
@@ -477,6 +598,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
   }
   fence_before();
   __syncthreads();
+  if (tid == 0) TRACE(3, 1, 2);
+  CTA_T(1);
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
@@ -537,8 +660,9 @@ int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
   splits = (int)((R + rps - 1) / rps);
   const size_t smem = (size_t)NcP * RC * 4 * 2 * 2;
   TnArgs g{A, lda, a_cb, a_cbs, B, ldb, C, ldc, a_colsum, (int)R, Mc, Nc, NcP, rps};
-  cudaError_t e = cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = NcP <= 64 ? k_gemm_tn_tc<8> : k_gemm_tn_tc<16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k_gemm_tn_tc<<<dim3(splits, mblk), TC_THREADS, smem, st>>>(g);
+  kern<<<dim3(splits, mblk), TC_THREADS, smem, st>>>(g);
   return PERT_OK;
 }
