@@ -23,6 +23,7 @@ struct SmallGemm {
   int M, N, K;
   int sam, sak, sbk, sbn, ldc;
   int relu, accumulate, ksplit;
+  int atomic;         // accumulate with atomicAdd (several problems of one launch add into the same C)
 };
 #define SG_MAX 12
 struct SmallGemmBatch {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) k_small_gemm(SmallGemmBatch batch) {
       float v = acc[i][j];
       if (g.bias && kpart == 0) v += __ldg(g.bias + n);
       float* c = g.C + (size_t)m * g.ldc + n;
-      if (ks > 1) {
+      if (ks > 1 || g.atomic) {
         atomicAdd(c, v);  // split-K: C pre-zeroed / accumulating, no relu/mask
       } else {
         if (g.relu) v = fmaxf(v, 0.f);
@@ -137,6 +138,7 @@ SmallGemm sg(const float* A, int sam, int sak, const float* B, int sbk, int sbn,
   g.A = A; g.B = B; g.bias = bias; g.mask = mask; g.C = C; g.M = M; g.N = N; g.K = K;
   g.sam = sam; g.sak = sak; g.sbk = sbk; g.sbn = sbn; g.ldc = ldc;
   g.relu = relu; g.accumulate = accumulate; g.ksplit = ksplit;
+  g.atomic = 0;
   return g;
 }
 
@@ -147,7 +149,7 @@ struct Seg {
   int rows, cols, src_ld, dst_ld;
   int transpose;  // dst[c*dst_ld + r] = src[r*src_ld + c]
 };
-#define SEG_MAX 40
+#define SEG_MAX 96   // 96 x 40 B of kernel parameters; layers are grouped into as few launches as fit
 struct SegList {
   Seg s[SEG_MAX];
   int count;
@@ -277,9 +279,8 @@ Ws carve(const PertModelDesc* d, long long N, long long E, long long B, float* b
 
 // segment list of conv layer l: weights -> W4 / W4^T (conv 0: columns permuted to [emb | x | pad]), biases,
 // lin_edge halves and their transposes
-SegList layer_segs(const PertModelDesc* d, const Ws& w, float* base, int l) {
-  SegList S;
-  S.count = 0;
+constexpr int SEGS_PER_LAYER_MAX = 24;
+void append_layer_segs(SegList& S, const PertModelDesc* d, const Ws& w, float* base, int l) {
   const int H = d->H, F = d->F, K = k_of(d, l);
   const int Din = (l == 0) ? F + H : H;
   auto add = [&](long long src, float* dst, int rows, int cols, int src_ld, int dst_ld, int tr) {
@@ -308,13 +309,13 @@ SegList layer_segs(const PertModelDesc* d, const Ws& w, float* base, int l) {
   add(d->off_we[l] + H, w.weB[l], H, H, 2 * H, H, 0);
   add(d->off_we[l], w.weAt[l], H, H, 2 * H, H, 1);
   add(d->off_we[l] + H, w.weBt[l], H, H, 2 * H, H, 1);
-  return S;
 }
 // same list but pointing at the packed-gradient buffers (for k_unpack)
-SegList layer_grad_segs(const PertModelDesc* d, const Ws& w, float* base, int l) {
-  SegList S = layer_segs(d, w, base, l);
+void append_layer_grad_segs(SegList& S, const PertModelDesc* d, const Ws& w, float* base, int l) {
+  const int first = S.count;
+  append_layer_segs(S, d, w, base, l);
   // remap dst from parameter pack to gradient pack (same relative layout inside each buffer)
-  for (int i = 0; i < S.count; ++i) {
+  for (int i = first; i < S.count; ++i) {
     Seg& s = S.s[i];
     if (s.transpose) continue;
     float* p = base + s.dst;
@@ -324,7 +325,6 @@ SegList layer_grad_segs(const PertModelDesc* d, const Ws& w, float* base, int l)
     else if (p == w.weA[l]) s.dst = w.dweA[l] - base;
     else if (p == w.weB[l]) s.dst = w.dweB[l] - base;
   }
-  return S;
 }
 
 int check_desc(const PertModelDesc* d) {
@@ -383,9 +383,16 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
   cudaStream_t st = (cudaStream_t)stream;
   const int H = d->H, L = d->n_convs;
   // 1. pack parameters (one launch per layer) and build the edge tables of all layers (one grouped launch each <=6)
-  for (int l = 0; l < L; ++l) {
-    SegList S = layer_segs(d, w, base, l);
-    k_pack<<<dim3(8, S.count), 256, 0, st>>>(params, base, S);
+  {
+    SegList S;
+    S.count = 0;
+    for (int l = 0; l < L; ++l) {
+      append_layer_segs(S, d, w, base, l);
+      if (S.count + SEGS_PER_LAYER_MAX > SEG_MAX || l == L - 1) {
+        k_pack<<<dim3(8, S.count), 256, 0, st>>>(params, base, S);
+        S.count = 0;
+      }
+    }
   }
   {
     SmallGemmBatch gb;
@@ -522,16 +529,27 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
       int ks_if = d->n_if >= 512 ? 8 : 1, ks_rpc = 1;
       gb.p[gb.count++] = sg(w.dt_if[l], 1, H, params + d->off_if, H, 1, nullptr, w.dweA[l], H, H, H, d->n_if, 0, 1, ks_if);
       gb.p[gb.count++] = sg(w.dt_rpc[l], 1, H, params + d->off_rpc, H, 1, nullptr, w.dweB[l], H, H, H, d->n_rpc, 0, 1, ks_rpc);
-      gb.p[gb.count++] = sg(w.dt_if[l], H, 1, w.weA[l], H, 1, nullptr, grads + d->off_if, H, d->n_if, H, H, 0, 1);
-      gb.p[gb.count++] = sg(w.dt_rpc[l], H, 1, w.weB[l], H, 1, nullptr, grads + d->off_rpc, H, d->n_rpc, H, H, 0, 1);
-      // accumulating into the same embedding-gradient rows from several layers must be serialised: one launch per layer
-      launch_small(gb, st);
-      gb.count = 0;
+      // every layer adds into the same embedding-gradient rows: atomic accumulation, all layers in one launch
+      gb.p[gb.count] = sg(w.dt_if[l], H, 1, w.weA[l], H, 1, nullptr, grads + d->off_if, H, d->n_if, H, H, 0, 1);
+      gb.p[gb.count++].atomic = 1;
+      gb.p[gb.count] = sg(w.dt_rpc[l], H, 1, w.weB[l], H, 1, nullptr, grads + d->off_rpc, H, d->n_rpc, H, H, 0, 1);
+      gb.p[gb.count++].atomic = 1;
+      if (gb.count + 4 > SG_MAX || l == 0 + L - 1) {
+        launch_small(gb, st);
+        gb.count = 0;
+      }
     }
   }
-  for (int l = 0; l < L; ++l) {
-    SegList S = layer_grad_segs(d, w, base, l);
-    k_unpack<<<dim3(8, S.count), 256, 0, st>>>(grads, base, S);
+  {
+    SegList S;
+    S.count = 0;
+    for (int l = 0; l < L; ++l) {
+      append_layer_grad_segs(S, d, w, base, l);
+      if (S.count + SEGS_PER_LAYER_MAX > SEG_MAX || l == L - 1) {
+        k_unpack<<<dim3(8, S.count), 256, 0, st>>>(grads, base, S);
+        S.count = 0;
+      }
+    }
   }
   PERT_LAUNCH_CHECK();
   return PERT_OK;
