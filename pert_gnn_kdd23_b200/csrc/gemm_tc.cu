@@ -603,7 +603,303 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient, TMA-fed: the same MMA scheme as k_gemm_tn_tc, but the operands reach the SM through a dedicated
+// loader warp issuing bulk copies (cp.async.bulk -> mbarrier complete_tx) into an NS-deep shared-memory ring,
+// so the bytes in flight per SM (NS x ~50 KB) no longer depend on how many loads the converter warps can keep
+// outstanding (the LDG path saturated at ~32 KB / 2500 cycles per SM), and the chunks are handed out dynamically
+// from a self-resetting global counter (static splits finished between 18 and 29 us on equal work).
+//   warp 9     loader: next chunk id <- atomicAdd; the chunk's rows of every column piece of A (a piece = pw columns
+//              inside one column block; with dense blocks, lda == pw, the piece is ONE contiguous 16 KB copy) and of
+//              B (one copy when ldb == Nc) -> ring stage.  Small copies are slow (measured ~70 cycles per 256-byte
+//              cp.async.bulk), so the per-row form is only the fallback for strided operands.
+//   warps 0-3  A converters: column t over the chunk's rows (LDS, conflict free) -> hi/lo -> TMEM
+//   warps 4-7  B converters: a lane reads 4 consecutive rows of one column (LDS.32, 32 lanes = 32 columns) and
+//              stores them as one 16-byte K-quad of the K-major operand stage (hi and lo)
+//   warp 8     MMA issuer
+// A chunk id >= nchunks is the stop sentinel; it travels through the ring and the operand stages.
+__device__ unsigned int g_tn_ctr[8];   // per blockIdx.y; the CTA drawing the last ticket resets it (one launch at a time)
+
+__device__ __forceinline__ void mbar_arrive_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int TMA_THREADS = 320;
+constexpr int RING_MAX = 4;
+struct TnTmaArgs {
+  const float* A;
+  int lda, a_cb;
+  long long a_cbs;
+  const float* B;
+  int ldb;
+  float* C;
+  int ldc;
+  float* colsum;
+  int R, Mc, Nc, NcP, nchunks, NS, pw, a_contig, b_contig;
+};
+struct TnTmaBars {
+  uint64_t ring_full[RING_MAX], ring_empty[RING_MAX], op_full[2], op_empty[2], done;
+  int ring_meta[RING_MAX], op_meta[2];
+};
+
+template <int GMAX>   // B-converter items (row quad x 32-column group) per warp: 4 * ceil(NcP / 32)
+__global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) TnTmaBars bars;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  CTA_T(0);
+  const int NcP = g.NcP, NS = g.NS;
+  const uint32_t LBO = 128, SBO = (RC / 4) * 128;
+  const size_t op_bytes = (size_t)NcP * RC * 4;           // one of hi / lo of one operand stage
+  unsigned char* ring0 = smem + 4 * op_bytes;
+  const int a_stage = RC * 512;
+  const int ring_bytes = a_stage + RC * g.Nc * 4;
+  const int m0 = blockIdx.y * 128;
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < RING_MAX; ++s) {
+      mbar_init(&bars.ring_full[s], 1);
+      mbar_init(&bars.ring_empty[s], 256);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.op_full[s], 256);
+      mbar_init(&bars.op_empty[s], 1);
+    }
+    mbar_init(&bars.done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 9) {
+    // ================= loader =================
+    const int pw = g.pw, npieces = 128 / pw;
+    const int vcols = min(128, g.Mc - m0);                 // multiple of pw
+    uint32_t rs = 0, rph = 0;
+    while (true) {
+      unsigned int c = 0;
+      if (lane == 0) c = atomicAdd(&g_tn_ctr[blockIdx.y], 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      mbar_wait(&bars.ring_empty[rs], rph ^ 1);
+      if (c >= (unsigned int)g.nchunks) {
+        if (lane == 0) {
+          if (c == (unsigned int)g.nchunks + gridDim.x - 1) g_tn_ctr[blockIdx.y] = 0;   // last ticket of the launch
+          bars.ring_meta[rs] = -1;
+          mbar_arrive(&bars.ring_full[rs]);
+        }
+        break;
+      }
+      const int r0 = (int)c * RC;
+      const int rows = min(RC, g.R - r0);
+      unsigned char* sA = ring0 + (size_t)rs * ring_bytes;
+      unsigned char* sB = sA + a_stage;
+      if (lane == 0) {
+        bars.ring_meta[rs] = rows;
+        mbar_arrive_tx(&bars.ring_full[rs], (uint32_t)rows * (uint32_t)(vcols + g.Nc) * 4u);
+      }
+      __syncwarp();
+      // stage layout: A piece-major [npieces][RC][pw], B [RC][Nc]
+      if (g.a_contig) {
+        if (lane < npieces && lane * pw < vcols) {
+          const int col = m0 + lane * pw;
+          bulk_g2s(sA + (size_t)lane * RC * pw * 4,
+                   g.A + (size_t)(col / g.a_cb) * g.a_cbs + (col % g.a_cb) + (size_t)r0 * g.lda, rows * pw * 4,
+                   &bars.ring_full[rs]);
+        }
+      } else {
+        for (int i = lane; i < rows * npieces; i += 32) {
+          const int p = i / rows, r = i - p * rows;
+          const int col = m0 + p * pw;
+          if (p * pw < vcols)
+            bulk_g2s(sA + ((size_t)p * RC + r) * pw * 4,
+                     g.A + (size_t)(col / g.a_cb) * g.a_cbs + (col % g.a_cb) + (size_t)(r0 + r) * g.lda, pw * 4,
+                     &bars.ring_full[rs]);
+        }
+      }
+      if (g.b_contig) {
+        if (lane == 31) bulk_g2s(sB, g.B + (size_t)r0 * g.ldb, rows * g.Nc * 4, &bars.ring_full[rs]);
+      } else {
+        for (int r = lane; r < rows; r += 32)
+          bulk_g2s(sB + (size_t)r * g.Nc * 4, g.B + (size_t)(r0 + r) * g.ldb, g.Nc * 4, &bars.ring_full[rs]);
+      }
+      if (++rs == (uint32_t)NS) { rs = 0; rph ^= 1; }
+    }
+  } else if (warp < 4) {
+    // ================= A converters + epilogue =================
+    const int mcol = m0 + tid;
+    const bool mok = mcol < g.Mc;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int a_off = (tid / g.pw) * RC * g.pw + (tid % g.pw);   // piece-major stage layout
+    uint32_t rs = 0, rph = 0, stage = 0, ph = 0;
+    int nproc = 0;
+    float csum = 0.f;
+    while (true) {
+      mbar_wait(&bars.ring_full[rs], rph);
+      const int rows = bars.ring_meta[rs];
+      if (rows < 0) break;
+      const float* sA = reinterpret_cast<const float*>(ring0 + (size_t)rs * ring_bytes) + a_off;
+      float av[RC];
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        const float v = sA[i * g.pw];
+        av[i] = (mok && i < rows) ? v : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < RC; ++i) csum += av[i];
+      mbar_wait(&bars.op_empty[stage], ph ^ 1);
+      fence_after();
+      const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
+#pragma unroll
+      for (int grp = 0; grp < RC / 16; ++grp) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          hi[i] = tf32_hi(av[grp * 16 + i]);
+          lo[i] = tf32_lo(av[grp * 16 + i], hi[i]);
+        }
+        tmem_st16(t_hi + grp * 16, hi);
+        tmem_st16(t_hi + RC + grp * 16, lo);
+      }
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&bars.ring_empty[rs]);               // every staged value has been consumed
+      if (tid == 0) bars.op_meta[stage] = rows;
+      mbar_arrive(&bars.op_full[stage]);
+      ++nproc;
+      stage ^= 1;
+      if (stage == 0) ph ^= 1;
+      if (++rs == (uint32_t)NS) { rs = 0; rph ^= 1; }
+    }
+    mbar_wait(&bars.op_empty[stage], ph ^ 1);          // pass the stop sentinel on to the MMA warp
+    if (tid == 0) bars.op_meta[stage] = -1;
+    mbar_arrive(&bars.op_full[stage]);
+    if (g.colsum && mok && nproc > 0) atomicAdd(g.colsum + mcol, csum);
+    if (nproc > 0) {
+      mbar_wait(&bars.done, 0);
+      fence_after();
+      for (int c0 = 0; c0 < NcP; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_off + D_COL + c0, r);
+        tmem_wait_ld();
+        if (mok) {
+          float* dst = g.C + (size_t)mcol * g.ldc + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (c0 + q * 4 < g.Nc)
+              red4(dst + q * 4, make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                            __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3])));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ================= B converters: ring stage [rows, Nc] -> K-major (K = row) hi/lo operand stage =================
+    const int w = warp - 4;
+    const int ngrp = (NcP + 31) / 32, items = (RC / 4) * ngrp;
+    uint32_t rs = 0, rph = 0, stage = 0, ph = 0;
+    while (true) {
+      mbar_wait(&bars.ring_full[rs], rph);
+      const int rows = bars.ring_meta[rs];
+      if (rows < 0) break;
+      const float* sBr = reinterpret_cast<const float*>(ring0 + (size_t)rs * ring_bytes + a_stage);
+      float xv[GMAX][4];
+#pragma unroll
+      for (int j = 0; j < GMAX; ++j) {
+        const int it = w + 4 * j;
+        const int rq = it / ngrp, n = (it - rq * ngrp) * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = rq * 4 + q;
+          float v = 0.f;
+          if (it < items && n < g.Nc) v = sBr[r * g.Nc + n];
+          xv[j][q] = r < rows ? v : 0.f;
+        }
+      }
+      mbar_wait(&bars.op_empty[stage], ph ^ 1);
+      unsigned char* sBhi = smem + (size_t)stage * 2 * op_bytes;
+      unsigned char* sBlo = sBhi + op_bytes;
+#pragma unroll
+      for (int j = 0; j < GMAX; ++j) {
+        const int it = w + 4 * j;
+        const int rq = it / ngrp, n = (it - rq * ngrp) * 32 + lane;
+        if (it < items && n < NcP) {
+          uint4 h, l;
+          h.x = tf32_hi(xv[j][0]); h.y = tf32_hi(xv[j][1]); h.z = tf32_hi(xv[j][2]); h.w = tf32_hi(xv[j][3]);
+          l.x = tf32_lo(xv[j][0], h.x); l.y = tf32_lo(xv[j][1], h.y);
+          l.z = tf32_lo(xv[j][2], h.z); l.w = tf32_lo(xv[j][3], h.w);
+          const size_t off = (size_t)(n >> 3) * SBO + (n & 7) * 16 + (size_t)rq * LBO;
+          *reinterpret_cast<uint4*>(sBhi + off) = h;
+          *reinterpret_cast<uint4*>(sBlo + off) = l;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&bars.ring_empty[rs]);
+      mbar_arrive(&bars.op_full[stage]);
+      stage ^= 1;
+      if (stage == 0) ph ^= 1;
+      if (++rs == (uint32_t)NS) { rs = 0; rph ^= 1; }
+    }
+    mbar_wait(&bars.op_empty[stage], ph ^ 1);
+    mbar_arrive(&bars.op_full[stage]);
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, NcP);
+      uint32_t stage = 0, ph = 0;
+      int n = 0;
+      while (true) {
+        mbar_wait(&bars.op_full[stage], ph);
+        fence_after();
+        if (bars.op_meta[stage] < 0) break;
+        const uint32_t bhi0 = smem_u32(smem + (size_t)stage * 2 * op_bytes);
+        const uint32_t blo0 = bhi0 + (uint32_t)op_bytes;
+        const uint32_t t_hi = tmem + A_COL + stage * 128;
+#pragma unroll
+        for (int s = 0; s < RC / 8; ++s) {
+          const uint32_t koff = (uint32_t)s * 2 * LBO;
+          const uint64_t bhi = make_desc(bhi0 + koff, LBO, SBO);
+          const uint64_t blo = make_desc(blo0 + koff, LBO, SBO);
+          mma_ts(tmem + D_COL, t_hi + s * 8, bhi, idesc, (n | s) ? 1u : 0u);
+          mma_ts(tmem + D_COL, t_hi + RC + s * 8, bhi, idesc, 1u);
+          mma_ts(tmem + D_COL, t_hi + s * 8, blo, idesc, 1u);
+        }
+        mma_commit(&bars.op_empty[stage]);
+        ++n;
+        stage ^= 1;
+        if (stage == 0) ph ^= 1;
+      }
+      if (n > 0) mma_commit(&bars.done);
+    }
+    __syncwarp();
+  }
+  fence_before();
+  __syncthreads();
+  CTA_T(1);
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static bool tma_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PERT_GEMM_TMA");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 static bool tc_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -653,6 +949,30 @@ int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
   if (Nc % 4 || Nc > 128 || ldc % 4 || !al16(C)) return PERT_ERR_UNSUPPORTED;
   const int NcP = (Nc + 15) / 16 * 16;
   const int mblk = (Mc + 127) / 128;
+  if (tma_enabled() && mblk <= 8) {
+    // TMA-fed kernel: rows of A are copied in pieces of pw columns that never straddle a column block
+    const int pw = a_cb < 128 ? a_cb : 128;
+    const bool ok = pw >= 4 && 128 % pw == 0 && a_cb % pw == 0 && Mc % pw == 0 && lda % 4 == 0 && a_cbs % 4 == 0 &&
+                    ldb % 4 == 0 && al16(A) && al16(B);
+    const size_t op = (size_t)NcP * RC * 4 * 2 * 2;
+    const size_t ring = (size_t)RC * 512 + (size_t)RC * Nc * 4;
+    int NS = (int)((226 * 1024 - op) / ring);
+    if (NS > RING_MAX) NS = RING_MAX;
+    if (ok && NS >= 2) {
+      const int nchunks = (int)((R + RC - 1) / RC);
+      int gx = PERT_NUM_SMS / mblk;
+      if (gx < 1) gx = 1;
+      if (gx > nchunks) gx = nchunks;
+      TnTmaArgs g{A,        lda, a_cb, a_cbs, B,   ldb,     C,  ldc, a_colsum,
+                  (int)R,   Mc,  Nc,   NcP,   nchunks, NS, pw, lda == pw ? 1 : 0, ldb == Nc ? 1 : 0};
+      const size_t smem = op + ring * NS;
+      auto kern = NcP <= 64 ? k_gemm_tn_tma<8> : (NcP <= 96 ? k_gemm_tn_tma<12> : k_gemm_tn_tma<16>);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      kern<<<dim3(gx, mblk), TMA_THREADS, smem, st>>>(g);
+      return PERT_OK;
+    }
+  }
   int splits = PERT_NUM_SMS / mblk;
   if (splits < 1) splits = 1;
   int rps = (int)((R + splits - 1) / splits);
