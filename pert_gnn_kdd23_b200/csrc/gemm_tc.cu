@@ -24,6 +24,7 @@
 //       smem layout (bank-conflict-free 8x4 patches) | warp 8 issues the MMAs.
 // These GEMMs are HBM-bound (K <= 256): A read once, C written once; the tensor cores only have to keep up.
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 
 namespace {
@@ -891,6 +892,311 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Forward / data-gradient GEMM, TMA-tiled: same roles and MMA scheme as k_gemm_nt_tc, but the A tiles are fetched by
+// a loader warp with 2-D tensor-map copies (cp.async.bulk.tensor, one [128 rows x 32 floats] box per 128-byte swizzle
+// span, SWIZZLE_128B) into an NS-deep ring, so the converter warps never issue global loads and their row-per-thread
+// 16-byte reads are bank-conflict free by the hardware swizzle (16-byte slot c of row r sits at slot c ^ (r & 7)).
+// Tiles are handed out dynamically from a self-resetting ticket counter (one per N block); the tile id travels with
+// the data: ring_meta -> a_meta -> d_meta, a negative id is the stop sentinel.
+// A is addressed as a 2-D tensor [row_blk * nblocks, a_cb] with pitch lda: column block b of a blocked operand starts at
+// tensor row b * row_blk (row_blk = a_cbs / lda), rows beyond M of a block alias the next block (their products are
+// never stored) and out-of-range columns / rows are zero-filled by the TMA unit.
+__device__ unsigned int g_nt_ctr[8];
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct NtTmaBars {
+  uint64_t ring_full[RING_MAX], ring_empty[RING_MAX], a_full[2], a_empty[2], d_full[2], d_empty[2];
+  int ring_meta[RING_MAX], a_meta[2], d_meta[2];
+};
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+    k_gemm_nt_tma(const __grid_constant__ CUtensorMap tmA, NtArgs g, int NS, int row_blk) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) NtTmaBars bars;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  CTA_T(0);
+  const int K = g.K, BN = g.BN;
+  const int n0 = blockIdx.y * BN;
+  const uint32_t LBO = 128, SBO = (uint32_t)(K / 4) * 128;
+  const int kq = K / 4;
+  unsigned char* sBhi = smem;
+  unsigned char* sBlo = smem + (size_t)BN * K * 4;
+  // swizzle atoms need 1024-byte alignment in the shared address space
+  unsigned char* ring0 = smem + (size_t)BN * K * 8;
+  ring0 += (1024u - (smem_u32(ring0) & 1023u)) & 1023u;
+  unsigned char* stD = ring0 + (size_t)NS * 32 * 1024;
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < RING_MAX; ++s) {
+      mbar_init(&bars.ring_full[s], 1);
+      mbar_init(&bars.ring_empty[s], 128);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.a_full[s], 128);
+      mbar_init(&bars.a_empty[s], 1);
+      mbar_init(&bars.d_full[s], 1);
+      mbar_init(&bars.d_empty[s], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = s_tmem;
+  const int mtiles = (g.M + 127) / 128;
+  const int nchunks = (K + KC - 1) / KC;
+
+  if (warp == 9) {
+    // ================= loader (one thread) =================
+    if (lane == 0) {
+      uint32_t rs = 0, rph = 0;
+      while (true) {
+        const unsigned int c = atomicAdd(&g_nt_ctr[blockIdx.y], 1u);
+        if (c >= (unsigned int)mtiles) {
+          if (c == (unsigned int)mtiles + gridDim.x - 1) g_nt_ctr[blockIdx.y] = 0;   // last ticket of the launch
+          mbar_wait(&bars.ring_empty[rs], rph ^ 1);
+          bars.ring_meta[rs] = -1;
+          mbar_arrive(&bars.ring_full[rs]);
+          break;
+        }
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int k0 = ch * KC;
+          const int kw = min(KC, K - k0);
+          const int x0 = k0 % g.a_cb, y0 = (k0 / g.a_cb) * row_blk + (int)c * 128;
+          mbar_wait(&bars.ring_empty[rs], rph ^ 1);
+          bars.ring_meta[rs] = (int)c;
+          unsigned char* st = ring0 + (size_t)rs * 32 * 1024;
+          const int nbox = kw > 32 ? 2 : 1;
+          mbar_arrive_tx(&bars.ring_full[rs], (uint32_t)nbox * 16384u);
+          tma_load_2d(st, &tmA, x0, y0, &bars.ring_full[rs]);
+          if (nbox == 2) tma_load_2d(st + 16384, &tmA, x0 + 32, y0, &bars.ring_full[rs]);
+          if (++rs == (uint32_t)NS) { rs = 0; rph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ================= A converters: ring stage (swizzled rows) -> hi/lo -> TMEM stage =================
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    uint32_t rs = 0, rph = 0, stage = 0, ph = 0;
+    int ch = 0;
+    while (true) {
+      mbar_wait(&bars.ring_full[rs], rph);
+      const int mt = bars.ring_meta[rs];
+      if (mt < 0) break;
+      const int kw = min(KC, K - ch * KC);
+      const unsigned char* row = ring0 + (size_t)rs * 32 * 1024 + tid * 128;
+      float4 vr[KC / 4];
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q)
+        vr[q] = *reinterpret_cast<const float4*>(row + (q >> 3) * 16384 + (((q & 7) ^ (tid & 7)) << 4));
+      mbar_wait(&bars.a_empty[stage], ph ^ 1);
+      fence_after();
+      const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
+#pragma unroll
+      for (int grp = 0; grp < KC / 16; ++grp) {
+        if (grp * 16 < kw) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = vr[grp * 4 + q];
+            hi[q * 4 + 0] = tf32_hi(v.x); lo[q * 4 + 0] = tf32_lo(v.x, hi[q * 4 + 0]);
+            hi[q * 4 + 1] = tf32_hi(v.y); lo[q * 4 + 1] = tf32_lo(v.y, hi[q * 4 + 1]);
+            hi[q * 4 + 2] = tf32_hi(v.z); lo[q * 4 + 2] = tf32_lo(v.z, hi[q * 4 + 2]);
+            hi[q * 4 + 3] = tf32_hi(v.w); lo[q * 4 + 3] = tf32_lo(v.w, hi[q * 4 + 3]);
+          }
+          tmem_st16(t_hi + grp * 16, hi);
+          tmem_st16(t_hi + KC + grp * 16, lo);
+        }
+      }
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&bars.ring_empty[rs]);
+      if (tid == 0) bars.a_meta[stage] = mt;
+      mbar_arrive(&bars.a_full[stage]);
+      if (++ch == nchunks) ch = 0;
+      stage ^= 1;
+      if (stage == 0) ph ^= 1;
+      if (++rs == (uint32_t)NS) { rs = 0; rph ^= 1; }
+    }
+    mbar_wait(&bars.a_empty[stage], ph ^ 1);
+    if (tid == 0) bars.a_meta[stage] = -1;
+    mbar_arrive(&bars.a_full[stage]);
+  } else {
+    // ---- B (weights) -> smem, split hi/lo, canonical K-major (warps 4-8, once per CTA, while A already streams)
+    {
+      const int t = tid - 128, w = t >> 5, nlo = lane & 7, klo = lane >> 3;
+      (void)t;
+      const int kqb = (kq + 3) / 4, nblk8 = (BN / 8) * kqb;
+      for (int b0 = w; b0 < nblk8; b0 += 8 * 5) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int b = b0 + u * 5;
+          const int n = (b / kqb) * 8 + nlo, kc = (b % kqb) * 4 + klo;
+          v[u] = (b < nblk8 && kc < kq && n0 + n < g.Nc) ? ldg4(g.B + (size_t)(n0 + n) * g.ldb + kc * 4) : f4zero();
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int b = b0 + u * 5;
+          const int n = (b / kqb) * 8 + nlo, kc = (b % kqb) * 4 + klo;
+          if (b < nblk8 && kc < kq) {
+            uint4 h, l;
+            h.x = tf32_hi(v[u].x); h.y = tf32_hi(v[u].y); h.z = tf32_hi(v[u].z); h.w = tf32_hi(v[u].w);
+            l.x = tf32_lo(v[u].x, h.x); l.y = tf32_lo(v[u].y, h.y); l.z = tf32_lo(v[u].z, h.z); l.w = tf32_lo(v[u].w, h.w);
+            const size_t off = (size_t)(n >> 3) * SBO + (n & 7) * 16 + (size_t)kc * LBO;
+            *reinterpret_cast<uint4*>(sBhi + off) = h;
+            *reinterpret_cast<uint4*>(sBlo + off) = l;
+          }
+        }
+      }
+    }
+    fence_async_smem();
+    asm volatile("bar.sync 3, 160;" ::: "memory");
+    if (warp == 4) {
+      // ================= MMA issuer (one thread) =================
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(128, BN);
+        const uint32_t bhi0 = smem_u32(sBhi), blo0 = smem_u32(sBlo);
+        uint32_t stage = 0, ph = 0, ds = 0, dph = 0;
+        bool stop = false;
+        while (!stop) {
+          uint32_t t_d = 0;
+          for (int ch = 0; ch < nchunks; ++ch) {
+            const int k0 = ch * KC;
+            const int kw = min(KC, K - k0);
+            mbar_wait(&bars.a_full[stage], ph);
+            fence_after();
+            const int mt = bars.a_meta[stage];
+            if (mt < 0) { stop = true; break; }
+            if (ch == 0) {
+              mbar_wait(&bars.d_empty[ds], dph ^ 1);
+              fence_after();
+              bars.d_meta[ds] = mt;
+              __threadfence_block();
+              t_d = tmem + D_COL + ds * 128;
+            }
+            const uint32_t t_hi = tmem + A_COL + stage * 128;
+            for (int s = 0; s < kw / 8; ++s) {
+              const uint32_t koff = (uint32_t)((k0 >> 3) + s) * 2 * LBO;
+              const uint64_t bhi = make_desc(bhi0 + koff, LBO, SBO);
+              const uint64_t blo = make_desc(blo0 + koff, LBO, SBO);
+              mma_ts(t_d, t_hi + s * 8, bhi, idesc, (ch | s) ? 1u : 0u);
+              mma_ts(t_d, t_hi + KC + s * 8, bhi, idesc, 1u);
+              mma_ts(t_d, t_hi + s * 8, blo, idesc, 1u);
+            }
+            mma_commit(&bars.a_empty[stage]);
+            stage ^= 1;
+            if (stage == 0) ph ^= 1;
+          }
+          if (stop) break;
+          mma_commit(&bars.d_full[ds]);
+          ds ^= 1;
+          if (ds == 0) dph ^= 1;
+        }
+        mbar_wait(&bars.d_empty[ds], dph ^ 1);             // stop sentinel for the epilogue warps
+        bars.d_meta[ds] = -1;
+        __threadfence_block();
+        mbar_arrive(&bars.d_full[ds]);
+      }
+      __syncwarp();
+    } else {
+      // ================= epilogue: accumulator stage -> registers -> (+bias, relu) -> global =================
+      const int q4 = warp & 3;
+      const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+      const int et = (warp - 5) * 32 + lane;
+      const int trow = q4 * 32 + lane;
+      const int c8 = et & 7, rsub = et >> 3;
+      uint32_t ds = 0, dph = 0;
+      float4 bv[4];
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const int col = n0 + sl * 32 + c8 * 4;
+        bv[sl] = (g.bias && sl * 32 + c8 * 4 < BN && col < g.Nc) ? ldg4(g.bias + col) : f4zero();
+      }
+      while (true) {
+        mbar_wait(&bars.d_full[ds], dph);
+        fence_after();
+        const int mt = bars.d_meta[ds];
+        if (mt < 0) break;
+        const int row0 = mt * 128;
+        const uint32_t t_d = tmem + lane_off + D_COL + ds * 128;
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int c0 = sl * 32;
+          if (c0 >= BN) break;
+          uint32_t r0[16], r1[16];
+          tmem_ld16(t_d + c0, r0);
+          tmem_ld16(t_d + c0 + 16, r1);
+          tmem_wait_ld();
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<uint4*>(stD + trow * 128 + (((q ^ trow) & 7) << 4)) =
+                make_uint4(r0[q * 4], r0[q * 4 + 1], r0[q * 4 + 2], r0[q * 4 + 3]);
+            *reinterpret_cast<uint4*>(stD + trow * 128 + ((((q + 4) ^ trow) & 7) << 4)) =
+                make_uint4(r1[q * 4], r1[q * 4 + 1], r1[q * 4 + 2], r1[q * 4 + 3]);
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const int col = n0 + c0 + c8 * 4;
+          if (c0 + c8 * 4 < BN && col < g.Nc) {
+            float* cbase = g.C + (size_t)(col / g.c_cb) * g.c_cbs + (col % g.c_cb);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 16 + rsub;
+              if (row0 + r < g.M) {
+                float4 o = *reinterpret_cast<const float4*>(stD + r * 128 + (((c8 ^ r) & 7) << 4));
+                o = f4add(o, bv[sl]);
+                if (g.relu) o = f4max(o, f4zero());
+                st4(cbase + (size_t)(row0 + r) * g.ldc, o);
+              }
+            }
+          }
+        }
+        fence_before();
+        mbar_arrive(&bars.d_empty[ds]);
+        ds ^= 1;
+        if (ds == 0) dph ^= 1;
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  CTA_T(1);
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static bool tma_enabled() {
   static int on = -1;
@@ -930,6 +1236,38 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
   const size_t smem = (size_t)BN * K * 4 * 2 + 32 * 1024 + 16 * 1024;   // B hi/lo + A staging + D staging
   if (smem > 227 * 1024) return PERT_ERR_UNSUPPORTED;
   NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu};
+  const int mtiles_all = (int)((M + 127) / 128);
+  if (tma_enabled() && nblk <= 8 && encode_tiled_fn()) {
+    // TMA-tiled kernel: A as a 2-D tensor [nblocks * row_blk, a_cb] with pitch lda (see k_gemm_nt_tma)
+    const int nblocks = (K + a_cb - 1) / a_cb;
+    const bool blocked = nblocks > 1;
+    const bool ok = (!blocked || (a_cbs % lda == 0 && a_cb % KC == 0)) && (size_t)lda * 4 % 16 == 0;
+    const size_t bbytes = ((size_t)BN * K * 8 + 1023) & ~(size_t)1023;
+    int NS = (int)((226 * 1024 - 1024 - (long long)bbytes - 16 * 1024) / (32 * 1024));
+    if (NS > RING_MAX) NS = RING_MAX;
+    if (ok && NS >= 2) {
+      const long long row_blk = blocked ? a_cbs / lda : 0;
+      CUtensorMap tm;
+      const cuuint64_t gdim[2] = {(cuuint64_t)(blocked ? a_cb : K),
+                                  (cuuint64_t)(blocked ? row_blk * (nblocks - 1) + M : M)};
+      const cuuint64_t gstr[1] = {(cuuint64_t)lda * 4};
+      const cuuint32_t box[2] = {32, 128};
+      const cuuint32_t estr[2] = {1, 1};
+      CUresult cr = encode_tiled_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)A, gdim, gstr, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr == CUDA_SUCCESS) {
+        const size_t smem2 = 1024 + bbytes + (size_t)NS * 32 * 1024 + 16 * 1024;
+        cudaError_t e2 = cudaFuncSetAttribute(k_gemm_nt_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) return (int)e2;
+        int gx2 = PERT_NUM_SMS / nblk;
+        if (gx2 < 1) gx2 = 1;
+        if (gx2 > mtiles_all) gx2 = mtiles_all;
+        k_gemm_nt_tma<<<dim3(gx2, nblk), TMA_THREADS, smem2, st>>>(tm, g, NS, (int)row_blk);
+        return PERT_OK;
+      }
+    }
+  }
   cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int mtiles = (int)((M + 127) / 128);
