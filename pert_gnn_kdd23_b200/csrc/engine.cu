@@ -175,24 +175,128 @@ __global__ void k_unpack(float* __restrict__ grads, const float* __restrict__ pa
   }
 }
 
-// z[b, 0:H] = pool[b]; z[b, H:2H] = entry_table[entry_id[b]]
-__global__ void k_head_concat(const float* __restrict__ pool, const float* __restrict__ table, int n_rows,
-                              const int64_t* __restrict__ ids, float* __restrict__ z, int B, int H, int* status) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * 2 * H) return;
-  int b = i / (2 * H), c = i - b * 2 * H;
-  float v;
-  if (c < H) v = pool[(size_t)b * H + c];
-  else {
-    int64_t r = ids[b];
-    if (r < 0 || r >= n_rows) {
-      if (status) atomicExch(status, PERT_ERR_RANGE);
-      r = 0;
-    }
-    v = table[(size_t)r * H + (c - H)];
+// ------------------------------------------------------------------ fused global head (reference model.py: global_linear1 -> ReLU -> global_linear2)
+// One warp per graph, HEAD_G graphs per CTA.  z = [pool | entry_emb[entry_id]], h1 = relu(W1 z + b1), out = W2 h1 + b2.
+constexpr int HEAD_G = 8;
+__global__ void __launch_bounds__(HEAD_G * 32) k_head_fwd(const float* __restrict__ pool, const float* __restrict__ table,
+                                                          int n_rows, const int64_t* __restrict__ ids,
+                                                          const float* __restrict__ W1, const float* __restrict__ b1,
+                                                          const float* __restrict__ W2, const float* __restrict__ b2,
+                                                          float* __restrict__ z, float* __restrict__ h1,
+                                                          float* __restrict__ out, int B, int H, int* status) {
+  extern __shared__ float hs[];                       // [HEAD_G][2H]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * HEAD_G + w;
+  if (b >= B) return;                                 // warp-uniform; no block-wide sync below
+  float* zs = hs + (size_t)w * 2 * H;
+  int64_t r = ids[b];
+  if (r < 0 || r >= n_rows) {
+    if (status && lane == 0) atomicExch(status, PERT_ERR_RANGE);
+    r = 0;
   }
-  z[i] = v;
+  for (int c = lane; c < 2 * H; c += 32) {
+    const float v = c < H ? pool[(size_t)b * H + c] : __ldg(table + (size_t)r * H + (c - H));
+    zs[c] = v;
+    z[(size_t)b * 2 * H + c] = v;
+  }
+  __syncwarp();
+  float o = 0.f;
+  for (int n0 = 0; n0 < H; n0 += 4) {                 // 4 output features per pass: independent row loads in flight
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = n0 + u;
+      if (n < H)
+        for (int k = lane * 4; k < 2 * H; k += 128) {
+          const float4 wv = ldg4(W1 + (size_t)n * 2 * H + k);
+          acc[u] = fmaf(wv.x, zs[k], fmaf(wv.y, zs[k + 1], fmaf(wv.z, zs[k + 2], fmaf(wv.w, zs[k + 3], acc[u]))));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
+      const int n = n0 + u;
+      if (n < H) {
+        const float hv = fmaxf(acc[u] + __ldg(b1 + n), 0.f);
+        if (lane == 0) h1[(size_t)b * H + n] = hv;
+        o = fmaf(hv, __ldg(W2 + n), o);
+      }
+    }
+  }
+  if (lane == 0) out[b] = o + __ldg(b2);
 }
+
+// Backward of the head for HEAD_G graphs per CTA: dh1 = dg W2 (h1 > 0); dz = dh1 W1 -> dpool | entry-embedding rows
+// (atomic scatter); dW2 += dg h1; db2 += dg; dW1 += dh1^T z; db1 += dh1 (block-level sums, then one atomic per value).
+__global__ void __launch_bounds__(HEAD_G * 32) k_head_bwd(const float* __restrict__ dg, const float* __restrict__ z,
+                                                          const float* __restrict__ h1, const float* __restrict__ W1,
+                                                          const float* __restrict__ W2, const int64_t* __restrict__ ids,
+                                                          int n_rows, float* __restrict__ dpool, float* __restrict__ g_entry,
+                                                          float* __restrict__ gW1, float* __restrict__ gb1,
+                                                          float* __restrict__ gW2, float* __restrict__ gb2, int B, int H) {
+  extern __shared__ float hs[];                       // z [HEAD_G][2H] | dh [HEAD_G][H]
+  float* zs_all = hs;
+  float* dh_all = hs + (size_t)HEAD_G * 2 * H;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * HEAD_G + w;
+  const bool act = b < B;
+  float* zs = zs_all + (size_t)w * 2 * H;
+  float* dh = dh_all + (size_t)w * H;
+  const float d = act ? dg[b] : 0.f;
+  for (int c = lane; c < 2 * H; c += 32) zs[c] = act ? z[(size_t)b * 2 * H + c] : 0.f;
+  for (int n = lane; n < H; n += 32) {
+    const float hv = act ? h1[(size_t)b * H + n] : 0.f;
+    dh[n] = hv > 0.f ? d * __ldg(W2 + n) : 0.f;
+  }
+  __syncwarp();
+  if (act) {
+    int64_t r = ids[b];
+    if (r < 0 || r >= n_rows) r = 0;                  // (the forward pass already raised the status flag)
+    for (int c0 = lane * 4; c0 < 2 * H; c0 += 128) {
+      float4 acc = f4zero();
+      for (int n = 0; n < H; ++n) {
+        const float dn = dh[n];
+        if (dn != 0.f) acc = f4fma(dn, ldg4(W1 + (size_t)n * 2 * H + c0), acc);
+      }
+      if (c0 < H) {
+        if (dpool) st4(dpool + (size_t)b * H + c0, acc);
+      } else {
+        float* e = g_entry + (size_t)r * H + (c0 - H);
+        atomicAdd(e + 0, acc.x); atomicAdd(e + 1, acc.y); atomicAdd(e + 2, acc.z); atomicAdd(e + 3, acc.w);
+      }
+    }
+  }
+  __syncthreads();
+  // weight gradients of the block's graphs
+  for (int x = threadIdx.x; x < H * 2 * H; x += blockDim.x) {
+    const int n = x / (2 * H), c = x - n * 2 * H;
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < HEAD_G; ++g) t = fmaf(dh_all[g * H + n], zs_all[g * 2 * H + c], t);
+    if (t != 0.f) atomicAdd(gW1 + x, t);
+  }
+  for (int n = threadIdx.x; n < H; n += blockDim.x) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < HEAD_G; ++g) {
+      t1 += dh_all[g * H + n];
+      const int bb = blockIdx.x * HEAD_G + g;
+      if (bb < B) t2 = fmaf(dg[bb], h1[(size_t)bb * H + n], t2);
+    }
+    if (t1 != 0.f) atomicAdd(gb1 + n, t1);
+    if (t2 != 0.f) atomicAdd(gW2 + n, t2);
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int g = 0; g < HEAD_G; ++g) {
+      const int bb = blockIdx.x * HEAD_G + g;
+      if (bb < B) t += dg[bb];
+    }
+    atomicAdd(gb2, t);
+  }
+}
+
 
 inline long long al64(long long n) { return (n + 63) / 64 * 64; }
 
@@ -436,16 +540,9 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
   TRY(pert_pool_fwd(w.out[L - 1], H, probs, pnn, batch, params + d->off_local_w, params + d->off_local_b, local_pred,
                     w.pool, N, B, H, status, st));
   if (B > 0) {
-    k_head_concat<<<pert_cdiv(B * 2 * H, 256), 256, 0, st>>>(w.pool, params + d->off_entry, d->n_entry, entry_id, w.z,
-                                                            (int)B, H, status);
-    SmallGemmBatch g1;
-    g1.count = 1;
-    g1.p[0] = sg(w.z, 2 * H, 1, params + d->off_g1_w, 1, 2 * H, params + d->off_g1_b, w.h1, H, (int)B, H, 2 * H, 1);
-    launch_small(g1, st);
-    SmallGemmBatch g2;
-    g2.count = 1;
-    g2.p[0] = sg(w.h1, H, 1, params + d->off_g2_w, 1, H, params + d->off_g2_b, global_pred, 1, (int)B, 1, H);
-    launch_small(g2, st);
+    k_head_fwd<<<pert_cdiv(B, HEAD_G), HEAD_G * 32, (size_t)HEAD_G * 2 * H * sizeof(float), st>>>(
+        w.pool, params + d->off_entry, d->n_entry, entry_id, params + d->off_g1_w, params + d->off_g1_b,
+        params + d->off_g2_w, params + d->off_g2_b, w.z, w.h1, global_pred, (int)B, H, status);
   }
   PERT_LAUNCH_CHECK();
   return PERT_OK;
@@ -470,25 +567,11 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
   cudaError_t e = cudaMemsetAsync(w.gzero_begin, 0, (size_t)(w.gzero_end - w.gzero_begin) * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   // ---- global head backward
-  if (B > 0) {
-    SmallGemmBatch g;
-    g.count = 0;
-    // dh1 = (d_global (x) W2) * (h1 > 0)
-    g.p[g.count++] = sg(d_global, 1, 1, params + d->off_g2_w, H, 1, nullptr, w.dh1, H, (int)B, H, 1, 0, 0, 1, w.h1);
-    // dW2[0,:] += d_global^T h1 ;  db2 += sum d_global
-    g.p[g.count++] = sg(d_global, 0, 1, w.h1, H, 1, nullptr, grads + d->off_g2_w, H, 1, H, (int)B, 0, 1);
-    g.p[g.count++] = sg(d_global, 0, 1, nullptr, 0, 0, nullptr, grads + d->off_g2_b, 1, 1, 1, (int)B, 0, 1);
-    launch_small(g, st);
-    g.count = 0;
-    // dpool = dh1 . W1[:, :H] ; dzent = dh1 . W1[:, H:]      (B(k,n) = W1[k, n (+H)])
-    g.p[g.count++] = sg(w.dh1, H, 1, params + d->off_g1_w, 2 * H, 1, nullptr, w.dpool, H, (int)B, H, H);
-    g.p[g.count++] = sg(w.dh1, H, 1, params + d->off_g1_w + H, 2 * H, 1, nullptr, w.dzent, H, (int)B, H, H);
-    // dW1 += dh1^T . z  ([H,2H]);  db1 += sum_b dh1
-    g.p[g.count++] = sg(w.dh1, 1, H, w.z, 2 * H, 1, nullptr, grads + d->off_g1_w, 2 * H, H, 2 * H, (int)B, 0, 1);
-    g.p[g.count++] = sg(w.dh1, 1, H, nullptr, 0, 0, nullptr, grads + d->off_g1_b, 1, H, 1, (int)B, 0, 1);
-    launch_small(g, st);
-    TRY(pert_embedding_bwd(w.dzent, H, entry_id, 1, grads + d->off_entry, d->n_entry, B, H, st));
-  }
+  if (B > 0)
+    k_head_bwd<<<pert_cdiv(B, HEAD_G), HEAD_G * 32, (size_t)HEAD_G * 3 * H * sizeof(float), st>>>(
+        d_global, w.z, w.h1, params + d->off_g1_w, params + d->off_g2_w, entry_id, d->n_entry, w.dpool,
+        grads + d->off_entry, grads + d->off_g1_w, grads + d->off_g1_b, grads + d->off_g2_w, grads + d->off_g2_b,
+        (int)B, H);
   // ---- pool / local head backward: g = dL/d out[L-1], written straight into the skip plane of dplanes
   float* dq = w.dplanes;
   float* dk = dq + N * H;
@@ -509,7 +592,9 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
     TRY(pert_gemm_tn(w.dplanes, H, H, N * (long long)H, w.x[l], K, 0, 0, w.dw4[l], K, w.db4[l], N, 4 * H, K, st));
     PROBE_STOP(4, l);
     PROBE_START(5, l);
-    TRY(pert_gemm_nt(w.dplanes, H, H, N * (long long)H, w.w4t[l], 4 * H, nullptr, w.dx, K, 0, 0, N, K, 4 * H, 0, 0, st));
+    // (conv 0: only the embedding columns [0, H) of dX0 are needed -- x and the pad columns carry no parameters)
+    TRY(pert_gemm_nt(w.dplanes, H, H, N * (long long)H, w.w4t[l], 4 * H, nullptr, w.dx, K, 0, 0, N, l == 0 ? H : K, 4 * H,
+                     0, 0, st));
     PROBE_STOP(5, l);
     if (l > 0) {
       // BN(+ReLU) backward of layer l-1: dx (grad wrt x[l]) -> g of conv l-1, into the skip plane

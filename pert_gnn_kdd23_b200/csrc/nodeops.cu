@@ -55,7 +55,8 @@ __global__ void k_copy_cols(const float* __restrict__ x, int F, float* __restric
 }
 
 // ---------------------------------------------------------------- batch norm
-constexpr int BN_ROWS = 256;  // rows per CTA chunk
+constexpr int BN_ROWS = 128;      // rows per CTA chunk (forward statistics)
+constexpr int BN_BWD_ROWS = 64;   // rows per CTA (backward reductions: atomics, so the chunk count is free)
 
 // per-chunk (mean, M2) with a two-pass centred sum (Chan et al. combination in finalize)
 __global__ void __launch_bounds__(256) k_bn_partial(const float* __restrict__ x, int ld, long long N, int H,
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
   const int vpr = H >> 2;
   const int rl_n = blockDim.x / vpr;
   const int cl = threadIdx.x % vpr, rl = threadIdx.x / vpr;
-  const long long r0 = (long long)blockIdx.x * BN_ROWS;
-  const int rows = (int)min((long long)BN_ROWS, N - r0);
+  const long long r0 = (long long)blockIdx.x * BN_BWD_ROWS;
+  const int rows = (int)min((long long)BN_BWD_ROWS, N - r0);
   float4 s1 = f4zero(), s2 = f4zero();
   if (rl < rl_n) {
     const float4 mu = ldg4(mean + cl * 4), rs = ldg4(rstd + cl * 4);
@@ -563,7 +564,7 @@ int pert_bn_bwd(const float* dy, int ld_dy, const float* y, int ld_y, const floa
   int rl_n = threads / vpr;
   size_t smem = (size_t)rl_n * 2 * H * sizeof(float);
   if (smem > 48 * 1024) return PERT_ERR_UNSUPPORTED;
-  k_bn_bwd_reduce<<<pert_cdiv(N, BN_ROWS), threads, smem, st>>>(dy, ld_dy, y, ld_y, x, ld_x, mean, rstd, N, H, relu,
+  k_bn_bwd_reduce<<<pert_cdiv(N, BN_BWD_ROWS), threads, smem, st>>>(dy, ld_dy, y, ld_y, x, ld_x, mean, rstd, N, H, relu,
                                                               sums);
   long long total = N * vpr;
   k_bn_bwd_apply<<<pert_cdiv(total, 256), 256, 0, st>>>(dy, ld_dy, y, ld_y, x, ld_x, mean, rstd, gamma, sums, dx,
