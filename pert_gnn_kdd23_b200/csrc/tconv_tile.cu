@@ -69,9 +69,18 @@ struct TileArgs {
   float* alpha;     // fwd: written; bwd: read
   float* dsp;       // bwd_dst: written; bwd_src: read
   float *dt_if, *dt_rpc;
+  float* rpc_ws;    // [N][2][RPC_FAST] per-target sums over in-edges of (alpha, ds) by rpc type, or null (see bwd_src)
   int N, tile_nodes, edge_cap;
   float inv_sqrt_c;
 };
+
+// Gradient of the (tiny, hot) rpc-type table without per-edge atomics: for an edge t -> i of rpc type b the table row
+// receives de = alpha_t g_i + ds_t q_i, so  dT_rpc[b] = sum_i (A_ib g_i + S_ib q_i)  with the per-target scalars
+// A_ib = sum_{t in in(i), rpc(t)=b} alpha_t and S_ib likewise over ds_t.  The target pass accumulates A, S in the lanes
+// (lane b of the node's group owns type b) and writes 2 x RPC_FAST floats per node; the source pass -- which has the
+// g and q tiles in shared memory anyway -- finishes with a [RPC_FAST x T] x [T x H] product per tile.  With the
+// per-edge shared-memory atomics the source pass took 52 us at the BASELINE cfg2 shape, without them 28 us.
+constexpr int RPC_FAST = 8;   // fast path for n_rpc <= 8 (the reference data has a handful of rpc types)
 
 // dynamic smem layout shared by the three kernels (NA per-edge 4-byte arrays, kernel specific):
 //   [bar 16 B][tile A: T*H][tile B: T*H][rpc table (source pass only): n_rpc*H][row/col ptr slice: T+1][NA x ecap]
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
     const int deg = p1 - p0;
     const int degmax = __reduce_max_sync(0xffffffffu, deg);
     // one edge record: source row offsets + e = T_if[a] + T_rpc[b]
-    auto edge = [&](int p, bool on, int& j, float& al, float4& e) {
+    auto edge = [&](int p, bool on, int& j, float& al, float4& e, int& rid) {
       j = n0;
       al = 0.f;
       int id = 0;
@@ -336,16 +345,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
       e = f4zero();
       if (HAS_E)
         e = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4), ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4));
+      rid = ID_RPC(id);
     };
     // pass 1: dalpha_t = <g_i, v_j + e_t> (staged), dot = sum_t alpha_t dalpha_t
     float dot = 0.f;
     for (int t = 0; t < degmax; ++t) {
       const bool on = t < deg;
       const int p = p0 + t;
-      int j;
+      int j, rid;
       float al;
       float4 e;
-      edge(p, on, j, al, e);
+      edge(p, on, j, al, e, rid);
       float4 vv;
       const unsigned sl = (unsigned)(j - n0);
       if (sl < (unsigned)nt) vv = lds4s(sa.tb + sl * (H * 4) + lane4);
@@ -361,13 +371,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
     __syncwarp();
     // pass 2: ds_t = alpha_t (dalpha_t - dot) / sqrt(C);  dq_i = sum_t ds_t (k_j + e_t)
     float4 dq = f4zero();
+    float sumA = 0.f, sumS = 0.f;          // lane b: sums of alpha / ds over this node's in-edges of rpc type b
     for (int t = 0; t < degmax; ++t) {
       const bool on = t < deg;
       const int p = p0 + t;
-      int j;
+      int j, rid;
       float al;
       float4 e;
-      edge(p, on, j, al, e);
+      edge(p, on, j, al, e, rid);
       float4 kk;
       const unsigned sl = (unsigned)(j - n0);
       if (sl < (unsigned)nt) kk = lds4s(sa.ta + sl * (H * 4) + lane4);
@@ -379,10 +390,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
       }
       const float ds = al * (da - dot) * a.inv_sqrt_c;
       dq = f4fma(ds, f4add(kk, e), dq);
+      if (HAS_E && on && lig == rid) { sumA += al; sumS += ds; }
       __syncwarp();                      // all lanes have read a.dsp[p] (overflow path) before lane 0 rewrites it
       if (on && lig == 0) a.dsp[p] = ds;
     }
     if (valid) st4(a.out + (size_t)i * H + lig * 4, dq);
+    if (HAS_E && a.rpc_ws && valid && lig < RPC_FAST) {
+      a.rpc_ws[(size_t)i * 2 * RPC_FAST + lig] = sumA;
+      a.rpc_ws[(size_t)i * 2 * RPC_FAST + RPC_FAST + lig] = sumS;
+    }
   }
 }
 
@@ -457,17 +473,40 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
       if (HAS_E && on) {
         const float4 de = f4fma(ds, qi, f4scale(al, gi));
         red4(a.dt_if + (size_t)ID_IF(id) * H + lig * 4, de);
-        float* prp = s_drpc + ID_RPC(id) * H + lig * 4;
-        atomicAdd(prp + 0, de.x);
-        atomicAdd(prp + 1, de.y);
-        atomicAdd(prp + 2, de.z);
-        atomicAdd(prp + 3, de.w);
+        if (!a.rpc_ws) {                 // general path (n_rpc > RPC_FAST): privatised table, per-edge atomics
+          float* prp = s_drpc + ID_RPC(id) * H + lig * 4;
+          atomicAdd(prp + 0, de.x);
+          atomicAdd(prp + 1, de.y);
+          atomicAdd(prp + 2, de.z);
+          atomicAdd(prp + 3, de.w);
+        }
       }
     }
     if (valid) {
       st4(a.dk + (size_t)jn * H + lig * 4, dk);
       st4(a.dv + (size_t)jn * H + lig * 4, dv);
     }
+  }
+  if (HAS_E && a.rpc_ws) {
+    // dT_rpc tile contribution: thread = (column, node slice); the per-target scalars are warp-uniform loads
+    constexpr int NSL = TILE_THREADS / H;
+    const int col = tid % H, slc = tid / H;
+    float acc[RPC_FAST];
+#pragma unroll
+    for (int b = 0; b < RPC_FAST; ++b) acc[b] = 0.f;
+#pragma unroll 2
+    for (int loc = slc; loc < nt; loc += NSL) {
+      const float4* wp = reinterpret_cast<const float4*>(a.rpc_ws + (size_t)(n0 + loc) * 2 * RPC_FAST);
+      const float4 A0 = __ldg(wp), A1 = __ldg(wp + 1), S0 = __ldg(wp + 2), S1 = __ldg(wp + 3);
+      const float gv = S.ta[(size_t)loc * H + col], qv = S.tb[(size_t)loc * H + col];
+      acc[0] = fmaf(A0.x, gv, fmaf(S0.x, qv, acc[0])); acc[1] = fmaf(A0.y, gv, fmaf(S0.y, qv, acc[1]));
+      acc[2] = fmaf(A0.z, gv, fmaf(S0.z, qv, acc[2])); acc[3] = fmaf(A0.w, gv, fmaf(S0.w, qv, acc[3]));
+      acc[4] = fmaf(A1.x, gv, fmaf(S1.x, qv, acc[4])); acc[5] = fmaf(A1.y, gv, fmaf(S1.y, qv, acc[5]));
+      acc[6] = fmaf(A1.z, gv, fmaf(S1.z, qv, acc[6])); acc[7] = fmaf(A1.w, gv, fmaf(S1.w, qv, acc[7]));
+    }
+#pragma unroll
+    for (int b = 0; b < RPC_FAST; ++b)
+      if (b < a.n_rpc && acc[b] != 0.f) atomicAdd(s_drpc + b * H + col, acc[b]);
   }
   if (HAS_E) {
     __syncthreads();
@@ -536,11 +575,33 @@ int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool h
   ad.tile_nodes = gd.T; ad.edge_cap = gd.ecap;
   as.tile_nodes = gs.T; as.edge_cap = gs.ecap;
   int rc;
+  float* ws = nullptr;   // stream-ordered scratch for the per-target rpc sums (see RPC_FAST)
+  if (has_e && a0.n_rpc <= RPC_FAST && LPR >= RPC_FAST && TILE_THREADS % H == 0) {
+    // keep freed scratch cached in the device's default pool (the default release threshold of 0 hands it back to the
+    // driver at every synchronisation, turning the next cudaMallocAsync into a real allocation)
+    static bool pool_ready[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+      pool_ready[dev] = true;
+    }
+    if (cudaMallocAsync((void**)&ws, (size_t)N * 2 * RPC_FAST * sizeof(float), st) != cudaSuccess) {
+      (void)cudaGetLastError();
+      ws = nullptr;
+    }
+  }
+  ad.rpc_ws = as.rpc_ws = ws;
   if (has_e) {
     if ((rc = set_smem(k_tile_bwd_dst<LPR, true>, gd.bytes))) return rc;
     if ((rc = set_smem(k_tile_bwd_src<LPR, true>, gs.bytes))) return rc;
     k_tile_bwd_dst<LPR, true><<<pert_cdiv(N, gd.T), TILE_THREADS, gd.bytes, st>>>(ad);
     k_tile_bwd_src<LPR, true><<<pert_cdiv(N, gs.T), TILE_THREADS, gs.bytes, st>>>(as);
+    if (ws) cudaFreeAsync(ws, st);
   } else {
     if ((rc = set_smem(k_tile_bwd_dst<LPR, false>, gd.bytes))) return rc;
     if ((rc = set_smem(k_tile_bwd_src<LPR, false>, gs.bytes))) return rc;
