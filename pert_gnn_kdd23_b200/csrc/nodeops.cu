@@ -58,9 +58,12 @@ __global__ void k_copy_cols(const float* __restrict__ x, int F, float* __restric
 constexpr int BN_ROWS = 128;      // rows per CTA chunk (forward statistics)
 constexpr int BN_BWD_ROWS = 64;   // rows per CTA (backward reductions: atomics, so the chunk count is free)
 
-// per-chunk (mean, M2) with a two-pass centred sum (Chan et al. combination in finalize)
+// per-chunk (mean, M2) with a two-pass centred sum in fp32; the chunks are combined in double precision:
+// acc[c] += n_b mean_b,  acc[H + c] += M2_b + n_b mean_b^2  (fp64 atomics; sum and sum of squares of fp32 data are
+// exact enough in fp64 that  M2 = S2 - S1^2 / N  has no cancellation problem), so no finalize kernel is needed --
+// k_bn_apply derives mean / rstd from acc in its prologue.
 __global__ void __launch_bounds__(256) k_bn_partial(const float* __restrict__ x, int ld, long long N, int H,
-                                                     float* __restrict__ part /*[chunks][2][H]*/) {
+                                                     double* __restrict__ acc /*[2][H], zeroed*/) {
   extern __shared__ float sm[];  // [rl][H] scratch, then mean[H]
   const int vpr = H >> 2;              // float4 lanes per row
   const int rl_n = blockDim.x / vpr;   // row lanes
@@ -112,50 +115,10 @@ __global__ void __launch_bounds__(256) k_bn_partial(const float* __restrict__ x,
   if (threadIdx.x < H) {
     float t = 0.f;
     for (int i = 0; i < rl_n; ++i) t += s_red[i * H + threadIdx.x];
-    part[((size_t)blockIdx.x * 2 + 0) * H + threadIdx.x] = s_mean[threadIdx.x];
-    part[((size_t)blockIdx.x * 2 + 1) * H + threadIdx.x] = t;
+    const double m = (double)s_mean[threadIdx.x], n = (double)rows;
+    atomicAdd(acc + threadIdx.x, n * m);
+    atomicAdd(acc + H + threadIdx.x, (double)t + n * m * m);
   }
-}
-
-__global__ void k_bn_finalize(const float* __restrict__ part, int chunks, long long N, int H, float eps,
-                              float momentum, float* __restrict__ mean, float* __restrict__ rstd,
-                              float* running_mean, float* running_var, long long* num_batches_tracked) {
-  // one warp per column: lanes stride over the chunk partials, then a shuffle tree of Chan merges
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= H) return;
-  float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
-  for (int k = lane; k < chunks; k += 32) {
-    float n_b = (float)min((long long)BN_ROWS, N - (long long)k * BN_ROWS);
-    float mean_b = part[((size_t)k * 2 + 0) * H + c], m2_b = part[((size_t)k * 2 + 1) * H + c];
-    float n = n_a + n_b, delta = mean_b - mean_a;
-    mean_a += delta * (n_b / n);
-    m2_a += m2_b + delta * delta * (n_a * n_b / n);
-    n_a = n;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float n_b = __shfl_xor_sync(0xffffffffu, n_a, o);
-    float mean_b = __shfl_xor_sync(0xffffffffu, mean_a, o);
-    float m2_b = __shfl_xor_sync(0xffffffffu, m2_a, o);
-    float n = n_a + n_b;
-    if (n > 0.f) {
-      float delta = mean_b - mean_a;
-      mean_a += delta * (n_b / n);
-      m2_a += m2_b + delta * delta * (n_a * n_b / n);
-    }
-    n_a = n;
-  }
-  if (lane != 0) return;
-  float var = m2_a / (float)N;  // biased, used to normalise
-  mean[c] = mean_a;
-  rstd[c] = 1.0f / sqrtf(var + eps);  // exact 1/sqrt (rsqrtf is ~2 ulp off ATen)
-  if (running_mean) {
-    float unbiased = (N > 1) ? m2_a / (float)(N - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean_a;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
-  }
-  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
 }
 
 // eval mode: mean = running_mean, rstd = 1/sqrt(running_var + eps)
@@ -167,24 +130,71 @@ __global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __res
   rstd[c] = 1.0f / sqrtf(rv[c] + eps);
 }
 
-__global__ void k_bn_apply(const float* __restrict__ x, int ld_x, const float* __restrict__ mean,
-                           const float* __restrict__ rstd, const float* __restrict__ gamma,
-                           const float* __restrict__ beta, float* __restrict__ y, int ld_y, long long N, int H,
-                           int relu) {
+// y = (relu)((x - mean) rstd gamma + beta).  acc != null (training): mean / rstd come from the fp64 sums of
+// k_bn_partial (every CTA derives them in its prologue; CTA 0 also stores them for the backward pass and updates the
+// running statistics); acc == null (eval): mean / rstd arrays are read.
+__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, int ld_x, float* __restrict__ mean,
+                                                   float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float* __restrict__ y, int ld_y,
+                                                   long long N, int H, int relu, const double* __restrict__ acc,
+                                                   float eps, float momentum, float* running_mean,
+                                                   float* running_var, long long* num_batches_tracked) {
+  extern __shared__ float s_par[];   // mean | rstd | gamma | beta
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float mu, rs;
+    if (acc) {
+      const double n = (double)N;
+      const double m = acc[c] / n;
+      double m2 = acc[H + c] - n * m * m;
+      if (m2 < 0.0) m2 = 0.0;
+      const double var = m2 / n;       // biased, used to normalise
+      mu = (float)m;
+      rs = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0) {
+        mean[c] = mu;
+        rstd[c] = rs;
+        if (running_mean) {
+          const double unbiased = (N > 1) ? m2 / (n - 1.0) : var;
+          running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+          running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+        if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+      }
+    } else {
+      mu = mean[c];
+      rs = rstd[c];
+    }
+    s_par[c] = mu;
+    s_par[H + c] = rs;
+    s_par[2 * H + c] = gamma[c];
+    s_par[3 * H + c] = beta[c];
+  }
+  __syncthreads();
   const int vpr = H >> 2;
-  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= N * vpr) return;
-  long long n = id / vpr;
-  int c = (int)(id % vpr) * 4;
-  float4 v = ldg4(x + (size_t)n * ld_x + c);
-  float4 mu = ldg4(mean + c), rs = ldg4(rstd + c), ga = ldg4(gamma + c), be = ldg4(beta + c);
-  float4 o;
-  o.x = fmaf((v.x - mu.x) * rs.x, ga.x, be.x);
-  o.y = fmaf((v.y - mu.y) * rs.y, ga.y, be.y);
-  o.z = fmaf((v.z - mu.z) * rs.z, ga.z, be.z);
-  o.w = fmaf((v.w - mu.w) * rs.w, ga.w, be.w);
-  if (relu) o = f4max(o, f4zero());
-  st4(y + (size_t)n * ld_y + c, o);
+  const long long total = N * vpr;
+  for (long long id0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; id0 < total;
+       id0 += 4LL * gridDim.x * blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {       // 4 independent row loads in flight
+      const long long id = id0 + (long long)u * gridDim.x * blockDim.x;
+      v[u] = id < total ? ldg4(x + (size_t)(id / vpr) * ld_x + (int)(id % vpr) * 4) : f4zero();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long id = id0 + (long long)u * gridDim.x * blockDim.x;
+      if (id >= total) break;
+      const int c = (int)(id % vpr) * 4;
+      const float4 mu = ld4(s_par + c), rs = ld4(s_par + H + c), ga = ld4(s_par + 2 * H + c), be = ld4(s_par + 3 * H + c);
+      float4 o;
+      o.x = fmaf((v[u].x - mu.x) * rs.x, ga.x, be.x);
+      o.y = fmaf((v[u].y - mu.y) * rs.y, ga.y, be.y);
+      o.z = fmaf((v[u].z - mu.z) * rs.z, ga.z, be.z);
+      o.w = fmaf((v[u].w - mu.w) * rs.w, ga.w, be.w);
+      if (relu) o = f4max(o, f4zero());
+      st4(y + (size_t)(id / vpr) * ld_y + c, o);
+    }
+  }
 }
 
 // sums[0:H] += sum_n dz,  sums[H:2H] += sum_n dz*xhat   with dz = dy * (y > 0 if relu)
@@ -505,8 +515,8 @@ int pert_copy_cols(const float* x, int F, float* out, int ld_out, int col0, long
 }
 
 long long pert_bn_workspace_bytes(long long N, int H) {
-  long long chunks = (N + BN_ROWS - 1) / BN_ROWS;
-  return (chunks * 2 * H + 2 * H) * 4 + 64;
+  (void)N;
+  return 2LL * H * 8 + 64;   // fp64 (sum, sum of squares) per column
 }
 
 // training != 0: batch statistics (and running-stat update when running_* given); else running statistics.
@@ -520,6 +530,7 @@ int pert_bn_fwd(const float* x, int ld_x, const float* gamma, const float* beta,
   if (!al16(x) || !al16(gamma) || !al16(beta) || !al16(mean) || !al16(rstd) || !al16(y)) return PERT_ERR_BADARG;
   if (N == 0) return PERT_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  double* acc = nullptr;
   if (training) {
     if (!workspace || workspace_bytes < pert_bn_workspace_bytes(N, H)) return PERT_ERR_BADARG;
     int chunks = pert_cdiv(N, BN_ROWS);
@@ -530,16 +541,22 @@ int pert_bn_fwd(const float* x, int ld_x, const float* gamma, const float* beta,
     if (rl_n < 1) return PERT_ERR_UNSUPPORTED;
     size_t smem = ((size_t)rl_n * H + H) * sizeof(float);
     if (smem > 48 * 1024) return PERT_ERR_UNSUPPORTED;
-    float* part = (float*)workspace;
-    k_bn_partial<<<chunks, threads, smem, st>>>(x, ld_x, N, H, part);
-    k_bn_finalize<<<pert_cdiv((long long)H * 32, 128), 128, 0, st>>>(part, chunks, N, H, eps, momentum, mean, rstd, running_mean,
-                                                    running_var, num_batches_tracked);
+    if ((uintptr_t)workspace & 7) return PERT_ERR_BADARG;
+    acc = (double*)workspace;
+    cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)2 * H * sizeof(double), st);
+    if (e != cudaSuccess) return (int)e;
+    k_bn_partial<<<chunks, threads, smem, st>>>(x, ld_x, N, H, acc);
   } else {
     if (!running_mean || !running_var) return PERT_ERR_BADARG;
     k_bn_eval_stats<<<pert_cdiv(H, 128), 128, 0, st>>>(running_mean, running_var, eps, H, mean, rstd);
   }
   long long total = N * (H / 4);
-  k_bn_apply<<<pert_cdiv(total, 256), 256, 0, st>>>(x, ld_x, mean, rstd, gamma, beta, y, ld_y, N, H, relu);
+  long long blocks = pert_cdiv(total, 256 * 4);
+  if (blocks > 8LL * PERT_NUM_SMS) blocks = 8LL * PERT_NUM_SMS;
+  k_bn_apply<<<(int)blocks, 256, (size_t)4 * H * sizeof(float), st>>>(x, ld_x, mean, rstd, gamma, beta, y, ld_y, N, H, relu, acc, eps,
+                                                              momentum, training ? running_mean : nullptr,
+                                                              training ? running_var : nullptr,
+                                                              training ? num_batches_tracked : nullptr);
   PERT_LAUNCH_CHECK();
   return PERT_OK;
 }

@@ -150,13 +150,26 @@ class Engine:
             self.ws_key = key
         return self.ws
 
+    def _pack_launches(self):
+        # mirrors engine.cu: conv 0 contributes 24 segments, the others 16; a launch holds at most 96
+        n, count = 0, 0
+        for l in range(self.n_convs):
+            count += 24 if l == 0 else 16
+            if count + 24 > 96 or l == self.n_convs - 1:
+                n, count = n + 1, 0
+        return n
+
     def launches_forward(self):
+        """Kernels pert_model_forward launches (memsets not counted): pack, edge tables (6 layers per launch),
+        embeddings + copy, per conv GEMM + attention, per BatchNorm partial + apply, pool, head."""
         L = self.n_convs
-        return L + (L + 5) // 6 + self.desc.n_cat + 1 + L * 2 + (L - 1) * 3 + 1 + 3
+        return self._pack_launches() + (L + 5) // 6 + self.desc.n_cat + 1 + 2 * L + 2 * (L - 1) + 1 + 1
 
     def launches_backward(self):
+        """head, pool, per conv (target pass, source pass, weight GEMM, data GEMM), per BatchNorm reduce + apply,
+        embedding scatters, edge-table gradients (3 layers per launch), unpack."""
         L = self.n_convs
-        return 2 + 1 + 1 + L * 4 + (L - 1) * 2 + self.desc.n_cat + L + L
+        return 1 + 1 + 4 * L + 2 * (L - 1) + self.desc.n_cat + (L + 2) // 3 + self._pack_launches()
 
     def forward(self, x, cat_X, entry_id, probs, pnn, batch, index: GraphIndex, training, probe=None):
         """-> (global_pred [B,1], local_pred [N,1]); keeps what backward needs in the workspace."""

@@ -297,7 +297,7 @@ class _BatchNormFn(torch.autograd.Function):
         call("pert_bn_fwd", ptr(x), H, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(nbt),
              float(eps), float(momentum), int(training), int(relu), ptr(stats[0]), ptr(stats[1]), ptr(y), H, N, H,
              ptr(ws), wsb, stream())
-        LAUNCHES["n"] += 3 if training else 2
+        LAUNCHES["n"] += 2
         ctx.cfg = (bool(training), bool(relu))
         ctx.save_for_backward(x, y, stats, gamma)
         return y
