@@ -176,104 +176,137 @@ __global__ void k_unpack(float* __restrict__ grads, const float* __restrict__ pa
 }
 
 // ------------------------------------------------------------------ fused global head (reference model.py: global_linear1 -> ReLU -> global_linear2)
-// One warp per graph, HEAD_G graphs per CTA.  z = [pool | entry_emb[entry_id]], h1 = relu(W1 z + b1), out = W2 h1 + b2.
+// HEAD_G graphs per CTA, one warp per graph.  z = [pool | entry_emb[entry_id]], h1 = relu(W1 z + b1), out = W2 h1 + b2.
+// W1 is staged in shared memory once per CTA (all loads in flight together): transposed [2H][H] for the forward
+// (lane = output feature, conflict free, no shuffles), row-major [H][2H] for the backward (lane = input column).
 constexpr int HEAD_G = 8;
-__global__ void __launch_bounds__(HEAD_G * 32) k_head_fwd(const float* __restrict__ pool, const float* __restrict__ table,
-                                                          int n_rows, const int64_t* __restrict__ ids,
-                                                          const float* __restrict__ W1, const float* __restrict__ b1,
-                                                          const float* __restrict__ W2, const float* __restrict__ b2,
-                                                          float* __restrict__ z, float* __restrict__ h1,
-                                                          float* __restrict__ out, int B, int H, int* status) {
-  extern __shared__ float hs[];                       // [HEAD_G][2H]
+constexpr int HEAD_T = HEAD_G * 32;
+__global__ void __launch_bounds__(HEAD_T) k_head_fwd(const float* __restrict__ pool, const float* __restrict__ table,
+                                                     int n_rows, const int64_t* __restrict__ ids,
+                                                     const float* __restrict__ W1, const float* __restrict__ b1,
+                                                     const float* __restrict__ W2, const float* __restrict__ b2,
+                                                     float* __restrict__ z, float* __restrict__ h1,
+                                                     float* __restrict__ out, int B, int H, int* status) {
+  extern __shared__ float hs[];                       // W1t [2H][H] | z [HEAD_G][2H]
+  float* w1t = hs;
+  float* zs_all = hs + (size_t)2 * H * H;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * HEAD_G + w;
-  if (b >= B) return;                                 // warp-uniform; no block-wide sync below
-  float* zs = hs + (size_t)w * 2 * H;
-  int64_t r = ids[b];
-  if (r < 0 || r >= n_rows) {
-    if (status && lane == 0) atomicExch(status, PERT_ERR_RANGE);
-    r = 0;
-  }
-  for (int c = lane; c < 2 * H; c += 32) {
-    const float v = c < H ? pool[(size_t)b * H + c] : __ldg(table + (size_t)r * H + (c - H));
-    zs[c] = v;
-    z[(size_t)b * 2 * H + c] = v;
-  }
-  __syncwarp();
-  float o = 0.f;
-  for (int n0 = 0; n0 < H; n0 += 4) {                 // 4 output features per pass: independent row loads in flight
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int K2 = 2 * H, kq = K2 / 4;
+  // lanes along n: the global reads are 16-byte pieces of different rows (32 KB, L2 resident), the transposing
+  // shared-memory stores are conflict free
+  for (int base = 0; base < H * kq; base += 8 * HEAD_T) {
+    float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int n = n0 + u;
-      if (n < H)
-        for (int k = lane * 4; k < 2 * H; k += 128) {
-          const float4 wv = ldg4(W1 + (size_t)n * 2 * H + k);
-          acc[u] = fmaf(wv.x, zs[k], fmaf(wv.y, zs[k + 1], fmaf(wv.z, zs[k + 2], fmaf(wv.w, zs[k + 3], acc[u]))));
-        }
+    for (int u = 0; u < 8; ++u) {
+      const int x = base + u * HEAD_T + threadIdx.x;
+      v[u] = x < H * kq ? ldg4(W1 + (size_t)(x % H) * K2 + (x / H) * 4) : f4zero();
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
-      const int n = n0 + u;
-      if (n < H) {
-        const float hv = fmaxf(acc[u] + __ldg(b1 + n), 0.f);
-        if (lane == 0) h1[(size_t)b * H + n] = hv;
-        o = fmaf(hv, __ldg(W2 + n), o);
+    for (int u = 0; u < 8; ++u) {
+      const int x = base + u * HEAD_T + threadIdx.x;
+      if (x < H * kq) {
+        const int n = x % H, k = (x / H) * 4;
+        w1t[(k + 0) * H + n] = v[u].x; w1t[(k + 1) * H + n] = v[u].y;
+        w1t[(k + 2) * H + n] = v[u].z; w1t[(k + 3) * H + n] = v[u].w;
       }
     }
   }
+  const int b = blockIdx.x * HEAD_G + w;
+  const bool act = b < B;
+  float* zs = zs_all + (size_t)w * K2;
+  if (act) {
+    int64_t r = ids[b];
+    if (r < 0 || r >= n_rows) {
+      if (status && lane == 0) atomicExch(status, PERT_ERR_RANGE);
+      r = 0;
+    }
+    for (int c = lane; c < K2; c += 32) {
+      const float v = c < H ? pool[(size_t)b * H + c] : __ldg(table + (size_t)r * H + (c - H));
+      zs[c] = v;
+      z[(size_t)b * K2 + c] = v;
+    }
+  }
+  __syncthreads();
+  if (!act) return;
+  float o = 0.f;
+  for (int n = lane; n < H; n += 32) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < K2; k += 2) {
+      a0 = fmaf(w1t[k * H + n], zs[k], a0);
+      a1 = fmaf(w1t[(k + 1) * H + n], zs[k + 1], a1);
+    }
+    const float hv = fmaxf(a0 + a1 + __ldg(b1 + n), 0.f);
+    h1[(size_t)b * H + n] = hv;
+    o = fmaf(hv, __ldg(W2 + n), o);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) o += __shfl_xor_sync(0xffffffffu, o, off);
   if (lane == 0) out[b] = o + __ldg(b2);
 }
 
 // Backward of the head for HEAD_G graphs per CTA: dh1 = dg W2 (h1 > 0); dz = dh1 W1 -> dpool | entry-embedding rows
 // (atomic scatter); dW2 += dg h1; db2 += dg; dW1 += dh1^T z; db1 += dh1 (block-level sums, then one atomic per value).
-__global__ void __launch_bounds__(HEAD_G * 32) k_head_bwd(const float* __restrict__ dg, const float* __restrict__ z,
-                                                          const float* __restrict__ h1, const float* __restrict__ W1,
-                                                          const float* __restrict__ W2, const int64_t* __restrict__ ids,
-                                                          int n_rows, float* __restrict__ dpool, float* __restrict__ g_entry,
-                                                          float* __restrict__ gW1, float* __restrict__ gb1,
-                                                          float* __restrict__ gW2, float* __restrict__ gb2, int B, int H) {
-  extern __shared__ float hs[];                       // z [HEAD_G][2H] | dh [HEAD_G][H]
-  float* zs_all = hs;
-  float* dh_all = hs + (size_t)HEAD_G * 2 * H;
+__global__ void __launch_bounds__(HEAD_T) k_head_bwd(const float* __restrict__ dg, const float* __restrict__ z,
+                                                     const float* __restrict__ h1, const float* __restrict__ W1,
+                                                     const float* __restrict__ W2, const int64_t* __restrict__ ids,
+                                                     int n_rows, float* __restrict__ dpool, float* __restrict__ g_entry,
+                                                     float* __restrict__ gW1, float* __restrict__ gb1,
+                                                     float* __restrict__ gW2, float* __restrict__ gb2, int B, int H) {
+  extern __shared__ float hs[];                       // W1 [H][2H] | z [HEAD_G][2H] | dh [HEAD_G][H]
+  const int K2 = 2 * H;
+  float* w1 = hs;
+  float* zs_all = hs + (size_t)H * K2;
+  float* dh_all = zs_all + (size_t)HEAD_G * K2;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int base = 0; base < H * K2 / 4; base += 8 * HEAD_T) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int x = base + u * HEAD_T + threadIdx.x;
+      v[u] = x < H * K2 / 4 ? ldg4(W1 + (size_t)x * 4) : f4zero();
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int x = base + u * HEAD_T + threadIdx.x;
+      if (x < H * K2 / 4) st4(w1 + (size_t)x * 4, v[u]);
+    }
+  }
   const int b = blockIdx.x * HEAD_G + w;
   const bool act = b < B;
-  float* zs = zs_all + (size_t)w * 2 * H;
+  float* zs = zs_all + (size_t)w * K2;
   float* dh = dh_all + (size_t)w * H;
   const float d = act ? dg[b] : 0.f;
-  for (int c = lane; c < 2 * H; c += 32) zs[c] = act ? z[(size_t)b * 2 * H + c] : 0.f;
+  for (int c = lane; c < K2; c += 32) zs[c] = act ? z[(size_t)b * K2 + c] : 0.f;
   for (int n = lane; n < H; n += 32) {
     const float hv = act ? h1[(size_t)b * H + n] : 0.f;
     dh[n] = hv > 0.f ? d * __ldg(W2 + n) : 0.f;
   }
-  __syncwarp();
+  __syncthreads();
   if (act) {
     int64_t r = ids[b];
     if (r < 0 || r >= n_rows) r = 0;                  // (the forward pass already raised the status flag)
-    for (int c0 = lane * 4; c0 < 2 * H; c0 += 128) {
-      float4 acc = f4zero();
-      for (int n = 0; n < H; ++n) {
-        const float dn = dh[n];
-        if (dn != 0.f) acc = f4fma(dn, ldg4(W1 + (size_t)n * 2 * H + c0), acc);
+    for (int c = lane; c < K2; c += 32) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+      for (int n = 0; n < H; n += 2) {
+        a0 = fmaf(dh[n], w1[n * K2 + c], a0);
+        a1 = fmaf(dh[n + 1], w1[(n + 1) * K2 + c], a1);
       }
-      if (c0 < H) {
-        if (dpool) st4(dpool + (size_t)b * H + c0, acc);
+      const float acc = a0 + a1;
+      if (c < H) {
+        if (dpool) dpool[(size_t)b * H + c] = acc;
       } else {
-        float* e = g_entry + (size_t)r * H + (c0 - H);
-        atomicAdd(e + 0, acc.x); atomicAdd(e + 1, acc.y); atomicAdd(e + 2, acc.z); atomicAdd(e + 3, acc.w);
+        atomicAdd(g_entry + (size_t)r * H + (c - H), acc);
       }
     }
   }
-  __syncthreads();
   // weight gradients of the block's graphs
-  for (int x = threadIdx.x; x < H * 2 * H; x += blockDim.x) {
-    const int n = x / (2 * H), c = x - n * 2 * H;
+  for (int x = threadIdx.x; x < H * K2; x += blockDim.x) {
+    const int n = x / K2, c = x - n * K2;
     float t = 0.f;
 #pragma unroll
-    for (int g = 0; g < HEAD_G; ++g) t = fmaf(dh_all[g * H + n], zs_all[g * 2 * H + c], t);
+    for (int g = 0; g < HEAD_G; ++g) t = fmaf(dh_all[g * H + n], zs_all[g * K2 + c], t);
     if (t != 0.f) atomicAdd(gW1 + x, t);
   }
   for (int n = threadIdx.x; n < H; n += blockDim.x) {
@@ -540,7 +573,12 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
   TRY(pert_pool_fwd(w.out[L - 1], H, probs, pnn, batch, params + d->off_local_w, params + d->off_local_b, local_pred,
                     w.pool, N, B, H, status, st));
   if (B > 0) {
-    k_head_fwd<<<pert_cdiv(B, HEAD_G), HEAD_G * 32, (size_t)HEAD_G * 2 * H * sizeof(float), st>>>(
+    const size_t hsm = ((size_t)2 * H * H + (size_t)HEAD_G * 2 * H) * sizeof(float);
+    if (hsm > 48 * 1024) {
+      cudaError_t he = cudaFuncSetAttribute(k_head_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm);
+      if (he != cudaSuccess) return (int)he;
+    }
+    k_head_fwd<<<pert_cdiv(B, HEAD_G), HEAD_T, hsm, st>>>(
         w.pool, params + d->off_entry, d->n_entry, entry_id, params + d->off_g1_w, params + d->off_g1_b,
         params + d->off_g2_w, params + d->off_g2_b, w.z, w.h1, global_pred, (int)B, H, status);
   }
@@ -567,11 +605,17 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
   cudaError_t e = cudaMemsetAsync(w.gzero_begin, 0, (size_t)(w.gzero_end - w.gzero_begin) * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   // ---- global head backward
-  if (B > 0)
-    k_head_bwd<<<pert_cdiv(B, HEAD_G), HEAD_G * 32, (size_t)HEAD_G * 3 * H * sizeof(float), st>>>(
+  if (B > 0) {
+    const size_t hsm = ((size_t)2 * H * H + (size_t)HEAD_G * 3 * H) * sizeof(float);
+    if (hsm > 48 * 1024) {
+      cudaError_t he = cudaFuncSetAttribute(k_head_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm);
+      if (he != cudaSuccess) return (int)he;
+    }
+    k_head_bwd<<<pert_cdiv(B, HEAD_G), HEAD_T, hsm, st>>>(
         d_global, w.z, w.h1, params + d->off_g1_w, params + d->off_g2_w, entry_id, d->n_entry, w.dpool,
         grads + d->off_entry, grads + d->off_g1_w, grads + d->off_g1_b, grads + d->off_g2_w, grads + d->off_g2_b,
         (int)B, H);
+  }
   // ---- pool / local head backward: g = dL/d out[L-1], written straight into the skip plane of dplanes
   float* dq = w.dplanes;
   float* dk = dq + N * H;
