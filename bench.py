@@ -344,9 +344,21 @@ def run_b200(args, rank, world, local_rank):
         l.backward()
         if world > 1:
             # the engine hands autograd ONE flat gradient buffer (every p.grad is a view of it): one all-reduce
-            flat = next(p.grad for p in model2.parameters() if p.grad is not None)._base
-            dist.all_reduce(flat)
-            flat.div_(world)
+            gs = [p.grad for p in model2.parameters() if p.grad is not None]
+            gb = getattr(model2._engine, "last_grad_buffer", None)
+            if gb is not None:
+                lo, hi = gb.data_ptr(), gb.data_ptr() + gb.numel() * gb.element_size()
+            if gb is not None and all(lo <= g.data_ptr() < hi for g in gs):
+                dist.all_reduce(gb)
+                gb.div_(world)
+            else:                              # autograd copied the views: flatten, reduce, scatter back
+                flat = torch.cat([g.reshape(-1) for g in gs])
+                dist.all_reduce(flat)
+                flat.div_(world)
+                o = 0
+                for g in gs:
+                    g.copy_(flat[o:o + g.numel()].view_as(g))
+                    o += g.numel()
         opt2.step()
         return float(l)                       # D2H read of the step's result, like pert_gnn.py:248
 

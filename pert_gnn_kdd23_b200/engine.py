@@ -232,6 +232,7 @@ class _EngineFn(torch.autograd.Function):
                                "(one in-flight forward per model replica)")
         gbuf = torch.zeros_like(eng.fp.flat)
         eng.backward(dg, dl, grads=gbuf)
+        eng.last_grad_buffer = gbuf      # every returned gradient is a view of this buffer (one all-reduce in DP)
         base = eng.fp.flat.data_ptr()
         outs = []
         for p in eng.fp.params:
