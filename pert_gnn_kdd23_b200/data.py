@@ -206,15 +206,21 @@ class DevicePrefetcher:
     def __init__(self, batches, device):
         self.batches = batches
         self.device = torch.device(device)
+        # the ring outlives one pass over ``batches`` (epochs re-use the same device buffers, so a CUDA-graph
+        # replayed step -- train.GraphedTrainStep keys its graphs by buffer address -- keeps hitting)
+        self._side = None
+        self._ring = [None, None, None]    # device slabs reused round-robin: no allocator traffic in the loop
+        self._done = [None, None, None]    # event: the training step that consumed ring[k] has been issued + finished
+        self._k = 0
 
     def __len__(self):
         return len(self.batches)
 
     def __iter__(self):
-        side = torch.cuda.Stream(self.device)
-        ring = [None, None, None]          # device slabs reused round-robin: no allocator traffic in the loop
-        done = [None, None, None]          # event: the training step that consumed ring[k] has been issued + finished
-        state = {"k": 0}
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        side, ring, done = self._side, self._ring, self._done
+        state = {"k": self._k}
 
         def load(b):
             if b.__dict__.get("_slab") is None:
@@ -242,18 +248,21 @@ class DevicePrefetcher:
             nxt = load(next(it))
         except StopIteration:
             return
-        while nxt is not None:
-            cur, ev, k = nxt
-            try:
-                nxt = load(next(it))
-            except StopIteration:
-                nxt = None
-            main = torch.cuda.current_stream(self.device)
-            main.wait_event(ev)
-            yield cur
-            d = torch.cuda.Event()
-            d.record(main)                 # everything the consumer launched on this batch
-            done[k] = d
+        try:
+            while nxt is not None:
+                cur, ev, k = nxt
+                try:
+                    nxt = load(next(it))
+                except StopIteration:
+                    nxt = None
+                main = torch.cuda.current_stream(self.device)
+                main.wait_event(ev)
+                yield cur
+                d = torch.cuda.Event()
+                d.record(main)             # everything the consumer launched on this batch
+                done[k] = d
+        finally:
+            self._k = state["k"]
 
 
 class DataLoader(_TorchDataLoader):

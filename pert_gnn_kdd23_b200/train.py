@@ -106,19 +106,18 @@ def train_step(model, optimizer, data, tau=0.5, dp: DataParallel | None = None):
     return loss
 
 
-def fused_train_step(model, optimizer: FusedAdam, data, tau=0.5, dp: DataParallel | None = None, index=None,
-                     probe=None):
-    """Same step as ``train_step`` but without autograd: engine forward -> pinball loss + its gradient (one
-    kernel) -> engine backward into the flat gradient buffer -> (all-reduce) -> fused Adam.  5 C calls per step.
-    Returns the device loss tensor [1]."""
-    from .index import cached_index
+def _fused_fwd_bwd(model, optimizer: FusedAdam, data, tau, index, probe, use_index_cache=True):
+    """Device work of one step up to the gradients: (index build) -> zero grads -> engine forward -> pinball loss +
+    its gradient -> engine backward into the flat gradient buffer.  Returns (loss [1], index)."""
+    from .index import build_index, cached_index
 
     eng = model.engine(optimizer.fp) if (model._engine is None or model._engine.fp is not optimizer.fp) \
         else model._engine
     x, cat_X, edge_index, edge_attr, pnn, probs, entry_id, batch = model_inputs(data)
     if index is None:
-        index = cached_index(edge_index, x.size(0), edge_attr, model.interface_embeds.num_embeddings,
-                             model.rpctype_embeds.num_embeddings)
+        n_if, n_rpc = model.interface_embeds.num_embeddings, model.rpctype_embeds.num_embeddings
+        index = cached_index(edge_index, x.size(0), edge_attr, n_if, n_rpc) if use_index_cache \
+            else build_index(edge_index, x.size(0), edge_attr, n_if, n_rpc, check=False)
     optimizer.zero_grad()
     with torch.no_grad():
         gpred, _ = eng.forward(x, cat_X, entry_id, probs, pnn, batch, index, model.training, probe=probe)
@@ -129,9 +128,87 @@ def fused_train_step(model, optimizer: FusedAdam, data, tau=0.5, dp: DataParalle
                   _lib.ptr(dy), _lib.stream())
         ops.LAUNCHES["n"] += 1
         eng.backward(dy, None, probe=probe)
+    return loss, index
+
+
+def fused_train_step(model, optimizer: FusedAdam, data, tau=0.5, dp: DataParallel | None = None, index=None,
+                     probe=None):
+    """Same step as ``train_step`` but without autograd: engine forward -> pinball loss + its gradient (one
+    kernel) -> engine backward into the flat gradient buffer -> (all-reduce) -> fused Adam.  5 C calls per step.
+    Returns the device loss tensor [1]."""
+    loss, _ = _fused_fwd_bwd(model, optimizer, data, tau, index, probe)
+    with torch.no_grad():
         scale = dp.all_reduce_grads() if dp is not None else 1.0
         optimizer.step(grad_scale=scale)
     return loss
+
+
+class GraphedTrainStep:
+    """``fused_train_step`` with the device work up to the gradients replayed from a CUDA graph.
+
+    One graph per (input buffers, shapes) key -- e.g. one per slab of ``data.DevicePrefetcher``'s ring, or one per
+    resident batch.  The graph holds: index build, gradient zeroing, engine forward, pinball loss, engine backward
+    (~45 kernel launches become one ``cudaGraphLaunch``: no per-kernel launch gaps on the GPU, ~0.5 ms less host
+    work per step).  The gradient all-reduce and Adam (its step count is a by-value kernel argument) are issued
+    eagerly after the replay.  The first step on a new key runs eagerly (it also does the library's one-time
+    initialisation), the second is captured; a key whose capture fails stays eager.  The reference has no
+    counterpart (its loop body, pert_gnn.py:231-247, launches every operator from Python each step)."""
+
+    def __init__(self, model, optimizer: FusedAdam, tau=0.5, dp: DataParallel | None = None, max_graphs=32):
+        self.model, self.opt, self.tau, self.dp = model, optimizer, tau, dp
+        self.max_graphs = max_graphs
+        self._seen = {}      # key -> "ran-once" | "failed" | entry dict
+        self.capture_error = None
+        self.replays = 0
+
+    @staticmethod
+    def _key(data):
+        return (data.x.data_ptr(), data.edge_index.data_ptr(), tuple(data.x.shape), int(data.edge_index.size(1)),
+                int(data.num_graphs))
+
+    def _finish(self, loss):
+        with torch.no_grad():
+            scale = self.dp.all_reduce_grads() if self.dp is not None else 1.0
+            self.opt.step(grad_scale=scale)
+        return loss
+
+    def __call__(self, data):
+        key = self._key(data)
+        ent = self._seen.get(key, "unseen")
+        if isinstance(ent, dict):
+            pass
+        elif ent == "ran-once" and len(self._seen) <= self.max_graphs:
+            ent = self._capture(data, key)
+        else:
+            if ent == "unseen":
+                self._seen[key] = "ran-once"
+            ent = None
+        if not isinstance(ent, dict):          # eager: first visit, capture failed, or too many keys
+            loss, _ = _fused_fwd_bwd(self.model, self.opt, data, self.tau, None, None)
+            return self._finish(loss)
+        ent["graph"].replay()
+        ops.LAUNCHES["n"] += ent["launches"]
+        self.replays += 1
+        return self._finish(ent["loss"])
+
+    def _capture(self, data, key):
+        g = torch.cuda.CUDAGraph()
+        l0 = ops.LAUNCHES["n"]
+        try:
+            with torch.cuda.graph(g):
+                # the index is rebuilt inside the graph: the same buffers may hold another batch at replay time
+                loss, index = _fused_fwd_bwd(self.model, self.opt, data, self.tau, None, None, use_index_cache=False)
+        except Exception as e:  # noqa: BLE001 - any capture failure leaves this key on the eager path
+            self.capture_error = repr(e)
+            ops.LAUNCHES["n"] = l0
+            self._seen[key] = "failed"
+            torch.cuda.synchronize()
+            return None
+        n = ops.LAUNCHES["n"] - l0
+        ops.LAUNCHES["n"] = l0
+        ent = {"graph": g, "loss": loss, "index": index, "data": data, "launches": n}
+        self._seen[key] = ent
+        return ent
 
 
 @torch.no_grad()

@@ -27,3 +27,19 @@ t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
 print(f"enqueue {1e3 * (t1 - t0) / K:.3f} ms/step, complete {1e3 * (t2 - t0) / K:.3f} ms/step")
+
+# same loop through the CUDA-graph replay path
+from pert_gnn_kdd23_b200.train import GraphedTrainStep  # noqa: E402
+
+gs = GraphedTrainStep(model, opt)
+for _ in range(5):
+    gs(b)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(K):
+    gs(b)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+t2 = time.perf_counter()
+print(f"graphed: enqueue {1e3 * (t1 - t0) / K:.3f} ms/step, complete {1e3 * (t2 - t0) / K:.3f} ms/step, "
+      f"replays {gs.replays}, capture_error {gs.capture_error}")

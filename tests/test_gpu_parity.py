@@ -356,6 +356,36 @@ def test_fused_train_step_matches_oracle_adam_step():
         assert_close(bbuf.float(), dict(oracle.named_buffers())[n].float(), what=n)
 
 
+def test_graphed_train_step_matches_eager():
+    """CUDA-graph replay of the step (train.GraphedTrainStep) == eager fused_train_step: same losses, same
+    parameters, and the graph path really ran (replays counted, no capture error)."""
+    import copy
+
+    from pert_gnn_kdd23_b200.train import FlatParams, FusedAdam, GraphedTrainStep, fused_train_step
+
+    _, model_a = make_models(1)
+    model_b = copy.deepcopy(model_a)
+    opt_a = FusedAdam(FlatParams(model_a), lr=1e-3)
+    opt_b = FusedAdam(FlatParams(model_b), lr=1e-3)
+    batches = [make_batch(1, 32, seed=s).to("cuda") for s in range(2)]
+    step_b = GraphedTrainStep(model_b, opt_b, 0.5)
+    for it in range(8):                                  # every key: eager, capture + replay, replay, replay
+        b = batches[it % 2]
+        la = fused_train_step(model_a, opt_a, b, 0.5)
+        lb = step_b(b)
+        assert_close(lb, la, rtol=1e-4, what=f"loss step {it}")
+    assert step_b.capture_error is None, step_b.capture_error
+    assert step_b.replays == 6
+    pa = dict(model_a.named_parameters())
+    for n, p in model_b.named_parameters():
+        if n.endswith("lin_key.bias") or (n.endswith("lin_skip.bias") and not n.startswith("convs.1.")):
+            continue                                     # zero-gradient parameters: +-lr rounding walk (see above)
+        assert_close(p, pa[n], rtol=2e-3, what=f"param {n} after 8 steps")
+    for n, bbuf in model_b.named_buffers():
+        if n.endswith("num_batches_tracked"):
+            assert int(bbuf) == int(dict(model_a.named_buffers())[n]) == 8, n
+
+
 def test_model_cfg1_eval():
     _model_parity(1, None, train=False)
 
