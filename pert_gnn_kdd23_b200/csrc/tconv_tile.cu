@@ -347,8 +347,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
         e = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4), ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4));
       rid = ID_RPC(id);
     };
-    // pass 1: dalpha_t = <g_i, v_j + e_t> (staged), dot = sum_t alpha_t dalpha_t
-    float dot = 0.f;
+    // ONE pass over the in-edges.  With d_t = <g_i, v_j + e_t> (shifted by the first edge's value c, which cancels
+    // exactly: sum_t ds_t = 0), w_t = alpha_t (d_t - c) and dot = sum_t w_t:
+    //   ds_t = alpha_t (d_t - c - dot) / sqrt(C)
+    //   dq_i = sum_t ds_t (k_j + e_t) = (P - dot Q) / sqrt(C),   P = sum_t w_t (k_j + e_t),  Q = sum_t alpha_t (k_j + e_t)
+    // so k_j, v_j and the table rows of an edge are fetched once (the two-pass form fetched the edge record and
+    // its table rows twice); ds_t is written by a scalar post-pass with the lanes spread over the node's edges.
+    float dot = 0.f, c_shift = 0.f;
+    float4 P = f4zero(), Q = f4zero();
+    float sumA = 0.f, sumW = 0.f;          // lane b: sums of alpha / w over this node's in-edges of rpc type b
     for (int t = 0; t < degmax; ++t) {
       const bool on = t < deg;
       const int p = p0 + t;
@@ -356,43 +363,40 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
       float al;
       float4 e;
       edge(p, on, j, al, e, rid);
-      float4 vv;
+      float4 kk, vv;
       const unsigned sl = (unsigned)(j - n0);
-      if (sl < (unsigned)nt) vv = lds4s(sa.tb + sl * (H * 4) + lane4);
-      else vv = ldg4(a.v + (size_t)j * H + lig * 4);
+      if (sl < (unsigned)nt) {
+        kk = lds4s(sa.ta + sl * (H * 4) + lane4);
+        vv = lds4s(sa.tb + sl * (H * 4) + lane4);
+      } else {
+        kk = ldg4(a.k + (size_t)j * H + lig * 4);
+        vv = ldg4(a.v + (size_t)j * H + lig * 4);
+      }
       const float da = gsum_full<LPR>(f4dot(g, f4add(vv, e)));
-      dot = fmaf(al, da, dot);
+      if (t == 0) c_shift = da;
+      const float dc = da - c_shift;
+      const float w = al * dc;             // alpha is 0 on finished groups
+      dot += w;
+      const float4 ke = f4add(kk, e);
+      P = f4fma(w, ke, P);
+      Q = f4fma(al, ke, Q);
+      if (HAS_E && on && lig == rid) { sumA += al; sumW += w; }
       if (on && lig == 0) {
         const int le = p - e_lo;
-        if (le < ne_s) stsf(sa.f1 + le * 4, da);
-        else a.dsp[p] = da;
+        if (le < ne_s) stsf(sa.f1 + le * 4, dc);
+        else a.dsp[p] = dc;
       }
     }
+    float4 dq;
+    dq.x = (P.x - dot * Q.x) * a.inv_sqrt_c; dq.y = (P.y - dot * Q.y) * a.inv_sqrt_c;
+    dq.z = (P.z - dot * Q.z) * a.inv_sqrt_c; dq.w = (P.w - dot * Q.w) * a.inv_sqrt_c;
+    const float sumS = (sumW - dot * sumA) * a.inv_sqrt_c;
     __syncwarp();
-    // pass 2: ds_t = alpha_t (dalpha_t - dot) / sqrt(C);  dq_i = sum_t ds_t (k_j + e_t)
-    float4 dq = f4zero();
-    float sumA = 0.f, sumS = 0.f;          // lane b: sums of alpha / ds over this node's in-edges of rpc type b
-    for (int t = 0; t < degmax; ++t) {
-      const bool on = t < deg;
-      const int p = p0 + t;
-      int j, rid;
-      float al;
-      float4 e;
-      edge(p, on, j, al, e, rid);
-      float4 kk;
-      const unsigned sl = (unsigned)(j - n0);
-      if (sl < (unsigned)nt) kk = lds4s(sa.ta + sl * (H * 4) + lane4);
-      else kk = ldg4(a.k + (size_t)j * H + lig * 4);
-      float da = 0.f;
-      if (on) {
-        const int le = p - e_lo;
-        da = (le < ne_s) ? ldsf(sa.f1 + le * 4) : a.dsp[p];
-      }
-      const float ds = al * (da - dot) * a.inv_sqrt_c;
-      dq = f4fma(ds, f4add(kk, e), dq);
-      if (HAS_E && on && lig == rid) { sumA += al; sumS += ds; }
-      __syncwarp();                      // all lanes have read a.dsp[p] (overflow path) before lane 0 rewrites it
-      if (on && lig == 0) a.dsp[p] = ds;
+    for (int p = p0 + lig; p < p1; p += LPR) {
+      const int le = p - e_lo;
+      const float dc = (le < ne_s) ? ldsf(sa.f1 + le * 4) : a.dsp[p];
+      const float al = (le < ne_s) ? ldsf(sa.f0 + le * 4) : __ldg(a.alpha + p);
+      a.dsp[p] = al * (dc - dot) * a.inv_sqrt_c;
     }
     if (valid) st4(a.out + (size_t)i * H + lig * 4, dq);
     if (HAS_E && a.rpc_ws && valid && lig < RPC_FAST) {
