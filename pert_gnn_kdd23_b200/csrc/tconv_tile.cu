@@ -16,6 +16,7 @@
 // Tile size (nodes) is chosen by the host so that two CTAs of 512 threads fit one SM; when the batch holds equally
 // sized graphs the tile is a whole number of graphs (no cut edges).
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -183,11 +184,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
   stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
   const int e_lo = S.ptr[0];
   const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
+  int bad = 0;   // a staged neighbour outside this tile
   for (int x = tid; x < ne_s; x += TILE_THREADS) {
-    S.e0[x] = __ldg(a.csr_src + e_lo + x);
+    const int nb_id = __ldg(a.csr_src + e_lo + x);
+    S.e0[x] = nb_id;
+    bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
     if (HAS_E) S.e1[x] = PACK_ID(__ldg(a.csr_if + e_lo + x), __ldg(a.csr_rpc + e_lo + x));
   }
-  __syncthreads();
+  // fast variant of the edge loops when every edge of the tile is staged and every neighbour row is in the tile
+  // (whole-graph tiles): no global-memory fallbacks are compiled into it
+  const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - e_lo <= a.edge_cap);
   mbar_wait(S.bar, 0);
 
   const SAddr sa = saddr_of(S);
@@ -203,87 +209,92 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
     q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
     if (a.s) s_n = ldg4(a.s + (size_t)(n0 + loc) * H + lig * 4);
   }
-  for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {   // warp-uniform: the warp's first group still has a node
-    const bool valid = loc < nt;
-    const int i = n0 + loc;
-    const float4 q = f4scale(qscale, q_n);
-    const float4 skip = s_n;
-    if (loc + GPC < nt) {
-      q_n = ldg4(a.q + (size_t)(i + GPC) * H + lig * 4);
-      if (a.s) s_n = ldg4(a.s + (size_t)(i + GPC) * H + lig * 4);
-    }
-    const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
-    const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
-    const int deg = p1 - p0;
-    const int degmax = __reduce_max_sync(0xffffffffu, deg);
-    float4 acc = f4zero();
-    float m = -INFINITY, Z = 0.f;
-    // software pipeline over edges: ids + table rows of edge t+1 are requested before edge t is consumed
-    int j = n0, id = 0;
-    float4 eif = f4zero(), erp = f4zero();
-    auto fetch = [&](int p, bool on) {
-      j = n0;
-      id = 0;
-      if (on) {
-        const int le = p - e_lo;
-        if (le < ne_s) {
-          j = ldsi(sa.e0 + le * 4);
-          if (HAS_E) id = ldsi(sa.e1 + le * 4);
-        } else {
-          j = __ldg(a.csr_src + p);
-          if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+  auto run = [&](auto fast_c) {
+    constexpr bool FAST = decltype(fast_c)::value;
+    for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {   // warp-uniform: the warp's first group still has a node
+      const bool valid = loc < nt;
+      const int i = n0 + loc;
+      const float4 q = f4scale(qscale, q_n);
+      const float4 skip = s_n;
+      if (loc + GPC < nt) {
+        q_n = ldg4(a.q + (size_t)(i + GPC) * H + lig * 4);
+        if (a.s) s_n = ldg4(a.s + (size_t)(i + GPC) * H + lig * 4);
+      }
+      const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
+      const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
+      const int deg = p1 - p0;
+      const int degmax = __reduce_max_sync(0xffffffffu, deg);
+      float4 acc = f4zero();
+      float m = -INFINITY, Z = 0.f;
+      // software pipeline over edges: ids + table rows of edge t+1 are requested before edge t is consumed
+      int j = n0, id = 0;
+      float4 eif = f4zero(), erp = f4zero();
+      auto fetch = [&](int p, bool on) {
+        j = n0;
+        id = 0;
+        if (on) {
+          const int le = p - e_lo;
+          if (FAST || le < ne_s) {
+            j = ldsi(sa.e0 + le * 4);
+            if (HAS_E) id = ldsi(sa.e1 + le * 4);
+          } else {
+            j = __ldg(a.csr_src + p);
+            if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+          }
         }
+        if (HAS_E) {
+          eif = ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4);
+          erp = ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4);
+        }
+      };
+      fetch(p0, 0 < deg);
+      for (int t = 0; t < degmax; ++t) {
+        const bool on = t < deg;
+        const int p = p0 + t;
+        const int cj = j;
+        const float4 e = f4add(eif, erp);
+        fetch(p + 1, t + 1 < deg);
+        float4 kk, vv;
+        const unsigned sl = (unsigned)(cj - n0);
+        if (FAST || sl < (unsigned)nt) {
+          kk = lds4s(sa.ta + sl * (H * 4) + lane4);
+          vv = lds4s(sa.tb + sl * (H * 4) + lane4);
+        } else {
+          kk = ldg4(a.k + (size_t)cj * H + lig * 4);
+          vv = ldg4(a.v + (size_t)cj * H + lig * 4);
+        }
+        if (HAS_E) {
+          kk = f4add(kk, e);
+          vv = f4add(vv, e);
+        }
+        const float s = gsum_full<LPR>(f4dot(q, kk));
+        if (on && lig == 0) {
+          const int le = p - e_lo;
+          if (FAST || le < ne_s) stsf(sa.f0 + le * 4, s);
+          else a.alpha[p] = s;
+        }
+        const float mn = on ? fmaxf(m, s) : m;
+        const float sc = on ? ex2(m - mn) : 1.f;
+        const float pz = on ? ex2(s - mn) : 0.f;
+        Z = fmaf(Z, sc, pz);
+        acc.x = fmaf(pz, vv.x, acc.x * sc);
+        acc.y = fmaf(pz, vv.y, acc.y * sc);
+        acc.z = fmaf(pz, vv.z, acc.z * sc);
+        acc.w = fmaf(pz, vv.w, acc.w * sc);
+        m = mn;
       }
-      if (HAS_E) {
-        eif = ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4);
-        erp = ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4);
-      }
-    };
-    fetch(p0, 0 < deg);
-    for (int t = 0; t < degmax; ++t) {
-      const bool on = t < deg;
-      const int p = p0 + t;
-      const int cj = j;
-      const float4 e = f4add(eif, erp);
-      fetch(p + 1, t + 1 < deg);
-      float4 kk, vv;
-      const unsigned sl = (unsigned)(cj - n0);
-      if (sl < (unsigned)nt) {
-        kk = lds4s(sa.ta + sl * (H * 4) + lane4);
-        vv = lds4s(sa.tb + sl * (H * 4) + lane4);
-      } else {
-        kk = ldg4(a.k + (size_t)cj * H + lig * 4);
-        vv = ldg4(a.v + (size_t)cj * H + lig * 4);
-      }
-      if (HAS_E) {
-        kk = f4add(kk, e);
-        vv = f4add(vv, e);
-      }
-      const float s = gsum_full<LPR>(f4dot(q, kk));
-      if (on && lig == 0) {
+      const float invZ = 1.0f / (Z + 1e-16f);
+      if (valid) st4(a.out + (size_t)i * H + lig * 4, f4add(f4scale(invZ, acc), skip));
+      __syncwarp();
+      for (int p = p0 + lig; p < p1; p += LPR) {
         const int le = p - e_lo;
-        if (le < ne_s) stsf(sa.f0 + le * 4, s);
-        else a.alpha[p] = s;
+        const float s = (FAST || le < ne_s) ? ldsf(sa.f0 + le * 4) : a.alpha[p];
+        a.alpha[p] = ex2(s - m) * invZ;
       }
-      const float mn = on ? fmaxf(m, s) : m;
-      const float sc = on ? ex2(m - mn) : 1.f;
-      const float pz = on ? ex2(s - mn) : 0.f;
-      Z = fmaf(Z, sc, pz);
-      acc.x = fmaf(pz, vv.x, acc.x * sc);
-      acc.y = fmaf(pz, vv.y, acc.y * sc);
-      acc.z = fmaf(pz, vv.z, acc.z * sc);
-      acc.w = fmaf(pz, vv.w, acc.w * sc);
-      m = mn;
     }
-    const float invZ = 1.0f / (Z + 1e-16f);
-    if (valid) st4(a.out + (size_t)i * H + lig * 4, f4add(f4scale(invZ, acc), skip));
-    __syncwarp();
-    for (int p = p0 + lig; p < p1; p += LPR) {
-      const int le = p - e_lo;
-      const float s = (le < ne_s) ? ldsf(sa.f0 + le * 4) : a.alpha[p];
-      a.alpha[p] = ex2(s - m) * invZ;
-    }
-  }
+  };
+  if (all_in) run(std::true_type{});
+  else run(std::false_type{});
 }
 
 // ============================================================== backward, target pass (dq, ds)
@@ -300,12 +311,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
   stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
   const int e_lo = S.ptr[0];
   const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
+  int bad = 0;   // a staged neighbour outside this tile
   for (int x = tid; x < ne_s; x += TILE_THREADS) {
-    S.e0[x] = __ldg(a.csr_src + e_lo + x);
+    const int nb_id = __ldg(a.csr_src + e_lo + x);
+    S.e0[x] = nb_id;
+    bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
     S.f0[x] = __ldg(a.alpha + e_lo + x);
     if (HAS_E) S.e1[x] = PACK_ID(__ldg(a.csr_if + e_lo + x), __ldg(a.csr_rpc + e_lo + x));
   }
-  __syncthreads();
+  // fast variant of the edge loops when every edge of the tile is staged and every neighbour row is in the tile
+  // (whole-graph tiles): no global-memory fallbacks are compiled into it
+  const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - e_lo <= a.edge_cap);
   mbar_wait(S.bar, 0);
 
   const SAddr sa = saddr_of(S);
@@ -316,94 +332,99 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
   int loc = g0 + grp;
   float4 g_n = f4zero();
   if (loc < nt) g_n = ldg4(a.g + (size_t)(n0 + loc) * H + lig * 4);
-  for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {
-    const bool valid = loc < nt;
-    const int i = n0 + loc;
-    const float4 g = g_n;
-    if (loc + GPC < nt) g_n = ldg4(a.g + (size_t)(i + GPC) * H + lig * 4);
-    const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
-    const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
-    const int deg = p1 - p0;
-    const int degmax = __reduce_max_sync(0xffffffffu, deg);
-    // one edge record: source row offsets + e = T_if[a] + T_rpc[b]
-    auto edge = [&](int p, bool on, int& j, float& al, float4& e, int& rid) {
-      j = n0;
-      al = 0.f;
-      int id = 0;
-      if (on) {
-        const int le = p - e_lo;
-        if (le < ne_s) {
-          j = ldsi(sa.e0 + le * 4);
-          al = ldsf(sa.f0 + le * 4);
-          if (HAS_E) id = ldsi(sa.e1 + le * 4);
+  auto run = [&](auto fast_c) {
+    constexpr bool FAST = decltype(fast_c)::value;
+    for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {
+      const bool valid = loc < nt;
+      const int i = n0 + loc;
+      const float4 g = g_n;
+      if (loc + GPC < nt) g_n = ldg4(a.g + (size_t)(i + GPC) * H + lig * 4);
+      const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
+      const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
+      const int deg = p1 - p0;
+      const int degmax = __reduce_max_sync(0xffffffffu, deg);
+      // one edge record: source row offsets + e = T_if[a] + T_rpc[b]
+      auto edge = [&](int p, bool on, int& j, float& al, float4& e, int& rid) {
+        j = n0;
+        al = 0.f;
+        int id = 0;
+        if (on) {
+          const int le = p - e_lo;
+          if (FAST || le < ne_s) {
+            j = ldsi(sa.e0 + le * 4);
+            al = ldsf(sa.f0 + le * 4);
+            if (HAS_E) id = ldsi(sa.e1 + le * 4);
+          } else {
+            j = __ldg(a.csr_src + p);
+            al = __ldg(a.alpha + p);
+            if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+          }
+        }
+        e = f4zero();
+        if (HAS_E)
+          e = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4), ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4));
+        rid = ID_RPC(id);
+      };
+      // ONE pass over the in-edges.  With d_t = <g_i, v_j + e_t> (shifted by the first edge's value c, which cancels
+      // exactly: sum_t ds_t = 0), w_t = alpha_t (d_t - c) and dot = sum_t w_t:
+      //   ds_t = alpha_t (d_t - c - dot) / sqrt(C)
+      //   dq_i = sum_t ds_t (k_j + e_t) = (P - dot Q) / sqrt(C),   P = sum_t w_t (k_j + e_t),  Q = sum_t alpha_t (k_j + e_t)
+      // so k_j, v_j and the table rows of an edge are fetched once (the two-pass form fetched the edge record and
+      // its table rows twice); ds_t is written by a scalar post-pass with the lanes spread over the node's edges.
+      float dot = 0.f, c_shift = 0.f;
+      float4 P = f4zero(), Q = f4zero();
+      float sumA = 0.f, sumW = 0.f;          // lane b: sums of alpha / w over this node's in-edges of rpc type b
+      for (int t = 0; t < degmax; ++t) {
+        const bool on = t < deg;
+        const int p = p0 + t;
+        int j, rid;
+        float al;
+        float4 e;
+        edge(p, on, j, al, e, rid);
+        float4 kk, vv;
+        const unsigned sl = (unsigned)(j - n0);
+        if (FAST || sl < (unsigned)nt) {
+          kk = lds4s(sa.ta + sl * (H * 4) + lane4);
+          vv = lds4s(sa.tb + sl * (H * 4) + lane4);
         } else {
-          j = __ldg(a.csr_src + p);
-          al = __ldg(a.alpha + p);
-          if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+          kk = ldg4(a.k + (size_t)j * H + lig * 4);
+          vv = ldg4(a.v + (size_t)j * H + lig * 4);
+        }
+        const float da = gsum_full<LPR>(f4dot(g, f4add(vv, e)));
+        if (t == 0) c_shift = da;
+        const float dc = da - c_shift;
+        const float w = al * dc;             // alpha is 0 on finished groups
+        dot += w;
+        const float4 ke = f4add(kk, e);
+        P = f4fma(w, ke, P);
+        Q = f4fma(al, ke, Q);
+        if (HAS_E && on && lig == rid) { sumA += al; sumW += w; }
+        if (on && lig == 0) {
+          const int le = p - e_lo;
+          if (FAST || le < ne_s) stsf(sa.f1 + le * 4, dc);
+          else a.dsp[p] = dc;
         }
       }
-      e = f4zero();
-      if (HAS_E)
-        e = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4), ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4));
-      rid = ID_RPC(id);
-    };
-    // ONE pass over the in-edges.  With d_t = <g_i, v_j + e_t> (shifted by the first edge's value c, which cancels
-    // exactly: sum_t ds_t = 0), w_t = alpha_t (d_t - c) and dot = sum_t w_t:
-    //   ds_t = alpha_t (d_t - c - dot) / sqrt(C)
-    //   dq_i = sum_t ds_t (k_j + e_t) = (P - dot Q) / sqrt(C),   P = sum_t w_t (k_j + e_t),  Q = sum_t alpha_t (k_j + e_t)
-    // so k_j, v_j and the table rows of an edge are fetched once (the two-pass form fetched the edge record and
-    // its table rows twice); ds_t is written by a scalar post-pass with the lanes spread over the node's edges.
-    float dot = 0.f, c_shift = 0.f;
-    float4 P = f4zero(), Q = f4zero();
-    float sumA = 0.f, sumW = 0.f;          // lane b: sums of alpha / w over this node's in-edges of rpc type b
-    for (int t = 0; t < degmax; ++t) {
-      const bool on = t < deg;
-      const int p = p0 + t;
-      int j, rid;
-      float al;
-      float4 e;
-      edge(p, on, j, al, e, rid);
-      float4 kk, vv;
-      const unsigned sl = (unsigned)(j - n0);
-      if (sl < (unsigned)nt) {
-        kk = lds4s(sa.ta + sl * (H * 4) + lane4);
-        vv = lds4s(sa.tb + sl * (H * 4) + lane4);
-      } else {
-        kk = ldg4(a.k + (size_t)j * H + lig * 4);
-        vv = ldg4(a.v + (size_t)j * H + lig * 4);
-      }
-      const float da = gsum_full<LPR>(f4dot(g, f4add(vv, e)));
-      if (t == 0) c_shift = da;
-      const float dc = da - c_shift;
-      const float w = al * dc;             // alpha is 0 on finished groups
-      dot += w;
-      const float4 ke = f4add(kk, e);
-      P = f4fma(w, ke, P);
-      Q = f4fma(al, ke, Q);
-      if (HAS_E && on && lig == rid) { sumA += al; sumW += w; }
-      if (on && lig == 0) {
+      float4 dq;
+      dq.x = (P.x - dot * Q.x) * a.inv_sqrt_c; dq.y = (P.y - dot * Q.y) * a.inv_sqrt_c;
+      dq.z = (P.z - dot * Q.z) * a.inv_sqrt_c; dq.w = (P.w - dot * Q.w) * a.inv_sqrt_c;
+      const float sumS = (sumW - dot * sumA) * a.inv_sqrt_c;
+      __syncwarp();
+      for (int p = p0 + lig; p < p1; p += LPR) {
         const int le = p - e_lo;
-        if (le < ne_s) stsf(sa.f1 + le * 4, dc);
-        else a.dsp[p] = dc;
+        const float dc = (FAST || le < ne_s) ? ldsf(sa.f1 + le * 4) : a.dsp[p];
+        const float al = (FAST || le < ne_s) ? ldsf(sa.f0 + le * 4) : __ldg(a.alpha + p);
+        a.dsp[p] = al * (dc - dot) * a.inv_sqrt_c;
+      }
+      if (valid) st4(a.out + (size_t)i * H + lig * 4, dq);
+      if (HAS_E && a.rpc_ws && valid && lig < RPC_FAST) {
+        a.rpc_ws[(size_t)i * 2 * RPC_FAST + lig] = sumA;
+        a.rpc_ws[(size_t)i * 2 * RPC_FAST + RPC_FAST + lig] = sumS;
       }
     }
-    float4 dq;
-    dq.x = (P.x - dot * Q.x) * a.inv_sqrt_c; dq.y = (P.y - dot * Q.y) * a.inv_sqrt_c;
-    dq.z = (P.z - dot * Q.z) * a.inv_sqrt_c; dq.w = (P.w - dot * Q.w) * a.inv_sqrt_c;
-    const float sumS = (sumW - dot * sumA) * a.inv_sqrt_c;
-    __syncwarp();
-    for (int p = p0 + lig; p < p1; p += LPR) {
-      const int le = p - e_lo;
-      const float dc = (le < ne_s) ? ldsf(sa.f1 + le * 4) : a.dsp[p];
-      const float al = (le < ne_s) ? ldsf(sa.f0 + le * 4) : __ldg(a.alpha + p);
-      a.dsp[p] = al * (dc - dot) * a.inv_sqrt_c;
-    }
-    if (valid) st4(a.out + (size_t)i * H + lig * 4, dq);
-    if (HAS_E && a.rpc_ws && valid && lig < RPC_FAST) {
-      a.rpc_ws[(size_t)i * 2 * RPC_FAST + lig] = sumA;
-      a.rpc_ws[(size_t)i * 2 * RPC_FAST + RPC_FAST + lig] = sumS;
-    }
-  }
+  };
+  if (all_in) run(std::true_type{});
+  else run(std::false_type{});
 }
 
 // ============================================================== backward, source pass (dk, dv, table grads)
@@ -424,14 +445,19 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   const int c_lo = S.ptr[0];
   const int ne_s = min(S.ptr[nt] - c_lo, a.edge_cap);
   // per out-edge (CSC order): target, and through the CSR slot its alpha, ds and attribute ids
+  int bad = 0;   // a staged neighbour outside this tile
   for (int x = tid; x < ne_s; x += TILE_THREADS) {
     const int p = __ldg(a.csc_pos + c_lo + x);
-    S.e0[x] = __ldg(a.csc_dst + c_lo + x);
+    const int nb_id = __ldg(a.csc_dst + c_lo + x);
+    S.e0[x] = nb_id;
+    bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
     S.f0[x] = __ldg(a.alpha + p);
     S.f1[x] = __ldg(a.dsp + p);
     if (HAS_E) S.e1[x] = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
   }
-  __syncthreads();
+  // fast variant of the edge loops when every edge of the tile is staged and every neighbour row is in the tile
+  // (whole-graph tiles): no global-memory fallbacks are compiled into it
+  const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - c_lo <= a.edge_cap);
   mbar_wait(S.bar, 0);
 
   const SAddr sa = saddr_of(S);
@@ -439,58 +465,63 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   constexpr int GPC = TILE_THREADS / LPR;
   const uint32_t lane4 = lig * 16;
   const int g0 = (tid >> 5) * GPW;
-  for (int loc = g0 + grp; g0 + (loc - g0 - grp) < nt; loc += GPC) {
-    const bool valid = loc < nt;
-    const int jn = n0 + loc;
-    const int c0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
-    const int c1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
-    const int deg = c1 - c0;
-    const int degmax = __reduce_max_sync(0xffffffffu, deg);
-    float4 dk = f4zero(), dv = f4zero();
-    for (int t = 0; t < degmax; ++t) {
-      const bool on = t < deg;
-      const int c = c0 + t;
-      int i = n0, id = 0;
-      float al = 0.f, ds = 0.f;
-      if (on) {
-        const int le = c - c_lo;
-        if (le < ne_s) {
-          i = ldsi(sa.e0 + le * 4); al = ldsf(sa.f0 + le * 4); ds = ldsf(sa.f1 + le * 4);
-          if (HAS_E) id = ldsi(sa.e1 + le * 4);
+  auto run = [&](auto fast_c) {
+    constexpr bool FAST = decltype(fast_c)::value;
+    for (int loc = g0 + grp; g0 + (loc - g0 - grp) < nt; loc += GPC) {
+      const bool valid = loc < nt;
+      const int jn = n0 + loc;
+      const int c0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
+      const int c1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
+      const int deg = c1 - c0;
+      const int degmax = __reduce_max_sync(0xffffffffu, deg);
+      float4 dk = f4zero(), dv = f4zero();
+      for (int t = 0; t < degmax; ++t) {
+        const bool on = t < deg;
+        const int c = c0 + t;
+        int i = n0, id = 0;
+        float al = 0.f, ds = 0.f;
+        if (on) {
+          const int le = c - c_lo;
+          if (FAST || le < ne_s) {
+            i = ldsi(sa.e0 + le * 4); al = ldsf(sa.f0 + le * 4); ds = ldsf(sa.f1 + le * 4);
+            if (HAS_E) id = ldsi(sa.e1 + le * 4);
+          } else {
+            const int p = __ldg(a.csc_pos + c);
+            i = __ldg(a.csc_dst + c); al = __ldg(a.alpha + p); ds = __ldg(a.dsp + p);
+            if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+          }
+        }
+        float4 gi, qi;
+        const unsigned sl = (unsigned)(i - n0);
+        if (FAST || sl < (unsigned)nt) {
+          gi = lds4s(sa.ta + sl * (H * 4) + lane4);
+          qi = lds4s(sa.tb + sl * (H * 4) + lane4);
         } else {
-          const int p = __ldg(a.csc_pos + c);
-          i = __ldg(a.csc_dst + c); al = __ldg(a.alpha + p); ds = __ldg(a.dsp + p);
-          if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+          gi = ldg4(a.g + (size_t)i * H + lig * 4);
+          qi = ldg4(a.q + (size_t)i * H + lig * 4);
+        }
+        dk = f4fma(ds, qi, dk);
+        dv = f4fma(al, gi, dv);
+        if (HAS_E && on) {
+          const float4 de = f4fma(ds, qi, f4scale(al, gi));
+          red4(a.dt_if + (size_t)ID_IF(id) * H + lig * 4, de);
+          if (!a.rpc_ws) {                 // general path (n_rpc > RPC_FAST): privatised table, per-edge atomics
+            float* prp = s_drpc + ID_RPC(id) * H + lig * 4;
+            atomicAdd(prp + 0, de.x);
+            atomicAdd(prp + 1, de.y);
+            atomicAdd(prp + 2, de.z);
+            atomicAdd(prp + 3, de.w);
+          }
         }
       }
-      float4 gi, qi;
-      const unsigned sl = (unsigned)(i - n0);
-      if (sl < (unsigned)nt) {
-        gi = lds4s(sa.ta + sl * (H * 4) + lane4);
-        qi = lds4s(sa.tb + sl * (H * 4) + lane4);
-      } else {
-        gi = ldg4(a.g + (size_t)i * H + lig * 4);
-        qi = ldg4(a.q + (size_t)i * H + lig * 4);
-      }
-      dk = f4fma(ds, qi, dk);
-      dv = f4fma(al, gi, dv);
-      if (HAS_E && on) {
-        const float4 de = f4fma(ds, qi, f4scale(al, gi));
-        red4(a.dt_if + (size_t)ID_IF(id) * H + lig * 4, de);
-        if (!a.rpc_ws) {                 // general path (n_rpc > RPC_FAST): privatised table, per-edge atomics
-          float* prp = s_drpc + ID_RPC(id) * H + lig * 4;
-          atomicAdd(prp + 0, de.x);
-          atomicAdd(prp + 1, de.y);
-          atomicAdd(prp + 2, de.z);
-          atomicAdd(prp + 3, de.w);
-        }
+      if (valid) {
+        st4(a.dk + (size_t)jn * H + lig * 4, dk);
+        st4(a.dv + (size_t)jn * H + lig * 4, dv);
       }
     }
-    if (valid) {
-      st4(a.dk + (size_t)jn * H + lig * 4, dk);
-      st4(a.dv + (size_t)jn * H + lig * 4, dv);
-    }
-  }
+  };
+  if (all_in) run(std::true_type{});
+  else run(std::false_type{});
   if (HAS_E && a.rpc_ws) {
     // dT_rpc tile contribution: thread = (column, node slice); the per-target scalars are warp-uniform loads
     constexpr int NSL = TILE_THREADS / H;
