@@ -5,7 +5,7 @@
 #include <vector>
 
 static void dump(const char* name, int roles, int iters, int evs, float ms) {
-  long long h[4][32][4];
+  long long h[6][32][4];
   cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
   long long t0 = h[0][0][0];
   printf("== %s  %.2f us/launch (cycles relative to first producer stamp)\n", name, ms * 1000.f);
@@ -31,7 +31,7 @@ static void dump(const char* name, int roles, int iters, int evs, float ms) {
          hi_entry - lo, lo_exit - lo, hi - lo, ct[0][0] - lo, ct[0][1] - lo);
   static unsigned long long zc[512][2];
   cudaMemcpyToSymbol(g_cta_t, zc, sizeof(zc));
-  static long long z[4][32][4];
+  static long long z[6][32][4];
   cudaMemcpyToSymbol(g_trace, z, sizeof(z));
 }
 
@@ -54,7 +54,7 @@ int main() {
     cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     if (rc) printf("nt fwd rc %d\n", rc);
   }
-  dump("NT forward [N,64]x[256,64]^T -> planes", 4, 7, 4, ms);
+  dump("NT forward [N,64]x[256,64]^T -> planes", 5, 8, 4, ms);
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
     // data gradient: dX[N,64] = dP[N,256 blocked] . Wt[64,256]^T   (B rows = output features, K = 256)
@@ -62,7 +62,7 @@ int main() {
     cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     if (rc) printf("nt dgrad rc %d\n", rc);
   }
-  dump("NT dgrad planes x [64,256]^T -> [N,64]", 4, 12, 4, ms);
+  dump("NT dgrad planes x [64,256]^T -> [N,64]", 5, 14, 4, ms);
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
     int rc = pert_gemm_tn_tc(P, H, H, N * H, X, H, 0, 0, dW, H, cs, N, 4 * H, H, 0);

@@ -95,7 +95,7 @@ __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x)
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
 
 #ifdef PERT_TC_TRACE
-__device__ long long g_trace[4][32][4];   // [role][tile or chunk][event] clock64 stamps of CTA (0,0)
+__device__ long long g_trace[6][32][4];   // [role][tile or chunk][event] clock64 stamps of CTA (0,0)
 __device__ unsigned long long g_cta_t[512][2];   // per-CTA globaltimer at entry / exit
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -913,15 +913,29 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
       : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(x),
+               "r"(y), "r"(z), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 struct NtTmaBars {
   uint64_t ring_full[RING_MAX], ring_empty[RING_MAX], a_full[2], a_empty[2], d_full[2], d_empty[2];
   int ring_meta[RING_MAX], a_meta[2], d_meta[2];
 };
 
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-    k_gemm_nt_tma(const __grid_constant__ CUtensorMap tmA, NtArgs g, int NS, int row_blk) {
+    k_gemm_nt_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, NtArgs g, int NS,
+                  int row_blk) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[128];
   __shared__ __align__(8) NtTmaBars bars;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   CTA_T(0);
@@ -964,6 +978,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
     // ================= loader (one thread) =================
     if (lane == 0) {
       uint32_t rs = 0, rph = 0;
+      int tr_i = 0;
       while (true) {
         const unsigned int c = atomicAdd(&g_nt_ctr[blockIdx.y], 1u);
         if (c >= (unsigned int)mtiles) {
@@ -977,7 +992,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
           const int k0 = ch * KC;
           const int kw = min(KC, K - k0);
           const int x0 = k0 % g.a_cb, y0 = (k0 / g.a_cb) * row_blk + (int)c * 128;
+          TRACE(0, tr_i, 0);
           mbar_wait(&bars.ring_empty[rs], rph ^ 1);
+          TRACE(0, tr_i, 1);
+          ++tr_i;
           bars.ring_meta[rs] = (int)c;
           unsigned char* st = ring0 + (size_t)rs * 32 * 1024;
           const int nbox = kw > 32 ? 2 : 1;
@@ -993,11 +1011,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
     // ================= A converters: ring stage (swizzled rows) -> hi/lo -> TMEM stage =================
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     uint32_t rs = 0, rph = 0, stage = 0, ph = 0;
-    int ch = 0;
+    int ch = 0, tr_i = 0;
     while (true) {
+      TRACE(1, tr_i, 0);
       mbar_wait(&bars.ring_full[rs], rph);
       const int mt = bars.ring_meta[rs];
       if (mt < 0) break;
+      TRACE(1, tr_i, 1);
       const int kw = min(KC, K - ch * KC);
       const unsigned char* row = ring0 + (size_t)rs * 32 * 1024 + tid * 128;
       float4 vr[KC / 4];
@@ -1006,6 +1026,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         vr[q] = *reinterpret_cast<const float4*>(row + (q >> 3) * 16384 + (((q & 7) ^ (tid & 7)) << 4));
       mbar_wait(&bars.a_empty[stage], ph ^ 1);
       fence_after();
+      TRACE(1, tr_i, 2);
       const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
 #pragma unroll
       for (int grp = 0; grp < KC / 16; ++grp) {
@@ -1028,6 +1049,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       mbar_arrive(&bars.ring_empty[rs]);
       if (tid == 0) bars.a_meta[stage] = mt;
       mbar_arrive(&bars.a_full[stage]);
+      TRACE(1, tr_i, 3);
+      ++tr_i;
       if (++ch == nchunks) ch = 0;
       stage ^= 1;
       if (stage == 0) ph ^= 1;
@@ -1065,6 +1088,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         }
       }
     }
+    if (tid - 128 < 128) {
+      const int c = tid - 128;
+      s_bias[c] = (g.bias && c < BN && n0 + c < g.Nc) ? __ldg(g.bias + n0 + c) : 0.f;
+    }
     fence_async_smem();
     asm volatile("bar.sync 3, 160;" ::: "memory");
     if (warp == 4) {
@@ -1074,15 +1101,18 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         const uint32_t bhi0 = smem_u32(sBhi), blo0 = smem_u32(sBlo);
         uint32_t stage = 0, ph = 0, ds = 0, dph = 0;
         bool stop = false;
+        int tr_i = 0;
         while (!stop) {
           uint32_t t_d = 0;
           for (int ch = 0; ch < nchunks; ++ch) {
             const int k0 = ch * KC;
             const int kw = min(KC, K - k0);
+            TRACE(2, tr_i, 0);
             mbar_wait(&bars.a_full[stage], ph);
             fence_after();
             const int mt = bars.a_meta[stage];
             if (mt < 0) { stop = true; break; }
+            TRACE(2, tr_i, 1);
             if (ch == 0) {
               mbar_wait(&bars.d_empty[ds], dph ^ 1);
               fence_after();
@@ -1100,6 +1130,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
               mma_ts(t_d, t_hi + s * 8, blo, idesc, 1u);
             }
             mma_commit(&bars.a_empty[stage]);
+            TRACE(2, tr_i, 2);
+            ++tr_i;
             stage ^= 1;
             if (stage == 0) ph ^= 1;
           }
@@ -1115,63 +1147,72 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       }
       __syncwarp();
     } else {
-      // ================= epilogue: accumulator stage -> registers -> (+bias, relu) -> global =================
+      // ================= epilogue: accumulator stage -> registers (+bias, relu) -> swizzled slab -> TMA store ======
+      // A thread owns one accumulator row.  Each epilogue WARP works on its own 32 rows: it writes their 32 columns
+      // of a slab into its 4 KB piece of shared memory in the 128-byte-swizzle pattern and its lane 0 hands the
+      // [32 x 32] box to the TMA unit (cp.async.bulk.tensor store) -- the global writes are asynchronous full lines,
+      // the warps never issue LDS/STG for them and never wait for each other (no CTA-level barrier in the loop; the
+      // thread-store version spent ~1200 cycles per slab, 4850 per 128x128 tile: the bottleneck of the forward GEMM).
+      // Two buffers per warp alternate; a buffer is rewritten only after the store that read it has drained.  The
+      // TMEM load of the next slab is in flight while the current one is written out.
       const int q4 = warp & 3;
       const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-      const int et = (warp - 5) * 32 + lane;
-      const int trow = q4 * 32 + lane;
-      const int c8 = et & 7, rsub = et >> 3;
+      unsigned char* wslab = stD + q4 * 4096;
       uint32_t ds = 0, dph = 0;
-      float4 bv[4];
-#pragma unroll
-      for (int sl = 0; sl < 4; ++sl) {
-        const int col = n0 + sl * 32 + c8 * 4;
-        bv[sl] = (g.bias && sl * 32 + c8 * 4 < BN && col < g.Nc) ? ldg4(g.bias + col) : f4zero();
-      }
+      uint32_t slab_ctr = 0;
+      int tr_i = 0;
+      const int nsl = (BN + 31) / 32;
       while (true) {
+        TRACE(4, tr_i, 0);
         mbar_wait(&bars.d_full[ds], dph);
         fence_after();
         const int mt = bars.d_meta[ds];
         if (mt < 0) break;
-        const int row0 = mt * 128;
+        TRACE(4, tr_i, 1);
+        const int row0 = mt * 128 + q4 * 32;
         const uint32_t t_d = tmem + lane_off + D_COL + ds * 128;
+        uint32_t ra[2][2][16];                            // [buffer][column half][16 columns]
+        tmem_ld16(t_d, ra[0][0]);
+        tmem_ld16(t_d + 16, ra[0][1]);
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
+          if (sl >= nsl) break;
           const int c0 = sl * 32;
-          if (c0 >= BN) break;
-          uint32_t r0[16], r1[16];
-          tmem_ld16(t_d + c0, r0);
-          tmem_ld16(t_d + c0 + 16, r1);
+          unsigned char* slab = wslab + (slab_ctr & 1) * 16384;
+          ++slab_ctr;
           tmem_wait_ld();
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            *reinterpret_cast<uint4*>(stD + trow * 128 + (((q ^ trow) & 7) << 4)) =
-                make_uint4(r0[q * 4], r0[q * 4 + 1], r0[q * 4 + 2], r0[q * 4 + 3]);
-            *reinterpret_cast<uint4*>(stD + trow * 128 + ((((q + 4) ^ trow) & 7) << 4)) =
-                make_uint4(r1[q * 4], r1[q * 4 + 1], r1[q * 4 + 2], r1[q * 4 + 3]);
+          if (sl + 1 < nsl) {
+            tmem_ld16(t_d + c0 + 32, ra[(sl + 1) & 1][0]);
+            tmem_ld16(t_d + c0 + 48, ra[(sl + 1) & 1][1]);
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          const int col = n0 + c0 + c8 * 4;
-          if (c0 + c8 * 4 < BN && col < g.Nc) {
-            float* cbase = g.C + (size_t)(col / g.c_cb) * g.c_cbs + (col % g.c_cb);
+          if (lane == 0) bulk_wait_read<1>();             // this warp's store from two slabs ago has read the buffer
+          __syncwarp();
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 16 + rsub;
-              if (row0 + r < g.M) {
-                float4 o = *reinterpret_cast<const float4*>(stD + r * 128 + (((c8 ^ r) & 7) << 4));
-                o = f4add(o, bv[sl]);
-                if (g.relu) o = f4max(o, f4zero());
-                st4(cbase + (size_t)(row0 + r) * g.ldc, o);
-              }
-            }
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(s_bias + c0 + q * 4);   // warp-uniform: broadcast
+            const uint32_t* rr = &ra[sl & 1][q >> 2][(q & 3) * 4];
+            float4 o = make_float4(__uint_as_float(rr[0]) + bq.x, __uint_as_float(rr[1]) + bq.y,
+                                   __uint_as_float(rr[2]) + bq.z, __uint_as_float(rr[3]) + bq.w);
+            if (g.relu) o = f4max(o, f4zero());
+            *reinterpret_cast<float4*>(slab + lane * 128 + (((q ^ lane) & 7) << 4)) = o;
+          }
+          fence_async_smem();                             // generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            const int col = n0 + c0;
+            tma_store_3d(&tmC, slab, col % g.c_cb, row0, col / g.c_cb);
+            bulk_commit();
           }
         }
+        // (the last tcgen05.wait::ld above covered every load of this accumulator stage)
         fence_before();
         mbar_arrive(&bars.d_empty[ds]);
+        TRACE(4, tr_i, 2);
+        ++tr_i;
         ds ^= 1;
         if (ds == 0) dph ^= 1;
       }
+      if (lane == 0) bulk_wait_all();                     // all stores complete before the CTA (and its smem) goes away
     }
   }
   fence_before();
@@ -1243,7 +1284,7 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
     const bool blocked = nblocks > 1;
     const bool ok = (!blocked || (a_cbs % lda == 0 && a_cb % KC == 0)) && (size_t)lda * 4 % 16 == 0;
     const size_t bbytes = ((size_t)BN * K * 8 + 1023) & ~(size_t)1023;
-    int NS = (int)((226 * 1024 - 1024 - (long long)bbytes - 16 * 1024) / (32 * 1024));
+    int NS = (int)((226 * 1024 - 1024 - (long long)bbytes - 32 * 1024) / (32 * 1024));
     if (NS > RING_MAX) NS = RING_MAX;
     if (ok && NS >= 2) {
       const long long row_blk = blocked ? a_cbs / lda : 0;
@@ -1256,14 +1297,29 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
       CUresult cr = encode_tiled_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)A, gdim, gstr, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      // C as a 3-D tensor {columns of one block, rows, blocks}: stores clip at M and at the block width
+      CUtensorMap tc;
+      const int cblocks = (Nc + c_cb - 1) / c_cb;
+      const bool c_ok = (c_cb % 32 == 0 || cblocks == 1) && (BN % 32 == 0 || nblk == 1) && (cblocks == 1 || Nc % c_cb == 0);
+      if (cr == CUDA_SUCCESS && c_ok) {
+        const cuuint64_t cdim[3] = {(cuuint64_t)(cblocks > 1 ? c_cb : Nc), (cuuint64_t)M, (cuuint64_t)cblocks};
+        const cuuint64_t cstr[2] = {(cuuint64_t)ldc * 4, cblocks > 1 ? (cuuint64_t)c_cbs * 4 : (cuuint64_t)ldc * 4 * (cuuint64_t)M};
+        const cuuint32_t cbox[3] = {32, 32, 1};   // one box per epilogue warp
+        const cuuint32_t cest[3] = {1, 1, 1};
+        cr = encode_tiled_fn()(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)C, cdim, cstr, cbox, cest,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else if (cr == CUDA_SUCCESS) {
+        cr = CUDA_ERROR_NOT_SUPPORTED;
+      }
       if (cr == CUDA_SUCCESS) {
-        const size_t smem2 = 1024 + bbytes + (size_t)NS * 32 * 1024 + 16 * 1024;
+        const size_t smem2 = 1024 + bbytes + (size_t)NS * 32 * 1024 + 32 * 1024;
         cudaError_t e2 = cudaFuncSetAttribute(k_gemm_nt_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e2 != cudaSuccess) return (int)e2;
         int gx2 = PERT_NUM_SMS / nblk;
         if (gx2 < 1) gx2 = 1;
         if (gx2 > mtiles_all) gx2 = mtiles_all;
-        k_gemm_nt_tma<<<dim3(gx2, nblk), TMA_THREADS, smem2, st>>>(tm, g, NS, (int)row_blk);
+        k_gemm_nt_tma<<<dim3(gx2, nblk), TMA_THREADS, smem2, st>>>(tm, tc, g, NS, (int)row_blk);
         return PERT_OK;
       }
     }
