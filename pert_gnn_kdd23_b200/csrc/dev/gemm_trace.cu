@@ -54,7 +54,7 @@ int main() {
     cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     if (rc) printf("nt fwd rc %d\n", rc);
   }
-  dump("NT forward [N,64]x[256,64]^T -> planes", 5, 8, 4, ms);
+  dump("NT forward [N,64]x[256,64]^T -> planes", 6, 8, 4, ms);
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
     // data gradient: dX[N,64] = dP[N,256 blocked] . Wt[64,256]^T   (B rows = output features, K = 256)
@@ -62,7 +62,7 @@ int main() {
     cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     if (rc) printf("nt dgrad rc %d\n", rc);
   }
-  dump("NT dgrad planes x [64,256]^T -> [N,64]", 5, 14, 4, ms);
+  dump("NT dgrad planes x [64,256]^T -> [N,64]", 6, 14, 4, ms);
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
     int rc = pert_gemm_tn_tc(P, H, H, N * H, X, H, 0, 0, dW, H, cs, N, 4 * H, H, 0);

@@ -1065,35 +1065,46 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       const int t = tid - 128, w = t >> 5, nlo = lane & 7, klo = lane >> 3;
       (void)t;
       const int kqb = (kq + 3) / 4, nblk8 = (BN / 8) * kqb;
-      for (int b0 = w; b0 < nblk8; b0 += 8 * 5) {
-        float4 v[8];
+      // block b = (n8, kb): 8 weight rows x 4 sixteen-byte K pieces; a warp takes blocks w, w+5, w+10, ... and walks
+      // (n8, kb) incrementally (no per-item integer division: this loop is on the MMA warp's critical path)
+      if (warp == 5) TRACE(5, 0, 0);
+      int n8 = w / kqb, kb = w - n8 * kqb;
+      for (int b0 = w; b0 < nblk8; b0 += 16 * 5) {
+        float4 v[16];   // 16 independent 16-byte loads in flight per thread
+        int n8l = n8, kbl = kb;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int b = b0 + u * 5;
-          const int n = (b / kqb) * 8 + nlo, kc = (b % kqb) * 4 + klo;
-          v[u] = (b < nblk8 && kc < kq && n0 + n < g.Nc) ? ldg4(g.B + (size_t)(n0 + n) * g.ldb + kc * 4) : f4zero();
+        for (int u = 0; u < 16; ++u) {
+          const int n = n8l * 8 + nlo, kc = kbl * 4 + klo;
+          v[u] = (b0 + u * 5 < nblk8 && kc < kq && n0 + n < g.Nc) ? ldg4(g.B + (size_t)(n0 + n) * g.ldb + kc * 4)
+                                                                   : f4zero();
+          kbl += 5;
+          while (kbl >= kqb) { kbl -= kqb; ++n8l; }
         }
+        if (warp == 5 && b0 == w) TRACE(5, 0, 1);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int b = b0 + u * 5;
-          const int n = (b / kqb) * 8 + nlo, kc = (b % kqb) * 4 + klo;
-          if (b < nblk8 && kc < kq) {
+        for (int u = 0; u < 16; ++u) {
+          const int kc = kb * 4 + klo;
+          if (b0 + u * 5 < nblk8 && kc < kq) {
             uint4 h, l;
             h.x = tf32_hi(v[u].x); h.y = tf32_hi(v[u].y); h.z = tf32_hi(v[u].z); h.w = tf32_hi(v[u].w);
             l.x = tf32_lo(v[u].x, h.x); l.y = tf32_lo(v[u].y, h.y); l.z = tf32_lo(v[u].z, h.z); l.w = tf32_lo(v[u].w, h.w);
-            const size_t off = (size_t)(n >> 3) * SBO + (n & 7) * 16 + (size_t)kc * LBO;
+            const uint32_t off = (uint32_t)n8 * SBO + (uint32_t)nlo * 16 + (uint32_t)kc * LBO;
             *reinterpret_cast<uint4*>(sBhi + off) = h;
             *reinterpret_cast<uint4*>(sBlo + off) = l;
           }
+          kb += 5;
+          while (kb >= kqb) { kb -= kqb; ++n8; }
         }
       }
     }
+    if (warp == 5) TRACE(5, 0, 2);
     if (tid - 128 < 128) {
       const int c = tid - 128;
       s_bias[c] = (g.bias && c < BN && n0 + c < g.Nc) ? __ldg(g.bias + n0 + c) : 0.f;
     }
     fence_async_smem();
     asm volatile("bar.sync 3, 160;" ::: "memory");
+    if (warp == 5) TRACE(5, 0, 3);
     if (warp == 4) {
       // ================= MMA issuer (one thread) =================
       if (lane == 0) {
