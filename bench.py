@@ -112,6 +112,35 @@ def make_batches(cfg, rank, count):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def _calibrate_threads(make_step, cores):
+    """The eager CPU path is a chain of small ops: more threads than it can use make it slower (128 threads ran ~10x
+    slower than 8-16 on the 128-core box).  Time one small step per candidate thread count and keep the fastest, so
+    that the CPU arm is the reference at its best, not at its most oversubscribed."""
+    cands = sorted({c for c in (cores, cores // 2, cores // 4, 32, 16, 8, 4) if 1 <= c <= cores}, reverse=True)
+    step = make_step()
+    best_t, best = cands[-1], float("inf")
+    torch.set_num_threads(cands[-1])
+    step()                                           # first-touch / allocator warm-up
+    for t in cands:
+        torch.set_num_threads(t)
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if dt < best:
+            best_t, best = t, dt
+    torch.set_num_threads(best_t)
+    return best_t
+
+
+def _sub_batch(cfg, n_graphs, seed_rank=0):
+    """A batch of the first n_graphs graphs of the cfg's synthetic data list (bounded CPU sample)."""
+    from pert_gnn_kdd23_b200.data import Batch
+    from pert_gnn_kdd23_b200.synthetic import make_data_list
+
+    dl = make_data_list(cfg)
+    return Batch.from_data_list(dl[:max(1, min(n_graphs, len(dl)))])
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path.  torch_geometric is not installable here, so this is the
     oracle port (oracle/model_oracle.py: op-for-op torch restatement of PyG 2.4.0 eager) on all host cores."""
@@ -121,14 +150,11 @@ def run_reference(args, rank, world):
     from pert_gnn_kdd23_b200.synthetic import CONFIGS, model_args
     from pert_gnn_kdd23_b200.train import model_inputs
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores_avail = os.cpu_count() or 1
     cfg = args.cfg
     torch.manual_seed(0)
     model = OracleSAGEDeterministic(*model_args(cfg))
     opt = torch.optim.Adam(model.parameters(), lr=3e-4)
-    batches = make_batches(cfg, 0, 2)
-    B = batches[0].num_graphs
 
     def step(b):
         opt.zero_grad()
@@ -138,6 +164,18 @@ def run_reference(args, rank, world):
         opt.step()
         return float(loss)
 
+    small = _sub_batch(cfg, 32)
+    cores = _calibrate_threads(lambda: (lambda: step(small)), cores_avail)
+    full = make_batches(cfg, 0, 1)[0]
+    B_full = full.num_graphs
+    t0 = time.perf_counter()
+    step(full)
+    t_full = time.perf_counter() - t0
+    # bounded sample: the whole --steps/--warmup run has to end within a few minutes on the host cores
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    B = B_full if t_full <= budget else max(16, int(B_full * budget / t_full))
+    batches = [full, make_batches(cfg, 0, 2)[1]] if B == B_full else [_sub_batch(cfg, B), _sub_batch(cfg, B)]
+    B = batches[0].num_graphs
     for i in range(args.warmup):
         step(batches[i % 2])
     t0 = time.perf_counter()
@@ -153,8 +191,10 @@ def run_reference(args, rank, world):
         "config": {"workload": f"cfg{cfg}: {B} DAGs x {c['nodes']} nodes/{c['edges']} edges, {c['hidden']}-dim, "
                                f"num_layers={c['num_layers']}", "global_batch": B},
         "cpu_baseline": {"value": val, "unit": "DAGs/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full train steps (fwd+bwd+Adam) of the {B}-graph batch; torch "
-                                   "restatement of the reference's PyG 2.4.0 eager ops (PyG itself not installable)"},
+                         "sample": f"{args.steps} train steps (fwd+bwd+Adam), each on {B} of the workload's {B_full} "
+                                   f"graphs; {cores} of {cores_avail} host threads (fastest of a calibration sweep); "
+                                   "torch restatement of the reference's PyG 2.4.0 eager ops (PyG itself not "
+                                   "installable)"},
         "e2e": {"value": val, "unit": "DAGs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,13 +207,11 @@ def cpu_baseline(cfg, budget_s=25.0):
     from pert_gnn_kdd23_b200.synthetic import model_args
     from pert_gnn_kdd23_b200.train import model_inputs
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores_avail = os.cpu_count() or 1
     torch.manual_seed(0)
     model = OracleSAGEDeterministic(*model_args(cfg))
     opt = torch.optim.Adam(model.parameters(), lr=3e-4)
-    b = make_batches(cfg, 0, 1)[0]
-    B = b.num_graphs
+    b = _sub_batch(cfg, 32)
 
     def step():
         opt.zero_grad()
@@ -183,6 +221,9 @@ def cpu_baseline(cfg, budget_s=25.0):
         opt.step()
         return float(loss)
 
+    cores = _calibrate_threads(lambda: step, cores_avail)
+    b = make_batches(cfg, 0, 1)[0]
+    B = b.num_graphs
     step()
     times = []
     t_start = time.perf_counter()
@@ -193,6 +234,7 @@ def cpu_baseline(cfg, budget_s=25.0):
     med = statistics.median(times)
     return {"value": B / med, "unit": "DAGs/s", "cores": cores, "kind": "port",
             "sample": f"{len(times)} full train steps (fwd+bwd+Adam) of the same {B}-graph cfg{cfg} batch, median; "
+                      f"{cores} of {cores_avail} host threads (fastest of a calibration sweep); "
                       "oracle = torch restatement of the reference's PyG 2.4.0 eager ops"}
 
 
