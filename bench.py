@@ -460,12 +460,21 @@ def run_b200(args, rank, world, local_rank):
 
     pf_ring = DevicePrefetcher([], dev)       # ONE prefetcher: its 3 device slabs (= 3 graph keys) persist across runs
 
+    from pert_gnn_kdd23_b200.train import AsyncLossReader
+
+    reader = AsyncLossReader(dev)
+
     def run_fused(nsteps):
-        last = None
+        # every step's loss is read back (4 B D2H into pinned memory + event, train.AsyncLossReader); the host
+        # consumes the value of step i-1 after it has enqueued step i, so the GPU never idles on the read-back
+        total = 0.0
         pf_ring.batches = [host_batches[i % N_ROT] for i in range(nsteps)]
         for data in pf_ring:
-            last = float(stepper(data))
-        return last
+            v = reader.push(stepper(data))
+            if v is not None:
+                total += v
+        v = reader.flush()
+        return total + (v if v is not None else 0.0)
 
     run_fused(max(args.warmup, 9))
     barrier()
@@ -539,7 +548,8 @@ def run_b200(args, rank, world, local_rank):
                       "ms_per_step": 1e3 * secs3 / args.steps,
                       "path": "data.DevicePrefetcher (pinned slab -> one H2D per step on a side stream, overlapped with "
                               "the previous step) + train.GraphedTrainStep (graph replay of index build, engine fwd, "
-                              "pinball kernel, engine bwd; eager fused Adam) + float(loss) every step"},
+                              "pinball kernel, engine bwd; eager fused Adam) + the loss of EVERY step read back "
+                              "(train.AsyncLossReader: 4-byte D2H + event behind each step, consumed one step later)"},
         "gpu_launches": launches, "wall_s": t_wall, "clocks": clocks, "final_loss": float(loss),
     }
     print(json.dumps(line), flush=True)

@@ -211,6 +211,38 @@ class GraphedTrainStep:
         return ent
 
 
+class AsyncLossReader:
+    """Per-step loss read-back that does not drain the stream: ``push(loss)`` enqueues a 4-byte D2H copy into a pinned
+    slot + an event right behind the step that produced ``loss`` and returns the value of the PREVIOUS push (whose
+    copy has long finished while the current step was being enqueued); ``flush()`` returns the last one.  The
+    reference reads ``loss.item()`` synchronously every step (pert_gnn.py:248); the running sum is identical, the GPU
+    just never waits for the host between steps."""
+
+    def __init__(self, device):
+        self.buf = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.pending = None
+        self.n = 0
+        self.device = device
+
+    def push(self, loss):
+        slot = self.n & 1
+        self.n += 1
+        self.buf[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.ev[slot].record()
+        prev = self.flush() if self.pending is not None else None
+        self.pending = slot
+        return prev
+
+    def flush(self):
+        if self.pending is None:
+            return None
+        self.ev[self.pending].synchronize()
+        v = float(self.buf[self.pending])
+        self.pending = None
+        return v
+
+
 @torch.no_grad()
 def eval_step(model, data, tau=0.5):
     """Loop body of reference pert_gnn.py:260-289: returns device sums (mae, mape, quantile loss * B)."""
