@@ -29,6 +29,7 @@ extern "C" {
 #define PERT_ERR_BADARG (-1)
 #define PERT_ERR_UNSUPPORTED (-2)
 #define PERT_ERR_RANGE (-3)
+#define PERT_ERR_PEER_TIMEOUT (-4)
 
 /* ABI version (major*1000 + minor). */
 int pert_version(void);
@@ -148,6 +149,22 @@ int pert_pinball_loss(const int64_t* y, const float* yhat, float tau, long long 
 /* torch.optim.Adam step (pert_gnn.py:343,247) over one flat parameter buffer; g is scaled by grad_scale. */
 int pert_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, long long step, float grad_scale, void* stream);
+
+/* ---- gradient all-reduce fused with Adam over NVLink peer memory (csrc/peer.cu) ---------------------------
+ * Data-parallel form of pert_adam_step: every rank publishes its flat gradient in an IPC-shared exchange buffer,
+ * waits for the peers' flags and applies Adam to the rank-ordered sum -- one kernel per step, no NCCL on the step
+ * path.  Setup: pert_peer_alloc on every rank, exchange the 64-byte handles out of band (torch.distributed
+ * all_gather), pert_peer_open the peers'.  `xbufs` is a HOST array of `world` device pointers (index = rank).
+ * `step` = 1, 2, ... must equal the number of calls so far on every rank (the arrival counter is monotonic).
+ * A peer that never arrives makes the kernel write PERT_ERR_PEER_TIMEOUT to `status` after ~3 s instead of hanging. */
+long long pert_peer_exchange_bytes(long long n);
+int pert_peer_alloc(long long bytes, void** ptr, unsigned char* handle64);
+int pert_peer_open(const unsigned char* handle64, void** ptr);
+int pert_peer_close(void* ptr);
+int pert_peer_free(void* ptr);
+int pert_allreduce_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, long long step, float grad_scale, void* const* xbufs, int rank,
+                        int world, int* status, void* stream);
 
 /* ---- whole-model step engine --------------------------------------------------------------------------
  * SAGEDeterministic.forward (model.py:76-114) and its backward as one call each: the same kernels as above,

@@ -43,6 +43,13 @@ SIGNATURES = {
     "pert_relu_bwd": (I, [P, P, LL, P]),
     "pert_pinball_loss": (I, [P, P, F, LL, F, P, P, P]),
     "pert_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, LL, F, P]),
+    # fused all-reduce + Adam over peer memory (csrc/peer.cu)
+    "pert_peer_exchange_bytes": (LL, [LL]),
+    "pert_peer_alloc": (I, [LL, P, P]),
+    "pert_peer_open": (I, [P, P]),
+    "pert_peer_close": (I, [P]),
+    "pert_peer_free": (I, [P]),
+    "pert_allreduce_adam": (I, [P, P, P, P, LL, F, F, F, F, F, LL, F, P, I, I, P, P]),
     # whole-model engine (first argument: const PertModelDesc*, see engine.py)
     "pert_model_workspace_bytes": (LL, [P, LL, LL, LL]),
     "pert_model_packed_bytes": (LL, [P]),
@@ -78,7 +85,8 @@ def check(rc, what):
     if rc != 0:
         if rc > 0:
             raise PertGnnError(f"{what}: CUDA error {rc}")
-        names = {-1: "bad argument", -2: "unsupported width/mode", -3: "index out of range"}
+        names = {-1: "bad argument", -2: "unsupported width/mode", -3: "index out of range",
+                 -4: "a data-parallel peer never arrived (timeout)"}
         raise PertGnnError(f"{what}: {names.get(rc, rc)}")
 
 

@@ -1,0 +1,187 @@
+// Gradient all-reduce fused with Adam over NVLink peer memory: ONE kernel per step on every rank, no NCCL call on
+// the step path (the reference is single-GPU: pert_gnn.py:343,247 `Adam.step`; this is its data-parallel form).
+//
+// Every rank owns an "exchange" allocation (cudaMalloc, exported with cudaIpcGetMemHandle and mapped by the peers):
+//   [ 2 x n_al floats : double-buffered copy of this rank's flat gradient ]
+//   [ PEER_MAX u64    : flags[src] = last step for which rank `src` has published its gradient ]
+//   [ u32             : grid arrival counter of this rank's own kernel ]
+// Step t on rank r:
+//   1. publish: copy the local gradient into buffer t&1 of the own exchange allocation (float4, whole grid);
+//      __threadfence_system; the LAST CTA to arrive (monotonic counter) stores t into flags[r] of EVERY rank
+//      (st.release.sys over NVLink).
+//   2. wait until flags[*] >= t locally (ld.acquire.sys; bounded spin: a lost peer sets `status` instead of hanging).
+//   3. every rank sums the world's buffers in rank order 0..W-1 (bit-identical sums on all ranks, replicas stay in
+//      sync exactly as with NCCL) reading the peers with cache-bypassing loads, and applies torch.optim.Adam's update.
+// No end barrier: buffer t&1 is rewritten at step t+2, which a rank can only reach after every peer has signalled
+// step t+1 -- i.e. after the peer's step-t kernel (the reader of that buffer) has completed in stream order.
+#include "common.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace {
+
+constexpr int PEER_MAX = 8;
+
+struct PeerArgs {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n, n_al;
+  float lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale;
+  float* xbuf[PEER_MAX];
+  int rank, world;
+  unsigned long long step;     // 1, 2, 3, ... (same on every rank)
+  unsigned int arrive_target;  // value of the grid counter that identifies the last CTA of this launch
+  int* status;
+};
+
+__device__ __forceinline__ unsigned long long* flags_of(float* xbuf, long long n_al) {
+  return reinterpret_cast<unsigned long long*>(xbuf + 2 * n_al);
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_allreduce_adam(PeerArgs a) {
+  __shared__ int s_last;
+  const long long n4 = a.n >> 2;                 // n is padded to a multiple of 4 by the caller's layout (n_al)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float* mine = a.xbuf[a.rank] + (a.step & 1ull) * a.n_al;
+  // ---- 1. publish
+  for (long long i = t0; i < n4; i += stride) st4(mine + i * 4, ldg4(a.g + i * 4));
+  for (long long i = (n4 << 2) + t0; i < a.n; i += stride) mine[i] = a.g[i];
+  __threadfence_system();
+  __syncthreads();
+  unsigned long long* my_flags = flags_of(a.xbuf[a.rank], a.n_al);
+  unsigned int* ctr = reinterpret_cast<unsigned int*>(my_flags + PEER_MAX);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ctr, 1u) == a.arrive_target);
+  __syncthreads();
+  if (s_last && threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(flags_of(a.xbuf[threadIdx.x], a.n_al) + a.rank, a.step);
+  }
+  // ---- 2. wait for every rank's gradient of this step
+  if (threadIdx.x < a.world) {
+    const long long t_start = clock64();
+    while (ld_acquire_sys(my_flags + threadIdx.x) < a.step) {
+      if (clock64() - t_start > 6000000000LL) {   // ~3 s: a peer is gone; report instead of hanging the device
+        if (a.status) atomicExch(a.status, PERT_ERR_PEER_TIMEOUT);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 3. reduce in rank order + Adam
+  const long long off = (a.step & 1ull) * a.n_al;
+  for (long long i = t0; i < n4; i += stride) {
+    float4 s = f4zero();
+    for (int r = 0; r < a.world; ++r) s = f4add(s, __ldcv(reinterpret_cast<const float4*>(a.xbuf[r] + off) + i));
+    const float4 pv = ld4(a.p + i * 4), mv = ld4(a.m + i * 4), vv = ld4(a.v + i * 4);
+    float gs[4] = {s.x, s.y, s.z, s.w}, pp[4] = {pv.x, pv.y, pv.z, pv.w}, mm[4] = {mv.x, mv.y, mv.z, mv.w},
+          vs[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gi = gs[k] * a.grad_scale;
+      if (a.wd != 0.f) gi = fmaf(a.wd, pp[k], gi);
+      mm[k] = mm[k] + (1.f - a.b1) * (gi - mm[k]);
+      vs[k] = a.b2 * vs[k] + (1.f - a.b2) * gi * gi;
+      pp[k] = pp[k] - (a.lr / a.bc1) * (mm[k] / (sqrtf(vs[k]) / a.bc2_sqrt + a.eps));
+    }
+    st4(a.p + i * 4, make_float4(pp[0], pp[1], pp[2], pp[3]));
+    st4(a.m + i * 4, make_float4(mm[0], mm[1], mm[2], mm[3]));
+    st4(a.v + i * 4, make_float4(vs[0], vs[1], vs[2], vs[3]));
+  }
+  for (long long i = (n4 << 2) + t0; i < a.n; i += stride) {
+    float s = 0.f;
+    for (int r = 0; r < a.world; ++r) s += __ldcv(a.xbuf[r] + off + i);
+    float gi = s * a.grad_scale;
+    const float pi = a.p[i];
+    if (a.wd != 0.f) gi = fmaf(a.wd, pi, gi);
+    const float mi = a.m[i] + (1.f - a.b1) * (gi - a.m[i]);
+    const float vi = a.b2 * a.v[i] + (1.f - a.b2) * gi * gi;
+    a.m[i] = mi;
+    a.v[i] = vi;
+    a.p[i] = pi - (a.lr / a.bc1) * (mi / (sqrtf(vi) / a.bc2_sqrt + a.eps));
+  }
+}
+
+inline long long al64(long long n) { return (n + 63) / 64 * 64; }
+
+}  // namespace
+
+extern "C" {
+
+long long pert_peer_exchange_bytes(long long n) {
+  if (n < 0) return 0;
+  return 2 * al64(n) * 4 + PEER_MAX * 8 + 64;
+}
+
+// Allocates + zeroes this rank's exchange buffer and returns its 64-byte CUDA IPC handle.
+int pert_peer_alloc(long long bytes, void** ptr, unsigned char* handle64) {
+  if (bytes <= 0 || !ptr || !handle64) return PERT_ERR_BADARG;
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  if ((e = cudaMemset(*ptr, 0, (size_t)bytes)) != cudaSuccess) return (int)e;
+  cudaIpcMemHandle_t h;
+  if ((e = cudaIpcGetMemHandle(&h, *ptr)) != cudaSuccess) return (int)e;
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  memcpy(handle64, &h, 64);
+  return PERT_OK;
+}
+int pert_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!handle64 || !ptr) return PERT_ERR_BADARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? PERT_OK : (int)e;
+}
+int pert_peer_close(void* ptr) {
+  if (!ptr) return PERT_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? PERT_OK : (int)e;
+}
+int pert_peer_free(void* ptr) {
+  if (!ptr) return PERT_OK;
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? PERT_OK : (int)e;
+}
+
+// xbufs: HOST array of `world` device pointers (index = rank; xbufs[rank] = own allocation, the others peer-mapped),
+// every allocation sized pert_peer_exchange_bytes(n).  `step` = 1, 2, ... identical on all ranks and equal to the
+// number of calls so far (it also is Adam's bias-correction step).  All ranks must call once per step.
+int pert_allreduce_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, long long step, float grad_scale, void* const* xbufs, int rank,
+                        int world, int* status, void* stream) {
+  if (!p || !g || !m || !v || n < 0 || step < 1 || !xbufs || world < 1 || world > PEER_MAX || rank < 0 || rank >= world)
+    return PERT_ERR_BADARG;
+  if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return PERT_ERR_BADARG;
+  if (n == 0) return PERT_OK;
+  PeerArgs a;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.n = n; a.n_al = al64(n);
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay;
+  a.bc1 = 1.f - powf(beta1, (float)step);
+  a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  a.grad_scale = grad_scale;
+  for (int r = 0; r < PEER_MAX; ++r) a.xbuf[r] = r < world ? (float*)xbufs[r] : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (!a.xbuf[r]) return PERT_ERR_BADARG;
+  a.rank = rank; a.world = world; a.step = (unsigned long long)step; a.status = status;
+  long long blocks = pert_cdiv(n / 4 + 1, 256);
+  if (blocks > PERT_NUM_SMS) blocks = PERT_NUM_SMS;   // all CTAs co-resident: they wait on each other's arrival
+  if (blocks < 1) blocks = 1;
+  // the grid counter is monotonic: after `step` launches of `blocks` CTAs the last arrival reads step*blocks - 1
+  a.arrive_target = (unsigned int)((unsigned long long)step * (unsigned long long)blocks - 1ull);
+  k_allreduce_adam<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  PERT_LAUNCH_CHECK();
+  return PERT_OK;
+}
+
+}  // extern "C"

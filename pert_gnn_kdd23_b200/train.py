@@ -71,6 +71,79 @@ class FusedAdam:
         ops.LAUNCHES["n"] += 1
 
 
+class PeerAdam(FusedAdam):
+    """FusedAdam whose step also averages the gradient over the data-parallel ranks: ONE kernel per step
+    (csrc/peer.cu) that publishes the flat gradient in a CUDA-IPC exchange buffer, waits for the peers' flags over
+    NVLink and applies Adam to the rank-ordered sum -- no NCCL call on the step path.  ``DataParallel`` skips its own
+    all-reduce when the optimiser is a PeerAdam.  Needs one process per GPU on one node (``torch.distributed``
+    initialised, used once to exchange the 64-byte IPC handles); with a single rank it degenerates to FusedAdam."""
+
+    fused_allreduce = True
+
+    def __init__(self, flat: FlatParams, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None):
+        super().__init__(flat, lr, betas, eps, weight_decay)
+        import ctypes
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._own = None
+        self._peers = []
+        self.status = torch.zeros(1, dtype=torch.int32, device=flat.flat.device)
+        if self.world == 1:
+            return
+        if self.world > 8:
+            raise _lib.PertGnnError("PeerAdam supports up to 8 ranks on one node")
+        L = _lib.lib()
+        nbytes = L.pert_peer_exchange_bytes(flat.numel)
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(L.pert_peer_alloc(nbytes, ctypes.byref(own), handle), "pert_peer_alloc")
+        self._own = own.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=flat.flat.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(self._own)
+                continue
+            hb = (ctypes.c_ubyte * 64)(*gathered[r].cpu().tolist())
+            pp = ctypes.c_void_p()
+            _lib.check(L.pert_peer_open(hb, ctypes.byref(pp)), "pert_peer_open")
+            self._peers.append(pp.value)
+            ptrs.append(pp.value)
+        self._xbufs = (ctypes.c_void_p * self.world)(*ptrs)
+        dist.barrier(group=group)      # every rank has mapped every buffer before the first step touches them
+
+    def step(self, grad_scale=1.0):
+        if self.world == 1:
+            return super().step(grad_scale)
+        self.t += 1
+        _lib.call("pert_allreduce_adam", _lib.ptr(self.fp.flat), _lib.ptr(self.fp.grad), _lib.ptr(self.m),
+                  _lib.ptr(self.v), self.fp.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t,
+                  float(grad_scale), self._xbufs, self.rank, self.world, _lib.ptr(self.status), _lib.stream())
+        ops.LAUNCHES["n"] += 1
+
+    def check(self):
+        """Synchronising check of the device status word (a peer that never arrived sets PERT_ERR_PEER_TIMEOUT)."""
+        code = int(self.status.item())
+        if code != 0:
+            _lib.check(code, "pert_allreduce_adam")
+
+    def close(self):
+        L = _lib.lib()
+        for pp in self._peers:
+            L.pert_peer_close(pp)
+        self._peers = []
+        if self._own:
+            if dist.is_initialized() and self.world > 1:
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)     # nobody still reads this buffer
+            L.pert_peer_free(self._own)
+            self._own = None
+
+
 class DataParallel:
     """One process per GPU; each rank owns a shard of the graphs; gradients are averaged with a single
     all-reduce of the flat gradient buffer (NCCL over NVLink on the box, gloo in the CPU tests).
@@ -81,8 +154,10 @@ class DataParallel:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
-    def all_reduce_grads(self):
-        if self.world > 1:
+    def all_reduce_grads(self, optimizer=None):
+        """Sums the flat gradient over the ranks (unless ``optimizer`` does it itself, see PeerAdam) and returns the
+        scale that turns the sum into the mean."""
+        if self.world > 1 and not getattr(optimizer, "fused_allreduce", False):
             dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.group)
         return 1.0 / self.world
 
@@ -95,7 +170,7 @@ def train_step(model, optimizer, data, tau=0.5, dp: DataParallel | None = None):
     loss = torch_quantile_loss(data.y.float(), global_pred.flatten(), tau)
     loss.backward()
     if isinstance(optimizer, FusedAdam):
-        scale = dp.all_reduce_grads() if dp is not None else 1.0
+        scale = dp.all_reduce_grads(optimizer) if dp is not None else 1.0
         optimizer.step(grad_scale=scale)
     else:
         if dp is not None:
@@ -138,7 +213,7 @@ def fused_train_step(model, optimizer: FusedAdam, data, tau=0.5, dp: DataParalle
     Returns the device loss tensor [1]."""
     loss, _ = _fused_fwd_bwd(model, optimizer, data, tau, index, probe)
     with torch.no_grad():
-        scale = dp.all_reduce_grads() if dp is not None else 1.0
+        scale = dp.all_reduce_grads(optimizer) if dp is not None else 1.0
         optimizer.step(grad_scale=scale)
     return loss
 
@@ -168,7 +243,7 @@ class GraphedTrainStep:
 
     def _finish(self, loss):
         with torch.no_grad():
-            scale = self.dp.all_reduce_grads() if self.dp is not None else 1.0
+            scale = self.dp.all_reduce_grads(self.opt) if self.dp is not None else 1.0
             self.opt.step(grad_scale=scale)
         return loss
 

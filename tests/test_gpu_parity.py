@@ -418,6 +418,22 @@ def test_prefetch_graph_async_loss_pipeline_matches_eager():
         assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (i, a, b)
 
 
+def test_peer_adam_two_gpus():
+    """Fused all-reduce + Adam over peer memory == NCCL all-reduce + FusedAdam (needs >= 2 GPUs; tests/dist_peer_adam.py
+    under torchrun, one rank per GPU)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(here, "dist_peer_adam.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert "PEER_ADAM_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 def test_model_cfg1_eval():
     _model_parity(1, None, train=False)
 
