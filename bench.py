@@ -43,6 +43,9 @@ def _peaks():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in a background thread (a query takes well
+    under a millisecond, so even a 30 ms region gets samples); falls back to an `nvidia-smi -lms` child process."""
+
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -51,8 +54,64 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         self.idx = gpu_index
+        self.nv = None
+        self._thread = None
+        self._stop = False
+        self._sm, self._mx, self._reasons = [], [], set()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch as _t
+
+                uuid = str(_t.cuda.get_device_properties(gpu_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = (pynvml, h)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv, h = self.nv
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        while not self._stop:
+            try:
+                self._sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if mx is not None:
+                    self._mx.append(float(mx))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in bits.items():
+                    if r & bit:
+                        self._reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.003)
+
+    def _stop_nvml(self):
+        self._stop = True
+        self._thread.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self._reasons)}
+        if self._sm:
+            out["sm_mhz"] = statistics.median(self._sm)
+            out["sm_max_mhz"] = max(self._mx) if self._mx else None
+            out["samples"] = len(self._sm)
+            out["source"] = "nvml"
+        return out
 
     def start(self):
+        if self.nv is not None:
+            import threading
+
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
@@ -61,6 +120,8 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self._thread is not None:
+            return self._stop_nvml()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
