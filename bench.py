@@ -6,15 +6,26 @@
 
 Workload (BASELINE.json configs[1]): Alibaba-trace-shaped synthetic batch, 256 DAGs x 200 nodes / 600 edges,
 64-dim, num_layers=3 (3 TransformerConv + 2 BN), fp32, per GPU (weak scaling for N > 1: every rank trains on
-its own 256-graph shard, ONE NCCL all-reduce of the flat gradient buffer per step).
+its own 256-graph shard; the gradient mean over the ranks is fused with Adam in one kernel over NVLink peer memory,
+train.PeerAdam, with one NCCL all-reduce of the flat gradient as the fallback).
 
-JSON line keys beyond the base contract:
-  roofline      dominant kernel of the step, algorithmic bytes / CUDA-event time inside the timed region
-  scatter_max   the BASELINE metric kernel ([E,64] -> [N,64] segment-max) timed alone, L2 flushed between launches
-  kernels       per-kernel in-step times (ms per step) for the instrumented launches
-  cpu_baseline  the oracle (torch restatement of the reference's PyG 2.4.0 ops) timed on this box's host cores
-  e2e           the reference's own loop body (pert_gnn.py:219-250) around the drop-in model: pinned host batch ->
-                .to(device) -> zero_grad -> forward -> pinball loss -> backward -> Adam.step -> float(loss)
+Arms and JSON keys beyond the base contract:
+  value         train.GraphedTrainStep on 8 rotating RESIDENT batches: index build + forward + pinball loss +
+                backward replayed from one CUDA graph per batch buffer, then the (fused) Adam  [PERT_BENCH_GRAPH=0:
+                eager train.fused_train_step]; CUDA events around exactly K steps, max over ranks
+  e2e           the same step fed from pinned HOST batches: data.DevicePrefetcher (one H2D copy per step on a side
+                stream, one step ahead) + graph replay + Adam + every step's loss read back (train.AsyncLossReader)
+  e2e_dropin    the reference's own loop body (pert_gnn.py:219-250) around the drop-in model, unchanged: pinned host
+                batch -> .to(device) -> zero_grad -> model.forward -> pinball loss -> backward -> torch Adam -> item()
+  kernels       per-kernel in-step times: CUDA events recorded by the engine (PertProbe) around one kernel family per
+                step, in eagerly issued train steps run right after the timed region
+  roofline      the kernel family with the largest share of the step: algorithmic bytes / its in-step time against
+                the measured HBM peak (MEASURED_PEAKS.json); traffic = DRAM bytes from the committed ncu capture
+  scatter_max   the BASELINE metric kernel ([E,64] -> [N,64] segment-max): trains of launches over rotating buffers
+                larger than L2 (and the single-launch-after-flush time)
+  cpu_baseline  the oracle (torch restatement of the reference's PyG 2.4.0 ops) on this box's host cores, thread
+                count chosen by a calibration sweep
+  clocks        NVML SM clock / throttle reasons sampled inside the timed region
 """
 import argparse
 import json
