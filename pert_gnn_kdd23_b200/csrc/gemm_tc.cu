@@ -15,14 +15,20 @@
 //       K-adjacent core matrices, SBO between N-adjacent), split hi/lo.
 //   D:  fp32 accumulator in TMEM; epilogue tcgen05.ld (lane = row).
 //
-// Both kernels are persistent, one CTA per SM, warp-specialised with mbarrier pipelines (2 stages):
+// Two generations of kernels live in this file (all persistent, one CTA per SM, warp-specialised, mbarrier pipelines):
+//   k_gemm_nt_tma / k_gemm_tn_tma (further down) -- the production path: a loader warp moves the operands with TMA
+//       (2-D tensor-map copies with 128-byte swizzle for the forward / data-gradient A tiles, large 1-D bulk copies
+//       for the weight-gradient chunks) into a multi-stage shared-memory ring, tiles / chunks are handed out by
+//       self-resetting ticket counters, and the forward epilogue leaves through TMA tensor stores.
+//   k_gemm_nt_tc / k_gemm_tn_tc -- the first generation (converter warps fetch their operands with LDG); still the
+//       path for operands the TMA kernels do not accept (strided rows) and for PERT_GEMM_TMA=0:
 //   NT (forward / data gradient, C[M,Nc] = A[M,K] . B[Nc,K]^T (+bias)):
 //       warps 0-3 load+split A chunks into TMEM stage s | warp 4 issues the MMAs (one thread) | warps 5-8 drain the
 //       accumulator stage (TMEM -> registers -> +bias -> global) while the next tile is being multiplied.
 //   TN (weight gradient, C[Mc,Nc] += A[R,Mc]^T . B[R,Nc], split over R, REDG.128 accumulation):
 //       warps 0-3 load A columns (coalesced across lanes) into TMEM | warps 4-7 transpose the B chunk into the K-major
 //       smem layout (bank-conflict-free 8x4 patches) | warp 8 issues the MMAs.
-// These GEMMs are HBM-bound (K <= 256): A read once, C written once; the tensor cores only have to keep up.
+// These GEMMs are memory-bound by shape (K <= 256): A read once, C written once; measured bounds in DESIGN.md section 3.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
