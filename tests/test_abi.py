@@ -41,6 +41,23 @@ def test_version_and_host_side_validation():
                               None, None) == -1
     assert L.pert_segment_reduce_fwd(None, None, None, None, 5, 0, 1, None) == -1
     assert L.pert_adam_step(None, None, None, None, 10, 1e-3, .9, .999, 1e-8, 0., 1, 1., None) == -1
+    assert L.pert_allreduce_adam(None, None, None, None, 10, 1e-3, .9, .999, 1e-8, 0., 1, 1., None, 0, 2, None,
+                                 None) == -1
+    assert L.pert_peer_exchange_bytes(1000) >= 2 * 1000 * 4 and L.pert_peer_exchange_bytes(-1) == 0
+    assert L.pert_peer_open(None, None) == -1 and L.pert_peer_close(None) == 0 and L.pert_peer_free(None) == 0
+
+
+def test_header_is_plain_c():
+    """The boundary is a C header: it must compile as C99 without any CUDA / C++ / torch include."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
 
 
 def test_product_path_refuses_cpu_tensors():
