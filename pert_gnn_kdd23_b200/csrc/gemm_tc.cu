@@ -1288,11 +1288,20 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
     return PERT_ERR_UNSUPPORTED;
   if (a_cb < K && a_cb % KC) return PERT_ERR_UNSUPPORTED;   // a K-chunk must not straddle two column blocks
   // N block: <= 128 accumulator columns per CTA, Nc split into equal multiples of 16
+  // (the whole [BN, K] weight block is resident in shared memory, hi and lo: for a deep K -- the data gradient at
+  // H = 128 has K = 512 -- the block is narrowed until it fits, at the price of re-reading A once per N block)
   int nblk = (Nc + 127) / 128;
-  while (Nc % nblk || (Nc / nblk) % 16) ++nblk;
-  const int BN = Nc / nblk;
-  const size_t smem = (size_t)BN * K * 4 * 2 + 32 * 1024 + 16 * 1024;   // B hi/lo + A staging + D staging
-  if (smem > 227 * 1024) return PERT_ERR_UNSUPPORTED;
+  size_t smem = 0;
+  int BN = 0;
+  for (;; ++nblk) {
+    if (nblk > Nc / 16) return PERT_ERR_UNSUPPORTED;
+    if (Nc % nblk || (Nc / nblk) % 16) continue;
+    BN = Nc / nblk;
+    smem = (size_t)BN * K * 4 * 2 + 32 * 1024 + 16 * 1024;   // B hi/lo + A staging + D staging
+    // the TMA kernel needs 1 KB alignment slack + 2 ring stages + 2 x 16 KB store slabs next to B
+    const size_t need = tma_enabled() ? (size_t)BN * K * 8 + 1024 + 1024 + 2 * 32 * 1024 + 32 * 1024 : smem;
+    if (need <= 226 * 1024) break;
+  }
   NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu};
   const int mtiles_all = (int)((M + 127) / 128);
   if (tma_enabled() && nblk <= 8 && encode_tiled_fn()) {

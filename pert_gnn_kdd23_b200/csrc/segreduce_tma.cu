@@ -2,7 +2,7 @@
 // are already in CSR (target-sorted) order: out[i,:] = max|sum over rows [rowptr[i], rowptr[i+1]) of msg.
 //
 // The rows of consecutive segments are contiguous, so a tile of TN consecutive segments is ONE contiguous byte range.
-// Persistent CTAs (one per SM) run a 4-stage (4 x 48 KB; same-box A/B: 3x64 0.60, 4x48 0.62, 5x40 0.60 of peak) mbarrier pipeline: a producer warp issues one TMA bulk copy
+// Persistent CTAs (one per SM) run a 3- or 4-stage (see Ring) mbarrier pipeline: a producer warp issues one TMA bulk copy
 // (cp.async.bulk, complete_tx on the stage's mbarrier) per tile -- no per-thread loads, no registers, tens of KB
 // in flight per SM independent of occupancy -- and 8 consumer warps reduce the staged rows from shared memory with
 // 16-byte accesses and write the [TN,H] result with streaming stores.  Segment boundaries travel with the tile
@@ -15,8 +15,14 @@
 namespace {
 
 constexpr int TN = 32;        // segments (nodes) per tile
-constexpr int STAGES = 4;
-constexpr int STAGE_BYTES = 48 * 1024;
+// ring geometry by row width: a tile of 32 segments at ~3 rows each is 12 / 24 / 48 KB for H = 32 / 64 / 128; the stage
+// must hold a tile with headroom (an oversized tile falls back to global loads), and 4 stages beat 3 when they fit
+// (same-box A/B at cfg2, H = 64: 3x64 KB 0.60, 4x48 KB 0.62, 5x40 KB 0.60 of the measured HBM peak)
+template <int LPR>
+struct Ring {
+  static constexpr int STAGES = (LPR >= 32) ? 3 : 4;
+  static constexpr int STAGE_BYTES = (LPR >= 32) ? 72 * 1024 : 48 * 1024;
+};
 constexpr int CONS_WARPS = 8;
 constexpr int THREADS = (CONS_WARPS + 1) * 32;
 
@@ -58,6 +64,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_segreduce_stream(const float* __
                                                                  const int* __restrict__ rowptr,
                                                                  float* __restrict__ out, int N, int ntiles) {
   constexpr int H = 4 * LPR;
+  constexpr int STAGES = Ring<LPR>::STAGES;
+  constexpr int STAGE_BYTES = Ring<LPR>::STAGE_BYTES;
   constexpr int CAP = STAGE_BYTES / (H * 4);
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_segreduce_stream(const float* __
 template <int LPR>
 int launch(const float* msg, const int* rowptr, float* out, long long N, int op, cudaStream_t st) {
   const int ntiles = (int)((N + TN - 1) / TN);
-  const size_t smem = (size_t)STAGES * STAGE_BYTES;
+  const size_t smem = (size_t)Ring<LPR>::STAGES * Ring<LPR>::STAGE_BYTES;
   int grid = PERT_NUM_SMS < ntiles ? PERT_NUM_SMS : ntiles;
   cudaError_t e;
   if (op == 1) {
