@@ -9,6 +9,7 @@
 // and an unpack kernel scatters the packed gradients back (+=) into the flat gradient buffer.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -464,6 +465,46 @@ void append_layer_grad_segs(SegList& S, const PertModelDesc* d, const Ws& w, flo
   }
 }
 
+// Auxiliary stream for the few places where independent small kernels can run beside the main chain (input prologue
+// next to the parameter pack + edge tables; edge-table gradients next to the conv-0 GEMMs).  Fork / join with events,
+// so the dependencies also hold inside a CUDA-graph capture.  Created on first (eager) use per device;
+// PERT_ENGINE_FORK=0 keeps everything on the caller's stream.
+struct AuxStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int state = 0;   // 0 untried, 1 ready, -1 unavailable
+};
+AuxStream* aux_stream() {
+  static AuxStream aux[64];
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("PERT_ENGINE_FORK");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  AuxStream& a = aux[dev];
+  if (a.state == 0) {
+    a.state = -1;
+    if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess)
+      a.state = 1;
+    else
+      (void)cudaGetLastError();
+  }
+  return a.state == 1 ? &a : nullptr;
+}
+bool aux_fork(AuxStream* a, cudaStream_t st) {
+  return a && cudaEventRecord(a->fork, st) == cudaSuccess && cudaStreamWaitEvent(a->s, a->fork, 0) == cudaSuccess;
+}
+int aux_join(AuxStream* a, cudaStream_t st) {
+  cudaError_t e = cudaEventRecord(a->join, a->s);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, a->join, 0);
+  return e == cudaSuccess ? PERT_OK : (int)e;
+}
+
 int check_desc(const PertModelDesc* d) {
   if (!d) return PERT_ERR_BADARG;
   if (d->n_convs < 2 || d->n_convs > PERT_MAX_CONVS || d->n_cat < 1 || d->n_cat > PERT_MAX_CAT) return PERT_ERR_BADARG;
@@ -519,6 +560,10 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
   if (workspace_bytes < w.total * 4) return PERT_ERR_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int H = d->H, L = d->n_convs;
+  // the input prologue (2.) does not depend on the packed parameters: it runs on the auxiliary stream beside 1.
+  AuxStream* ax = aux_stream();
+  const bool forked = aux_fork(ax, st);
+  cudaStream_t s2 = forked ? ax->s : st;
   // 1. pack parameters (one launch per layer) and build the edge tables of all layers (one grouped launch each <=6)
   {
     SegList S;
@@ -547,8 +592,9 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
   // 2. prologue: X0 = [sum_i cat_emb_i[cat_X[:,i]] | x | 0]
   for (int i = 0; i < d->n_cat; ++i)
     TRY(pert_embedding_fwd(params + d->off_cat[i], d->cat_rows[i], cat_X + i, d->n_cat, w.x[0], d->k0, N, H, i > 0,
-                           status, st));
-  TRY(pert_copy_cols(x, d->F, w.x[0], d->k0, H, N, st));
+                           status, s2));
+  TRY(pert_copy_cols(x, d->F, w.x[0], d->k0, H, N, s2));
+  if (forked) TRY(aux_join(ax, st));
   // 3. conv stack
   for (int l = 0; l < L; ++l) {
     const int K = k_of(d, l);
@@ -623,6 +669,29 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
   float* dskip = dv + N * H;
   TRY(pert_pool_bwd(B > 0 ? w.dpool : nullptr, d_local, w.out[L - 1], H, probs, pnn, batch, params + d->off_local_w,
                     dskip, H, grads + d->off_local_w, grads + d->off_local_b, N, B, H, st));
+  // ---- edge tables: dWeA = dT_if^T . if_emb ; d if_emb += dT_if . WeA   (and the rpc halves), all layers grouped.
+  // They depend only on the conv backward passes (dT tables), so they run on the auxiliary stream beside the conv-0
+  // GEMMs and the embedding scatters; the unpack at the end waits for them.
+  auto table_grads = [&](cudaStream_t ts) {
+    SmallGemmBatch gb;
+    gb.count = 0;
+    for (int l = 0; l < L; ++l) {
+      int ks_if = d->n_if >= 512 ? 8 : 1, ks_rpc = 1;
+      gb.p[gb.count++] = sg(w.dt_if[l], 1, H, params + d->off_if, H, 1, nullptr, w.dweA[l], H, H, H, d->n_if, 0, 1, ks_if);
+      gb.p[gb.count++] = sg(w.dt_rpc[l], 1, H, params + d->off_rpc, H, 1, nullptr, w.dweB[l], H, H, H, d->n_rpc, 0, 1, ks_rpc);
+      // every layer adds into the same embedding-gradient rows: atomic accumulation, all layers in one launch
+      gb.p[gb.count] = sg(w.dt_if[l], H, 1, w.weA[l], H, 1, nullptr, grads + d->off_if, H, d->n_if, H, H, 0, 1);
+      gb.p[gb.count++].atomic = 1;
+      gb.p[gb.count] = sg(w.dt_rpc[l], H, 1, w.weB[l], H, 1, nullptr, grads + d->off_rpc, H, d->n_rpc, H, H, 0, 1);
+      gb.p[gb.count++].atomic = 1;
+      if (gb.count + 4 > SG_MAX || l == 0 + L - 1) {
+        launch_small(gb, ts);
+        gb.count = 0;
+      }
+    }
+  };
+  AuxStream* ax = aux_stream();
+  bool forked = false;
   for (int l = L - 1; l >= 0; --l) {
     const int K = k_of(d, l);
     float* pl = w.planes[l];
@@ -631,6 +700,10 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
                        csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.dt_if[l], w.dt_rpc[l],
                        d->n_rpc, N, E, B, H, st));
     PROBE_STOP(2, l);
+    if (l == 0) {                       // every dT table is complete now
+      forked = aux_fork(ax, st);
+      if (forked) table_grads(ax->s);
+    }
     // weight / bias gradients of the fused node linear (packed), data gradient
     PROBE_START(4, l);
     TRY(pert_gemm_tn(w.dplanes, H, H, N * (long long)H, w.x[l], K, 0, 0, w.dw4[l], K, w.db4[l], N, 4 * H, K, st));
@@ -650,25 +723,8 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
   // ---- categorical embedding gradients from dX0[:, 0:H]
   for (int i = 0; i < d->n_cat; ++i)
     TRY(pert_embedding_bwd(w.dx, d->k0, cat_X + i, d->n_cat, grads + d->off_cat[i], d->cat_rows[i], N, H, st));
-  // ---- edge tables: dWeA = dT_if^T . if_emb ; d if_emb += dT_if . WeA   (and the rpc halves), all layers grouped
-  {
-    SmallGemmBatch gb;
-    gb.count = 0;
-    for (int l = 0; l < L; ++l) {
-      int ks_if = d->n_if >= 512 ? 8 : 1, ks_rpc = 1;
-      gb.p[gb.count++] = sg(w.dt_if[l], 1, H, params + d->off_if, H, 1, nullptr, w.dweA[l], H, H, H, d->n_if, 0, 1, ks_if);
-      gb.p[gb.count++] = sg(w.dt_rpc[l], 1, H, params + d->off_rpc, H, 1, nullptr, w.dweB[l], H, H, H, d->n_rpc, 0, 1, ks_rpc);
-      // every layer adds into the same embedding-gradient rows: atomic accumulation, all layers in one launch
-      gb.p[gb.count] = sg(w.dt_if[l], H, 1, w.weA[l], H, 1, nullptr, grads + d->off_if, H, d->n_if, H, H, 0, 1);
-      gb.p[gb.count++].atomic = 1;
-      gb.p[gb.count] = sg(w.dt_rpc[l], H, 1, w.weB[l], H, 1, nullptr, grads + d->off_rpc, H, d->n_rpc, H, H, 0, 1);
-      gb.p[gb.count++].atomic = 1;
-      if (gb.count + 4 > SG_MAX || l == 0 + L - 1) {
-        launch_small(gb, st);
-        gb.count = 0;
-      }
-    }
-  }
+  if (forked) TRY(aux_join(ax, st));
+  else table_grads(st);
   {
     SegList S;
     S.count = 0;
