@@ -216,8 +216,11 @@ int pert_model_forward(const PertModelDesc* desc, const float* params, float* bn
                        const float* pnn, const int64_t* batch, long long N, long long E, long long B,
                        const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, void* workspace,
                        long long workspace_bytes, int training, float* global_pred, float* local_pred, int* status,
-                       const PertProbe* probe, void* stream);
-/* Must follow pert_model_forward on the same workspace.  d_global [B], d_local [N] or NULL. */
+                       const PertProbe* probe, void* index_ready, void* stream);
+/* index_ready: optional cudaEvent_t recorded (on another stream) after the graph index was built: the forward waits
+ * for it only right before the first attention kernel, so the index build overlaps the parameter pack, the input
+ * prologue and the first GEMM.  NULL = the index is already complete in `stream` order.
+ * Must follow pert_model_forward on the same workspace.  d_global [B], d_local [N] or NULL. */
 int pert_model_backward(const PertModelDesc* desc, const float* params, float* grads, const int64_t* cat_X,
                         const int64_t* entry_id, const float* probs, const float* pnn, const int64_t* batch,
                         long long N, long long E, long long B, const int* rowptr, const int* csr_src,

@@ -550,7 +550,7 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
                        const float* pnn, const int64_t* batch, long long N, long long E, long long B,
                        const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, void* workspace,
                        long long workspace_bytes, int training, float* global_pred, float* local_pred, int* status,
-                       const PertProbe* probe, void* stream) {
+                       const PertProbe* probe, void* index_ready, void* stream) {
   TRY(check_desc(d));
   if (!params || !x || !cat_X || !entry_id || !probs || !pnn || !batch || !rowptr || !workspace || !global_pred)
     return PERT_ERR_BADARG;
@@ -602,6 +602,10 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
     TRY(pert_gemm_nt(w.x[l], K, 0, 0, w.w4[l], K, w.b4[l], w.planes[l], H, H, N * (long long)H, N, 4 * H, K, 0, 0, st));
     PROBE_STOP(3, l);
     float* pl = w.planes[l];
+    if (l == 0 && index_ready) {      // the graph index was built on another stream: first use is here
+      cudaError_t we = cudaStreamWaitEvent(st, (cudaEvent_t)index_ready, 0);
+      if (we != cudaSuccess) return (int)we;
+    }
     PROBE_START(1, l);
     TRY(pert_tconv_fwd(pl, pl + N * H, pl + 2 * N * H, pl + 3 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, w.t_if[l],
                        w.t_rpc[l], w.out[l], H, w.alpha[l], d->n_rpc, N, E, B, H, st));
@@ -720,11 +724,13 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
                       grads + d->off_bn_b[l - 1], w.sums, N, H, st));
     }
   }
-  // ---- categorical embedding gradients from dX0[:, 0:H]
-  for (int i = 0; i < d->n_cat; ++i)
-    TRY(pert_embedding_bwd(w.dx, d->k0, cat_X + i, d->n_cat, grads + d->off_cat[i], d->cat_rows[i], N, H, st));
   if (forked) TRY(aux_join(ax, st));
   else table_grads(st);
+  // ---- categorical embedding gradients from dX0[:, 0:H] (auxiliary stream) beside the gradient unpack (main stream)
+  const bool forked2 = aux_fork(ax, st);
+  for (int i = 0; i < d->n_cat; ++i)
+    TRY(pert_embedding_bwd(w.dx, d->k0, cat_X + i, d->n_cat, grads + d->off_cat[i], d->cat_rows[i], N, H,
+                           forked2 ? ax->s : st));
   {
     SegList S;
     S.count = 0;
@@ -736,6 +742,7 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
       }
     }
   }
+  if (forked2) TRY(aux_join(ax, st));
   PERT_LAUNCH_CHECK();
   return PERT_OK;
 }

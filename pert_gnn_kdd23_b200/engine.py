@@ -171,7 +171,8 @@ class Engine:
         L = self.n_convs
         return 1 + 1 + 4 * L + 2 * (L - 1) + self.desc.n_cat + (L + 2) // 3 + self._pack_launches()
 
-    def forward(self, x, cat_X, entry_id, probs, pnn, batch, index: GraphIndex, training, probe=None):
+    def forward(self, x, cat_X, entry_id, probs, pnn, batch, index: GraphIndex, training, probe=None,
+                index_ready=None):
         """-> (global_pred [B,1], local_pred [N,1]); keeps what backward needs in the workspace."""
         N, E, B = x.size(0), index.E, entry_id.numel()
         ws = self._workspace(N, E, B)
@@ -189,7 +190,8 @@ class Engine:
             C.byref(self.desc), p(self.fp.flat), p(self.bn_running), p(self.bn_nbt), p(x), p(cat_X), p(entry_id),
             p(probs), p(pnn), p(batch), N, E, B, p(index.rowptr), p(index.csr_src), p(index.csr_if), p(index.csr_rpc),
             p(ws), ws.numel() * 4, int(training), p(gpred), p(lpred), p(index.status),
-            C.byref(probe) if probe is not None else None, _lib.stream())
+            C.byref(probe) if probe is not None else None,
+            C.c_void_p(index_ready.cuda_event) if index_ready is not None else None, _lib.stream())
         _lib.check(rc, "pert_model_forward")
         ops.LAUNCHES["n"] += self.launches_forward()
         self._saved = (x, cat_X, entry_id, probs, pnn, batch, index, bool(training), N, E, B)

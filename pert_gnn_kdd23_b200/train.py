@@ -181,6 +181,17 @@ def train_step(model, optimizer, data, tau=0.5, dp: DataParallel | None = None):
     return loss
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return st
+
+
 def _fused_fwd_bwd(model, optimizer: FusedAdam, data, tau, index, probe, use_index_cache=True):
     """Device work of one step up to the gradients: (index build) -> zero grads -> engine forward -> pinball loss +
     its gradient -> engine backward into the flat gradient buffer.  Returns (loss [1], index)."""
@@ -189,13 +200,25 @@ def _fused_fwd_bwd(model, optimizer: FusedAdam, data, tau, index, probe, use_ind
     eng = model.engine(optimizer.fp) if (model._engine is None or model._engine.fp is not optimizer.fp) \
         else model._engine
     x, cat_X, edge_index, edge_attr, pnn, probs, entry_id, batch = model_inputs(data)
+    index_ready = None
     if index is None:
         n_if, n_rpc = model.interface_embeds.num_embeddings, model.rpctype_embeds.num_embeddings
-        index = cached_index(edge_index, x.size(0), edge_attr, n_if, n_rpc) if use_index_cache \
-            else build_index(edge_index, x.size(0), edge_attr, n_if, n_rpc, check=False)
+        if use_index_cache:
+            index = cached_index(edge_index, x.size(0), edge_attr, n_if, n_rpc)
+        else:
+            # build the index on a side stream: the forward only waits for it right before the first attention
+            # kernel, so it overlaps the parameter pack, the input prologue and the first GEMM
+            main = torch.cuda.current_stream(x.device)
+            side = _side_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                index = build_index(edge_index, x.size(0), edge_attr, n_if, n_rpc, check=False)
+                index_ready = torch.cuda.Event()
+                index_ready.record(side)
     optimizer.zero_grad()
     with torch.no_grad():
-        gpred, _ = eng.forward(x, cat_X, entry_id, probs, pnn, batch, index, model.training, probe=probe)
+        gpred, _ = eng.forward(x, cat_X, entry_id, probs, pnn, batch, index, model.training, probe=probe,
+                               index_ready=index_ready)
         B = gpred.size(0)
         loss = torch.empty(1, device=gpred.device, dtype=torch.float32)
         dy = torch.empty(B, device=gpred.device, dtype=torch.float32)
