@@ -95,24 +95,46 @@ class PeerAdam(FusedAdam):
         if self.world > 8:
             raise _lib.PertGnnError("PeerAdam supports up to 8 ranks on one node")
         L = _lib.lib()
-        nbytes = L.pert_peer_exchange_bytes(flat.numel)
-        own = ctypes.c_void_p()
+        dev = flat.flat.device
+
+        def all_ok(ok):
+            # every rank takes part in every collective of the setup, whatever happened locally: a rank that failed
+            # must not leave the others waiting in a different collective
+            t = torch.tensor([1.0 if ok else 0.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return float(t) > 0.0
+
+        err = None
         handle = (ctypes.c_ubyte * 64)()
-        _lib.check(L.pert_peer_alloc(nbytes, ctypes.byref(own), handle), "pert_peer_alloc")
-        self._own = own.value
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device=flat.flat.device)
+        try:
+            nbytes = L.pert_peer_exchange_bytes(flat.numel)
+            own = ctypes.c_void_p()
+            _lib.check(L.pert_peer_alloc(nbytes, ctypes.byref(own), handle), "pert_peer_alloc")
+            self._own = own.value
+        except Exception as e:  # noqa: BLE001
+            err = e
+        if not all_ok(err is None):
+            self.close(collective=False)
+            raise _lib.PertGnnError(f"PeerAdam setup failed on some rank (local error: {err!r})")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         gathered = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(gathered, mine, group=group)
         ptrs = []
-        for r in range(self.world):
-            if r == self.rank:
-                ptrs.append(self._own)
-                continue
-            hb = (ctypes.c_ubyte * 64)(*gathered[r].cpu().tolist())
-            pp = ctypes.c_void_p()
-            _lib.check(L.pert_peer_open(hb, ctypes.byref(pp)), "pert_peer_open")
-            self._peers.append(pp.value)
-            ptrs.append(pp.value)
+        try:
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(self._own)
+                    continue
+                hb = (ctypes.c_ubyte * 64)(*gathered[r].cpu().tolist())
+                pp = ctypes.c_void_p()
+                _lib.check(L.pert_peer_open(hb, ctypes.byref(pp)), "pert_peer_open")
+                self._peers.append(pp.value)
+                ptrs.append(pp.value)
+        except Exception as e:  # noqa: BLE001
+            err = e
+        if not all_ok(err is None):
+            self.close(collective=False)
+            raise _lib.PertGnnError(f"PeerAdam peer mapping failed on some rank (local error: {err!r})")
         self._xbufs = (ctypes.c_void_p * self.world)(*ptrs)
         dist.barrier(group=group)      # every rank has mapped every buffer before the first step touches them
 
@@ -131,13 +153,13 @@ class PeerAdam(FusedAdam):
         if code != 0:
             _lib.check(code, "pert_allreduce_adam")
 
-    def close(self):
+    def close(self, collective=True):
         L = _lib.lib()
         for pp in self._peers:
             L.pert_peer_close(pp)
         self._peers = []
         if self._own:
-            if dist.is_initialized() and self.world > 1:
+            if collective and dist.is_initialized() and self.world > 1:
                 torch.cuda.synchronize()
                 dist.barrier(group=self.group)     # nobody still reads this buffer
             L.pert_peer_free(self._own)
