@@ -198,6 +198,24 @@ def _collate(data_list):
     return Batch.from_data_list(data_list)
 
 
+def shard_by_edges(data_list, world):
+    """Data-parallel partition of a list of graphs over ``world`` ranks, balanced by edge count rather than by graph
+    count (the conv kernels' work is per edge, and call-graph sizes are power-law distributed).
+    Greedy longest-processing-time: graphs in descending edge order, each to the currently lightest rank (ties: fewer
+    graphs, then lower rank).  Deterministic; returns ``world`` lists of indices into ``data_list`` (each sorted
+    ascending so a rank keeps the dataset order).  The reference is single-GPU and has no counterpart."""
+    assert world >= 1
+    sizes = [(int(d.num_edges) + 1, i) for i, d in enumerate(data_list)]      # +1: isolated graphs still cost a row
+    order = sorted(sizes, key=lambda t: (-t[0], t[1]))
+    load = [0] * world
+    parts = [[] for _ in range(world)]
+    for sz, i in order:
+        r = min(range(world), key=lambda k: (load[k], len(parts[k]), k))
+        parts[r].append(i)
+        load[r] += sz
+    return [sorted(p) for p in parts]
+
+
 class DevicePrefetcher:
     """Iterates an iterable of host ``Batch`` objects and yields device batches, issuing the (single-slab) H2D copy
     of batch i+1 on a side stream while batch i is being trained on -- the step no longer waits for PCIe.
