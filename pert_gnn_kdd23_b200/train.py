@@ -283,8 +283,9 @@ class GraphedTrainStep:
 
     @staticmethod
     def _key(data):
-        return (data.x.data_ptr(), data.edge_index.data_ptr(), tuple(data.x.shape), int(data.edge_index.size(1)),
-                int(data.num_graphs))
+        # every tensor the captured kernels read must sit where it sat at capture time
+        ptrs = tuple(t.data_ptr() for t in model_inputs(data) if torch.is_tensor(t)) + (data.y.data_ptr(),)
+        return ptrs + (tuple(data.x.shape), int(data.edge_index.size(1)), int(data.num_graphs))
 
     def _finish(self, loss):
         with torch.no_grad():
