@@ -6,14 +6,27 @@
  * repository ships in pert_gnn_kdd23_b200/_lib.py) a maintainer of the reference would add.
  *
  * Conventions (all entry points):
- *   - every buffer is a CALLER-OWNED DEVICE pointer (the library never allocates or frees);
- *     fp32 row-major, `ld*` = row stride in floats; indices int32 inside the library, int64 where the
- *     reference's tensors are int64 (edge_index, edge_attr, batch, ids);
- *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, nothing synchronises;
+ *   - every data buffer (inputs, outputs, workspaces, scratch) is a CALLER-OWNED DEVICE pointer: the library
+ *     allocates no device memory for data (the one exception is pert_peer_alloc, whose purpose is to allocate the
+ *     IPC-shareable exchange buffer);  fp32 row-major, `ld*` = row stride in floats; indices int32 inside the library,
+ *     int64 where the reference's tensors are int64 (edge_index, edge_attr, batch, ids);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, nothing synchronises; every call acts on the
+ *     CURRENT CUDA device, which must be the device that owns the buffers and the stream (the Python binding enters
+ *     torch.cuda.device(tensor.device) around each call);
  *   - return value: 0 = ok; > 0 = cudaError_t of a failed launch/memset; < 0 = library code
  *     (PERT_ERR_*).  Never throws, never exits.  Out-of-range indices found ON THE DEVICE are
  *     reported by writing PERT_ERR_RANGE into the optional device word `status`;
- *   - no global mutable state: re-entrant, thread-safe per stream;
+ *   - library-owned state (all of it; none of it is data): (1) a per-device ring of 8192 self-resetting tile-ticket
+ *     counters for the dynamically scheduled tensor-core GEMMs -- every launch takes the next slot (host atomic), so
+ *     concurrent launches on different streams / threads / captured graphs do not share a counter unless 8192 GEMM
+ *     launches separate them while the first is still running; (2) per device, one auxiliary non-blocking stream and
+ *     two events the step engine (pert_model_forward/backward) uses to run independent small kernels beside the main
+ *     chain (fork/join by events, capture-safe; PERT_ENGINE_FORK=0 disables); the host-side issue of engine calls on
+ *     one device is serialised by a mutex, so engines driven from several host threads / streams stay correct (their
+ *     side work shares that one auxiliary stream); (3) the cached
+ *     cuTensorMapEncodeTiled driver entry point; (4) environment switches read once: PERT_GEMM_TC, PERT_GEMM_TMA,
+ *     PERT_TCONV_TILE, PERT_ENGINE_FORK (debug A/B only).
+ *     With that, operator-level calls are re-entrant and thread-safe across streams;
  *   - rows of float matrices must be 16-byte aligned (ld % 4 == 0, base pointer 16-byte aligned)
  *     unless stated otherwise.
  */
@@ -31,7 +44,7 @@ extern "C" {
 #define PERT_ERR_RANGE (-3)
 #define PERT_ERR_PEER_TIMEOUT (-4)
 
-/* ABI version (major*1000 + minor). */
+/* ABI version (major*1000 + minor).  2000: pert_tconv_bwd takes rpc_ws; node_depth / eval-metric entry points. */
 int pert_version(void);
 
 /* ---- index construction (integer, bit-exact) ---------------------------------------------------
@@ -60,6 +73,17 @@ int pert_graph_ptr(const int64_t* batch, long long N, long long B, int* ptr, voi
 int pert_min_depth(const int* gptr, long long B, const int* colptr, const int* csc_dst, const int* roots,
                    int* depth, void* stream);
 
+/* The tensor the reference stores as Data.node_depth (misc.py:159-175: unreachable -> 0, divide by the graph's max
+ * depth or 1; misc.py:215,368: torch.tensor(float, dtype=long) truncation -> {0,1}) from pert_min_depth's output.
+ * gptr[B+1], depth[N] int32 (-1 unreachable), node_depth[N] int64 (viewed [N,1] by the caller). */
+int pert_node_depth(const int* gptr, long long B, const int* depth, int64_t* node_depth, void* stream);
+
+/* Level-major node order inside each graph (BASELINE north_star "per-level index layout for coalescing"):
+ * order[N] int32 = node ids sorted by (graph, level, id), unreachable nodes last inside their graph
+ * (definition: oracle/index_oracle.py:level_order).  The reference has no counterpart (its model never reads
+ * node_depth); it is a layout key for collation. */
+int pert_level_order(const int* gptr, long long B, const int* depth, int* order, void* stream);
+
 /* ---- segmented reduce (the scatter-max / scatter-add metric kernel) -----------------------------
  * out[i,:] = reduce over CSR segment i of msg rows; op 0 = sum, 1 = max; empty segment -> 0.
  * Replaces torch_geometric.utils.scatter(reduce='max'|'sum') as used by utils.softmax and
@@ -84,12 +108,16 @@ int pert_tconv_fwd(const float* q, const float* k, const float* v, const float* 
                    float* out, int ld_out, float* alpha, int n_rpc, long long N, long long E, long long B_hint, int H,
                    void* stream);
 /* g = dL/dout [N,H] (stride ld_g).  Writes dq,dk,dv [N,H] (stride ld_d), dsp [E] scratch; ACCUMULATES
- * (+=, atomics) into dt_if [n_if,H] and dt_rpc [n_rpc,H] (caller zeroes them once per step). */
+ * (+=, atomics) into dt_if [n_if,H] and dt_rpc [n_rpc,H] (caller zeroes them once per step).
+ * rpc_ws: caller scratch of PERT_TCONV_RPC_WS_FLOATS * N floats (per-target sums of alpha / ds by rpc type, written by
+ * the target pass and consumed by the source pass of the same call) or NULL; with NULL, or n_rpc > 8, the rpc-table
+ * gradient falls back to per-edge shared-memory atomics (same result, slower). */
+#define PERT_TCONV_RPC_WS_FLOATS 16
 int pert_tconv_bwd(const float* g, int ld_g, const float* q, const float* k, const float* v, int ld,
                    const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr,
                    const int* csc_pos, const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha,
-                   float* dq, float* dk, float* dv, int ld_d, float* dsp, float* dt_if, float* dt_rpc, int n_rpc,
-                   long long N, long long E, long long B_hint, int H, void* stream);
+                   float* dq, float* dk, float* dv, int ld_d, float* dsp, float* rpc_ws, float* dt_if, float* dt_rpc,
+                   int n_rpc, long long N, long long E, long long B_hint, int H, void* stream);
 
 /* ---- dense linears (exact fp32) --------------------------------------------------------------------
  * Replace torch_geometric.nn.Linear / the lin_* of TransformerConv (model.py:26-55,105,110-112).
@@ -145,6 +173,11 @@ int pert_relu_bwd(const float* y, float* dy, long long n, void* stream);
  * dyhat[B] = grad_scale * dloss/dyhat (either output may be NULL). */
 int pert_pinball_loss(const int64_t* y, const float* yhat, float tau, long long B, float grad_scale, float* loss,
                       float* dyhat, void* stream);
+
+/* Eval / epoch metrics without host syncs (pert_gnn.py:249, :284-289): acc[0] += sum|yhat - y|, acc[1] += sum(|yhat - y| / y),
+ * acc[2] += B * pinball_tau(y, yhat)  (= sum of the per-graph pinball terms).  acc: 3 doubles on the device, zeroed by
+ * the caller at the start of an epoch and read back once at its end. */
+int pert_eval_metrics(const int64_t* y, const float* yhat, float tau, long long B, double* acc, void* stream);
 
 /* torch.optim.Adam step (pert_gnn.py:343,247) over one flat parameter buffer; g is scaled by grad_scale. */
 int pert_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

@@ -14,8 +14,10 @@ Module / parameter names are identical to the reference so ``state_dict``
 keys match (``convs.{i}.lin_{key,query,value,edge,skip}``, ``bns.{i}``,
 ``local_linear``, ``global_linear{1,2}``, ``cat_embedding.{i}``,
 ``entry_embeds``, ``interface_embeds``, ``rpctype_embeds``).  The reference's
-``edge_linear = Linear(-1, 2H)`` (model.py:68) is a lazy parameter that is
-never materialised nor used; it is omitted here (optimizers skip it in PyG).
+``edge_linear = Linear(-1, 2H)`` (model.py:68) is lazy and never used: in PyG 2.4.0 its
+weight stays an UninitializedParameter (not restated) while its bias IS a real [2H]
+parameter (uninitialised memory there; zeros here) that never receives a gradient,
+so ``edge_linear.bias`` is kept for ``state_dict`` / ``parameters()`` parity.
 """
 import math
 
@@ -137,6 +139,8 @@ class OracleSAGEDeterministic(torch.nn.Module):
         self.entry_embeds = torch.nn.Embedding(entry_id_max + 1, H)
         self.interface_embeds = torch.nn.Embedding(interface_id_max + 1, H)
         self.rpctype_embeds = torch.nn.Embedding(rpctype_id_max + 1, H)
+        self.edge_linear = torch.nn.Module()                  # model.py:68: lazy Linear(-1, 2H), never used
+        self.edge_linear.bias = torch.nn.Parameter(torch.zeros(2 * H))
 
     def reset_parameters(self):
         for conv in self.convs:

@@ -23,11 +23,13 @@ SIGNATURES = {
     "pert_build_index": (I, [P, P, I, LL, LL, I, I, P, P, P, P, P, P, P, P, P, LL, P, P]),
     "pert_graph_ptr": (I, [P, LL, LL, P, P, LL, P, P]),
     "pert_min_depth": (I, [P, LL, P, P, P, P, P]),
+    "pert_node_depth": (I, [P, LL, P, P, P]),
+    "pert_level_order": (I, [P, LL, P, P, P]),
     "pert_segment_reduce_fwd": (I, [P, P, P, P, LL, I, I, P]),
     "pert_segment_reduce_bwd": (I, [P, P, P, P, P, P, LL, I, I, P]),
     "pert_tconv_supported_width": (I, [I]),
     "pert_tconv_fwd": (I, [P, P, P, P, I, P, P, P, P, P, P, P, I, P, I, LL, LL, LL, I, P]),
-    "pert_tconv_bwd": (I, [P, I, P, P, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, I, LL, LL, LL, I,
+    "pert_tconv_bwd": (I, [P, I, P, P, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, LL, LL, LL, I,
                            P]),
     "pert_gemm_nt": (I, [P, I, I, LL, P, I, P, P, I, I, LL, LL, I, I, I, I, P]),
     "pert_gemm_tn": (I, [P, I, I, LL, P, I, I, LL, P, I, P, LL, I, I, P]),
@@ -42,6 +44,7 @@ SIGNATURES = {
     "pert_pool_bwd": (I, [P, P, P, I, P, P, P, P, P, I, P, P, LL, LL, I, P]),
     "pert_relu_bwd": (I, [P, P, LL, P]),
     "pert_pinball_loss": (I, [P, P, F, LL, F, P, P, P]),
+    "pert_eval_metrics": (I, [P, P, F, LL, P, P]),
     "pert_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, LL, F, P]),
     # fused all-reduce + Adam over peer memory (csrc/peer.cu)
     "pert_peer_exchange_bytes": (LL, [LL]),
@@ -99,6 +102,31 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device_of(fn):
+    """Decorator: run ``fn`` with the CUDA device of its first CUDA-tensor argument current.  The C library launches
+    on the current device and ``stream()`` returns that device's current stream, so every binding that takes tensors
+    must pin the device (reference loop: ``--device N`` + ``model.to(f'cuda:{N}')`` never calls ``set_device``)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                dev = a.device
+                break
+            d = getattr(a, "device", None)             # objects that carry a device (Engine, GraphIndex, FlatParams)
+            if isinstance(d, torch.device) and d.type == "cuda":
+                dev = d
+                break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
 
 
 def call(name, *args):

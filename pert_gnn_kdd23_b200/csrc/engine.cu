@@ -11,6 +11,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 namespace {
 
@@ -349,7 +350,7 @@ struct Ws {
   float* bn_stats[PERT_MAX_CONVS];
   float *bn_part, *pool, *z, *h1;
   // backward temporaries
-  float *dplanes, *dx, *dsp, *sums, *dpool, *dzent, *dh1;
+  float *dplanes, *dx, *dsp, *rpc_ws, *sums, *dpool, *dzent, *dh1;
   long long total;  // floats
   long long packed_floats;
 };
@@ -407,6 +408,7 @@ Ws carve(const PertModelDesc* d, long long N, long long E, long long B, float* b
   int kmax = d->k0 > H ? d->k0 : H;
   w.dx = take(N * kmax);
   w.dsp = take(E);
+  w.rpc_ws = take(N * PERT_TCONV_RPC_WS_FLOATS);
   w.sums = take(2LL * H);
   w.dpool = take(B * H);
   w.dzent = take(B * H);
@@ -474,6 +476,11 @@ struct AuxStream {
   cudaEvent_t fork = nullptr, join = nullptr;
   int state = 0;   // 0 untried, 1 ready, -1 unavailable
 };
+// host-side issue of engine calls is serialised per process: the fork/join events of the auxiliary stream are shared
+std::mutex& engine_mutex() {
+  static std::mutex m;
+  return m;
+}
 AuxStream* aux_stream() {
   static AuxStream aux[64];
   static int enabled = -1;
@@ -552,6 +559,7 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
                        long long workspace_bytes, int training, float* global_pred, float* local_pred, int* status,
                        const PertProbe* probe, void* index_ready, void* stream) {
   TRY(check_desc(d));
+  std::lock_guard<std::mutex> issue_lock(engine_mutex());
   if (!params || !x || !cat_X || !entry_id || !probs || !pnn || !batch || !rowptr || !workspace || !global_pred)
     return PERT_ERR_BADARG;
   if (E > 0 && (!csr_src || !csr_if || !csr_rpc)) return PERT_ERR_BADARG;
@@ -644,6 +652,7 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
                         const int* csc_dst, void* workspace, long long workspace_bytes, int training,
                         const float* d_global, const float* d_local, const PertProbe* probe, void* stream) {
   TRY(check_desc(d));
+  std::lock_guard<std::mutex> issue_lock(engine_mutex());
   if (!params || !grads || !cat_X || !entry_id || !probs || !pnn || !batch || !rowptr || !colptr || !workspace ||
       !d_global)
     return PERT_ERR_BADARG;
@@ -701,7 +710,7 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
     float* pl = w.planes[l];
     PROBE_START(2, l);
     TRY(pert_tconv_bwd(dskip, H, pl, pl + N * H, pl + 2 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos,
-                       csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.dt_if[l], w.dt_rpc[l],
+                       csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.rpc_ws, w.dt_if[l], w.dt_rpc[l],
                        d->n_rpc, N, E, B, H, st));
     PROBE_STOP(2, l);
     if (l == 0) {                       // every dT table is complete now

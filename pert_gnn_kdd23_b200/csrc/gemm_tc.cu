@@ -30,6 +30,7 @@
 //       smem layout (bank-conflict-free 8x4 patches) | warp 8 issues the MMAs.
 // These GEMMs are memory-bound by shape (K <= 256): A read once, C written once; measured bounds in DESIGN.md section 3.
 #include "common.cuh"
+#include <atomic>
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -138,6 +139,7 @@ struct NtArgs {
   int ldc, c_cb;
   long long c_cbs;
   int M, Nc, K, BN, relu;
+  unsigned int* ctr;   // this launch's ticket counters (one per blockIdx.y), see ticket_slot()
 };
 
 struct NtBars {
@@ -626,7 +628,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tn_tc(TnArgs g) {
 //              stores them as one 16-byte K-quad of the K-major operand stage (hi and lo)
 //   warp 8     MMA issuer
 // A chunk id >= nchunks is the stop sentinel; it travels through the ring and the operand stages.
-__device__ unsigned int g_tn_ctr[8];   // per blockIdx.y; the CTA drawing the last ticket resets it (one launch at a time)
+// Tile tickets: every launch of a dynamically scheduled GEMM draws its tickets from its OWN slot of a ring of
+// self-resetting device counters (8 counters per slot, one per blockIdx.y).  The host hands out slots round-robin
+// (atomic), so two launches that run concurrently on different streams -- or two replicas captured into different CUDA
+// graphs -- never share a counter unless TICKET_SLOTS launches were issued in between while the first was still running.
+// The CTA that draws the last ticket of a launch resets the counter, so a slot (also one baked into a captured graph)
+// is reusable as soon as its launch has finished.
+constexpr int TICKET_SLOTS = 8192;
+__device__ unsigned int g_ticket_ring[TICKET_SLOTS * 8];
 
 __device__ __forceinline__ void mbar_arrive_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -650,6 +659,7 @@ struct TnTmaArgs {
   int ldc;
   float* colsum;
   int R, Mc, Nc, NcP, nchunks, NS, pw, a_contig, b_contig;
+  unsigned int* ctr;   // this launch's ticket counters (see g_ticket_ring)
 };
 struct TnTmaBars {
   uint64_t ring_full[RING_MAX], ring_empty[RING_MAX], op_full[2], op_empty[2], done;
@@ -699,12 +709,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
     uint32_t rs = 0, rph = 0;
     while (true) {
       unsigned int c = 0;
-      if (lane == 0) c = atomicAdd(&g_tn_ctr[blockIdx.y], 1u);
+      if (lane == 0) c = atomicAdd(&g.ctr[blockIdx.y], 1u);
       c = __shfl_sync(0xffffffffu, c, 0);
       mbar_wait(&bars.ring_empty[rs], rph ^ 1);
       if (c >= (unsigned int)g.nchunks) {
         if (lane == 0) {
-          if (c == (unsigned int)g.nchunks + gridDim.x - 1) g_tn_ctr[blockIdx.y] = 0;   // last ticket of the launch
+          if (c == (unsigned int)g.nchunks + gridDim.x - 1) g.ctr[blockIdx.y] = 0;   // last ticket of the launch
           bars.ring_meta[rs] = -1;
           mbar_arrive(&bars.ring_full[rs]);
         }
@@ -909,7 +919,6 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
 // A is addressed as a 2-D tensor [row_blk * nblocks, a_cb] with pitch lda: column block b of a blocked operand starts at
 // tensor row b * row_blk (row_blk = a_cbs / lda), rows beyond M of a block alias the next block (their products are
 // never stored) and out-of-range columns / rows are zero-filled by the TMA unit.
-__device__ unsigned int g_nt_ctr[8];
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
   asm volatile(
@@ -986,9 +995,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       uint32_t rs = 0, rph = 0;
       int tr_i = 0;
       while (true) {
-        const unsigned int c = atomicAdd(&g_nt_ctr[blockIdx.y], 1u);
+        const unsigned int c = atomicAdd(&g.ctr[blockIdx.y], 1u);
         if (c >= (unsigned int)mtiles) {
-          if (c == (unsigned int)mtiles + gridDim.x - 1) g_nt_ctr[blockIdx.y] = 0;   // last ticket of the launch
+          if (c == (unsigned int)mtiles + gridDim.x - 1) g.ctr[blockIdx.y] = 0;   // last ticket of the launch
           mbar_wait(&bars.ring_empty[rs], rph ^ 1);
           bars.ring_meta[rs] = -1;
           mbar_arrive(&bars.ring_full[rs]);
@@ -1256,6 +1265,19 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+// next ticket slot of the current device's ring (host side: one atomic increment per launch, thread-safe)
+static unsigned int* ticket_slot() {
+  static std::atomic<unsigned int> next{0};
+  static std::atomic<unsigned int*> base_of[64];          // per device; resolved on the first (eager) launch
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  unsigned int* base = base_of[dev].load(std::memory_order_acquire);
+  if (!base) {
+    if (cudaGetSymbolAddress((void**)&base, g_ticket_ring) != cudaSuccess) return nullptr;
+    base_of[dev].store(base, std::memory_order_release);
+  }
+  return base + (size_t)(next.fetch_add(1u, std::memory_order_relaxed) % TICKET_SLOTS) * 8;
+}
 static bool tma_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -1302,7 +1324,7 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
     const size_t need = tma_enabled() ? (size_t)BN * K * 8 + 1024 + 1024 + 2 * 32 * 1024 + 32 * 1024 : smem;
     if (need <= 226 * 1024) break;
   }
-  NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu};
+  NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu, nullptr};
   const int mtiles_all = (int)((M + 127) / 128);
   if (tma_enabled() && nblk <= 8 && encode_tiled_fn()) {
     // TMA-tiled kernel: A as a 2-D tensor [nblocks * row_blk, a_cb] with pitch lda (see k_gemm_nt_tma)
@@ -1342,6 +1364,8 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
         const size_t smem2 = 1024 + bbytes + (size_t)NS * 32 * 1024 + 32 * 1024;
         cudaError_t e2 = cudaFuncSetAttribute(k_gemm_nt_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e2 != cudaSuccess) return (int)e2;
+        g.ctr = ticket_slot();
+        if (!g.ctr) return (int)cudaGetLastError();
         int gx2 = PERT_NUM_SMS / nblk;
         if (gx2 < 1) gx2 = 1;
         if (gx2 > mtiles_all) gx2 = mtiles_all;
@@ -1384,7 +1408,8 @@ int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
       if (gx < 1) gx = 1;
       if (gx > nchunks) gx = nchunks;
       TnTmaArgs g{A,        lda, a_cb, a_cbs, B,   ldb,     C,  ldc, a_colsum,
-                  (int)R,   Mc,  Nc,   NcP,   nchunks, NS, pw, lda == pw ? 1 : 0, ldb == Nc ? 1 : 0};
+                  (int)R,   Mc,  Nc,   NcP,   nchunks, NS, pw, lda == pw ? 1 : 0, ldb == Nc ? 1 : 0, ticket_slot()};
+      if (!g.ctr) return (int)cudaGetLastError();
       const size_t smem = op + ring * NS;
       auto kern = NcP <= 64 ? k_gemm_tn_tma<8> : (NcP <= 96 ? k_gemm_tn_tma<12> : k_gemm_tn_tma<16>);
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

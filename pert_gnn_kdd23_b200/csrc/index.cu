@@ -250,6 +250,70 @@ __global__ void k_min_depth(const int* __restrict__ gptr, const int* __restrict_
     if (depth[n] == 0x7fffffff) depth[n] = -1;
 }
 
+
+// ---- stored node_depth tensor (reference misc.py:159-175 + the long cast of :215 / :368), one CTA per graph ----------
+// unreachable (-1) -> 0; divide by the graph's max depth (1 if that is 0) in float64 like numpy does; the
+// torch.tensor(float ndarray, dtype=torch.long) of the reference truncates toward zero -> values in {0, 1}.
+__global__ void k_node_depth(const int* __restrict__ gptr, const int* __restrict__ depth, int64_t* __restrict__ out) {
+  const int g = blockIdx.x;
+  const int n0 = gptr[g], n1 = gptr[g + 1];
+  __shared__ int smax;
+  if (threadIdx.x == 0) smax = 0;
+  __syncthreads();
+  int m = 0;
+  for (int n = n0 + threadIdx.x; n < n1; n += blockDim.x) m = max(m, depth[n]);   // -1 never wins against 0
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(&smax, m);
+  __syncthreads();
+  const double norm = smax > 0 ? (double)smax : 1.0;
+  for (int n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+    const int d = depth[n];
+    out[n] = (int64_t)((double)(d < 0 ? 0 : d) / norm);
+  }
+}
+
+// ---- level-major node order inside each graph (BASELINE north_star "per-level index layout"; definition:
+// oracle/index_oracle.py:level_order): order = stable sort of the graph's nodes by level, unreachable (-1) last.
+// One CTA per graph: histogram of levels in shared memory (levels <= LV_MAX, deeper ones clamp into the last bucket
+// and are ordered there by a rank pass), exclusive scan, stable placement by counting the earlier nodes of the
+// same level (graphs are a few hundred nodes: O(n * n / threads) compares, no atomics -> deterministic).
+constexpr int LV_MAX = 1023;
+__global__ void __launch_bounds__(256) k_level_order(const int* __restrict__ gptr, const int* __restrict__ depth,
+                                                     int* __restrict__ order) {
+  const int g = blockIdx.x;
+  const int n0 = gptr[g], n1 = gptr[g + 1], n = n1 - n0;
+  __shared__ int hist[LV_MAX + 2];
+  for (int x = threadIdx.x; x < LV_MAX + 2; x += blockDim.x) hist[x] = 0;
+  __syncthreads();
+  auto key = [&](int v) {
+    const int d = depth[n0 + v];
+    return d < 0 ? LV_MAX + 1 : (d > LV_MAX ? LV_MAX : d);
+  };
+  for (int v = threadIdx.x; v < n; v += blockDim.x) atomicAdd(&hist[key(v)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {                       // exclusive scan of <= 1025 buckets
+    int run = 0;
+    for (int b = 0; b < LV_MAX + 2; ++b) {
+      const int c = hist[b];
+      hist[b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < n; v += blockDim.x) {
+    const int kv = key(v);
+    const int dv = depth[n0 + v];
+    int rank = 0;
+    // earlier nodes of the same bucket; inside the clamped bucket order by (true depth, id)
+    for (int u = 0; u < n; ++u) {
+      if (key(u) != kv) continue;
+      const int du = depth[n0 + u];
+      rank += (du < dv) || (du == dv && u < v);
+    }
+    order[n0 + hist[kv] + rank] = n0 + v;
+  }
+}
+
 __global__ void k_graph_ptr_count(const int64_t* __restrict__ batch, int N, int B, int* __restrict__ ptr, int* status) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -265,7 +329,7 @@ __global__ void k_graph_ptr_count(const int64_t* __restrict__ batch, int N, int 
 
 extern "C" {
 
-int pert_version(void) { return 1000; }
+int pert_version(void) { return 2000; }
 
 long long pert_index_workspace_bytes(long long N, long long E) {
   if (N < 0 || E < 0) return PERT_ERR_BADARG;
@@ -353,6 +417,24 @@ int pert_min_depth(const int* gptr, long long B_, const int* colptr, const int* 
   if (B_ < 0 || !gptr || !colptr || !roots || !depth) return PERT_ERR_BADARG;
   if (B_ == 0) return PERT_OK;
   k_min_depth<<<(int)B_, 128, 0, (cudaStream_t)stream_>>>(gptr, colptr, csc_dst, roots, depth);
+  PERT_LAUNCH_CHECK();
+  return PERT_OK;
+}
+
+// node_depth[N] int64 = the tensor the reference stores on every Data (misc.py:159-175,215,368) from the raw min-depth.
+int pert_node_depth(const int* gptr, long long B_, const int* depth, int64_t* node_depth, void* stream_) {
+  if (B_ < 0 || !gptr || !depth || !node_depth) return PERT_ERR_BADARG;
+  if (B_ == 0) return PERT_OK;
+  k_node_depth<<<(int)B_, 128, 0, (cudaStream_t)stream_>>>(gptr, depth, node_depth);
+  PERT_LAUNCH_CHECK();
+  return PERT_OK;
+}
+
+// order[N] int32: node ids in (graph, level, id) order, unreachable last inside their graph.
+int pert_level_order(const int* gptr, long long B_, const int* depth, int* order, void* stream_) {
+  if (B_ < 0 || !gptr || !depth || !order) return PERT_ERR_BADARG;
+  if (B_ == 0) return PERT_OK;
+  k_level_order<<<(int)B_, 256, 0, (cudaStream_t)stream_>>>(gptr, depth, order);
   PERT_LAUNCH_CHECK();
   return PERT_OK;
 }

@@ -480,6 +480,36 @@ inline bool al16(const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 
 
 }  // namespace
 
+
+// ---- eval metrics (reference pert_gnn.py:284-289, :249): block sums in double, one atomic per block and metric
+__global__ void __launch_bounds__(256) k_eval_metrics(const int64_t* __restrict__ y, const float* __restrict__ yhat,
+                                                      float tau, int B, double* __restrict__ acc) {
+  double mae = 0.0, mape = 0.0, q = 0.0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    const float yt = (float)y[b];                 // y.float() / int64 -> float32 promotion of the reference
+    const float e = yt - yhat[b];
+    const float ae = fabsf(yhat[b] - yt);
+    mae += (double)ae;
+    mape += (double)(ae / yt);
+    q += (double)fmaxf(tau * e, (tau - 1.0f) * e);
+  }
+  __shared__ double red[3][8];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    mae += __shfl_xor_sync(0xffffffffu, mae, off);
+    mape += __shfl_xor_sync(0xffffffffu, mape, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = mae; red[1][w] = mape; red[2][w] = q; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
 extern "C" {
 
 int pert_embedding_fwd(const float* table, int n_rows, const int64_t* ids, int id_stride, float* out, int ld_out,
@@ -661,6 +691,16 @@ int pert_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
   float bc2 = 1.f - powf(beta2, (float)step);
   k_adam<<<pert_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                              bc1, sqrtf(bc2), grad_scale);
+  PERT_LAUNCH_CHECK();
+  return PERT_OK;
+}
+
+int pert_eval_metrics(const int64_t* y, const float* yhat, float tau, long long B, double* acc, void* stream) {
+  if (B < 0 || !y || !yhat || !acc) return PERT_ERR_BADARG;
+  if (B == 0) return PERT_OK;
+  int grid = pert_cdiv(B, 256);
+  if (grid > 64) grid = 64;
+  k_eval_metrics<<<grid, 256, 0, (cudaStream_t)stream>>>(y, yhat, tau, (int)B, acc);
   PERT_LAUNCH_CHECK();
   return PERT_OK;
 }

@@ -436,8 +436,8 @@ int pert_tile_fwd(const float* q, const float* k, const float* v, const float* s
 int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, const float* v, int ld, const int* rowptr,
                   const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr, const int* csc_pos,
                   const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha, float* dq, float* dk,
-                  float* dv, int ld_d, float* dsp, float* dt_if, float* dt_rpc, int n_rpc, long long N, long long E,
-                  long long B, int H, cudaStream_t st);
+                  float* dv, int ld_d, float* dsp, float* rpc_ws, float* dt_if, float* dt_rpc, int n_rpc, long long N,
+                  long long E, long long B, int H, cudaStream_t st);
 static bool tile_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -488,8 +488,8 @@ int pert_tconv_fwd(const float* q, const float* k, const float* v, const float* 
 int pert_tconv_bwd(const float* g, int ld_g, const float* q, const float* k, const float* v, int ld,
                    const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr,
                    const int* csc_pos, const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha,
-                   float* dq, float* dk, float* dv, int ld_d, float* dsp, float* dt_if, float* dt_rpc, int n_rpc,
-                   long long N, long long E, long long B_hint, int H, void* stream) {
+                   float* dq, float* dk, float* dv, int ld_d, float* dsp, float* rpc_ws, float* dt_if, float* dt_rpc,
+                   int n_rpc, long long N, long long E, long long B_hint, int H, void* stream) {
   if (N < 0 || E < 0 || !g || !q || !k || !v || !rowptr || !colptr || !dq || !dk || !dv) return PERT_ERR_BADARG;
   if (ld % 4 || ld_g % 4 || ld_d % 4 || !aligned16(g) || !aligned16(q) || !aligned16(k) || !aligned16(v) ||
       !aligned16(dq) || !aligned16(dk) || !aligned16(dv))
@@ -499,7 +499,7 @@ int pert_tconv_bwd(const float* g, int ld_g, const float* q, const float* k, con
   if (N == 0) return PERT_OK;
   if (tile_enabled() && ld_d == H) {
     int rt = pert_tile_bwd(g, ld_g, q, k, v, ld, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos, csc_dst, t_if, t_rpc,
-                           alpha, dq, dk, dv, ld_d, dsp, dt_if, dt_rpc, n_rpc, N, E, B_hint, H, (cudaStream_t)stream);
+                           alpha, dq, dk, dv, ld_d, dsp, rpc_ws, dt_if, dt_rpc, n_rpc, N, E, B_hint, H, (cudaStream_t)stream);
     if (rt != PERT_ERR_UNSUPPORTED) {
       if (rt) return rt;
       PERT_LAUNCH_CHECK();

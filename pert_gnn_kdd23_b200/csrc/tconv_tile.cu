@@ -610,33 +610,14 @@ int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool h
   ad.tile_nodes = gd.T; ad.edge_cap = gd.ecap;
   as.tile_nodes = gs.T; as.edge_cap = gs.ecap;
   int rc;
-  float* ws = nullptr;   // stream-ordered scratch for the per-target rpc sums (see RPC_FAST)
-  if (has_e && a0.n_rpc <= RPC_FAST && LPR >= RPC_FAST && TILE_THREADS % H == 0) {
-    // keep freed scratch cached in the device's default pool (the default release threshold of 0 hands it back to the
-    // driver at every synchronisation, turning the next cudaMallocAsync into a real allocation)
-    static bool pool_ready[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      }
-      pool_ready[dev] = true;
-    }
-    if (cudaMallocAsync((void**)&ws, (size_t)N * 2 * RPC_FAST * sizeof(float), st) != cudaSuccess) {
-      (void)cudaGetLastError();
-      ws = nullptr;
-    }
-  }
+  // per-target rpc sums (see RPC_FAST) live in caller scratch; without it the general atomics path runs
+  float* ws = (has_e && a0.n_rpc <= RPC_FAST && LPR >= RPC_FAST && TILE_THREADS % H == 0) ? a0.rpc_ws : nullptr;
   ad.rpc_ws = as.rpc_ws = ws;
   if (has_e) {
     if ((rc = set_smem(k_tile_bwd_dst<LPR, true>, gd.bytes))) return rc;
     if ((rc = set_smem(k_tile_bwd_src<LPR, true>, gs.bytes))) return rc;
     k_tile_bwd_dst<LPR, true><<<pert_cdiv(N, gd.T), TILE_THREADS, gd.bytes, st>>>(ad);
     k_tile_bwd_src<LPR, true><<<pert_cdiv(N, gs.T), TILE_THREADS, gs.bytes, st>>>(as);
-    if (ws) cudaFreeAsync(ws, st);
   } else {
     if ((rc = set_smem(k_tile_bwd_dst<LPR, false>, gd.bytes))) return rc;
     if ((rc = set_smem(k_tile_bwd_src<LPR, false>, gs.bytes))) return rc;
@@ -672,8 +653,8 @@ int pert_tile_fwd(const float* q, const float* k, const float* v, const float* s
 int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, const float* v, int ld, const int* rowptr,
                   const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr, const int* csc_pos,
                   const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha, float* dq, float* dk,
-                  float* dv, int ld_d, float* dsp, float* dt_if, float* dt_rpc, int n_rpc, long long N, long long E,
-                  long long B, int H, cudaStream_t st) {
+                  float* dv, int ld_d, float* dsp, float* rpc_ws, float* dt_if, float* dt_rpc, int n_rpc, long long N,
+                  long long E, long long B, int H, cudaStream_t st) {
   if (ld != H || ld_g != H || ld_d != H || (t_if && ((size_t)n_rpc * H * 4 > 16 * 1024 || n_rpc > 1023)))
     return PERT_ERR_UNSUPPORTED;
   TileArgs a{};
@@ -682,7 +663,7 @@ int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, con
   a.colptr = colptr; a.csc_pos = csc_pos; a.csc_dst = csc_dst;
   a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc;
   a.out = dq; a.dk = dk; a.dv = dv; a.alpha = const_cast<float*>(alpha); a.dsp = dsp;
-  a.dt_if = dt_if; a.dt_rpc = dt_rpc;
+  a.dt_if = dt_if; a.dt_rpc = dt_rpc; a.rpc_ws = rpc_ws;
   a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
   switch (H) {
     case 32: return launch_bwd<8>(a, N, E, B, t_if != nullptr, st);

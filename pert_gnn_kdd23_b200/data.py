@@ -246,11 +246,15 @@ class DevicePrefetcher:
             host = b.__dict__["_slab"]
             k = state["k"]
             state["k"] = (k + 1) % len(ring)
-            if ring[k] is None or ring[k].numel() < host.numel():
-                ring[k] = torch.empty(host.numel(), dtype=torch.uint8, device=self.device)
             if done[k] is not None:
                 side.wait_event(done[k])   # the step that read this slab must be over before it is overwritten
             with torch.cuda.stream(side):
+                if ring[k] is None or ring[k].numel() < host.numel():
+                    # allocated ON the side stream: the caching allocator then only hands out a block whose previous
+                    # users are ordered before this stream's work (a block freed on the main stream could still be
+                    # read there); the consumer's use is ordered by the event below + record_stream
+                    ring[k] = torch.empty(host.numel(), dtype=torch.uint8, device=self.device)
+                    ring[k].record_stream(torch.cuda.current_stream(self.device))
                 dslab = ring[k][:host.numel()]
                 dslab.copy_(host, non_blocking=True)
             ev = torch.cuda.Event()

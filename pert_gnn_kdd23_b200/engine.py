@@ -137,17 +137,29 @@ class Engine:
         self.n_convs = n_convs
         self.ws = None
         self.ws_key = (0, 0, 0)
+        self.ws_generation = 0
         self._saved = None
 
     # ------------------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.fp.flat.device
+
+    def reserve(self, N, E, B):
+        """Pre-size the workspace (growth only).  ``ws_generation`` changes whenever the buffer is re-allocated: a CUDA
+        graph captured over the old buffer must not be replayed any more (train.GraphedTrainStep checks it)."""
+        return self._workspace(int(N), int(E), int(B))
+
     def _workspace(self, N, E, B):
         if self.ws is None or N > self.ws_key[0] or E > self.ws_key[1] or B > self.ws_key[2]:
             key = (max(N, self.ws_key[0]), max(E, self.ws_key[1]), max(B, self.ws_key[2]))
             nbytes = self.lib.pert_model_workspace_bytes(C.byref(self.desc), *key)
             if nbytes < 0:
                 _lib.check(int(nbytes), "pert_model_workspace_bytes")
-            self.ws = torch.zeros(nbytes // 4, device=self.fp.flat.device, dtype=torch.float32)
+            with torch.cuda.device(self.fp.flat.device):
+                self.ws = torch.zeros(nbytes // 4, device=self.fp.flat.device, dtype=torch.float32)
             self.ws_key = key
+            self.ws_generation += 1
         return self.ws
 
     def _pack_launches(self):
@@ -171,6 +183,7 @@ class Engine:
         L = self.n_convs
         return 1 + 1 + 4 * L + 2 * (L - 1) + self.desc.n_cat + (L + 2) // 3 + self._pack_launches()
 
+    @_lib.on_device_of
     def forward(self, x, cat_X, entry_id, probs, pnn, batch, index: GraphIndex, training, probe=None,
                 index_ready=None):
         """-> (global_pred [B,1], local_pred [N,1]); keeps what backward needs in the workspace."""
@@ -197,6 +210,7 @@ class Engine:
         self._saved = (x, cat_X, entry_id, probs, pnn, batch, index, bool(training), N, E, B)
         return gpred, lpred
 
+    @_lib.on_device_of
     def backward(self, d_global, d_local=None, grads=None, probe=None):
         """Accumulates (+=) parameter gradients into ``grads`` (default: the flat gradient buffer)."""
         x, cat_X, entry_id, probs, pnn, batch, index, training, N, E, B = self._saved

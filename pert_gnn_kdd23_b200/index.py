@@ -19,6 +19,10 @@ _CHECK = os.environ.get("PERT_CHECK_INDICES", "0") == "1"
 
 
 class GraphIndex:
+    @property
+    def device(self):
+        return self._buf.device
+
     __slots__ = ("N", "E", "rowptr", "perm", "csr_src", "csr_if", "csr_rpc", "colptr", "csc_pos",
                  "csc_dst", "status", "has_attr", "n_if", "n_rpc", "num_graphs", "_buf", "__weakref__")
 
@@ -34,6 +38,7 @@ def _al(n, a=64):
     return (n + a - 1) // a * a
 
 
+@_lib.on_device_of
 def build_index(edge_index, num_nodes, edge_attr=None, n_if=0, n_rpc=0, check=None):
     """edge_index int64 [2,E] on cuda; edge_attr int64 [E,>=2] (cols 0,1 = interface, rpctype) or None."""
     if not edge_index.is_cuda:
@@ -75,6 +80,7 @@ def build_index(edge_index, num_nodes, edge_attr=None, n_if=0, n_rpc=0, check=No
     return gi
 
 
+@_lib.on_device_of
 def graph_ptr(batch, num_graphs):
     """int32 ptr [B+1] from a PyG ``batch`` vector (cuda int64)."""
     assert batch.is_cuda and batch.dtype == torch.int64
@@ -86,6 +92,7 @@ def graph_ptr(batch, num_graphs):
     return ptr
 
 
+@_lib.on_device_of
 def min_depth(gptr, index, roots):
     """Level index: min hop depth from ``roots[g]`` (global node ids, int32 [B]) per graph; -1 unreachable."""
     B = gptr.numel() - 1
@@ -93,6 +100,25 @@ def min_depth(gptr, index, roots):
     _lib.call("pert_min_depth", _lib.ptr(gptr), B, _lib.ptr(index.colptr), _lib.ptr(index.csc_dst),
               _lib.ptr(roots.to(torch.int32).contiguous()), _lib.ptr(depth), _lib.stream())
     return depth
+
+
+@_lib.on_device_of
+def node_depth(gptr, depth):
+    """The tensor the reference stores as ``Data.node_depth`` ([N,1] int64, misc.py:159-175 + the long cast of
+    :215/:368) from the raw min-depth of ``min_depth``."""
+    B = gptr.numel() - 1
+    out = torch.empty(depth.numel(), 1, dtype=torch.int64, device=depth.device)
+    _lib.call("pert_node_depth", _lib.ptr(gptr), B, _lib.ptr(depth.contiguous()), _lib.ptr(out), _lib.stream())
+    return out
+
+
+@_lib.on_device_of
+def level_order(gptr, depth):
+    """Level-major node order inside each graph (int32 [N]; oracle/index_oracle.py:level_order)."""
+    B = gptr.numel() - 1
+    out = torch.empty(depth.numel(), dtype=torch.int32, device=depth.device)
+    _lib.call("pert_level_order", _lib.ptr(gptr), B, _lib.ptr(depth.contiguous()), _lib.ptr(out), _lib.stream())
+    return out
 
 
 # ---- small cache so the 2..5 conv layers of one forward (and repeated calls on the same batch) share one index

@@ -38,24 +38,31 @@ class SAGEDeterministic(torch.nn.Module):
         self.entry_embeds = torch.nn.Embedding(entry_id_max + 1, H)
         self.interface_embeds = torch.nn.Embedding(interface_id_max + 1, H)
         self.rpctype_embeds = torch.nn.Embedding(rpctype_id_max + 1, H)
-        self.edge_linear = Linear(-1, 2 * H)   # lazy + unused in the reference forward (model.py:68): no params
+        self.edge_linear = Linear(-1, 2 * H)   # lazy + unused in the reference forward (model.py:68): bias only
         # True: whole forward/backward issued by the C++ step engine (csrc/engine.cu); False: one autograd
         # Function per operator (ops.py).  Same kernels, same results; the engine removes the interpreter gaps.
         self.use_engine = True
         self._engine = None
 
     def engine(self, flat=None):
-        """The step engine of this replica (created on first use; re-created if the parameters moved)."""
-        eng = self._engine
-        if eng is not None and flat is None:
-            p0 = next(self.parameters())
-            lo = eng.fp.flat.data_ptr()
-            if lo <= p0.data_ptr() < lo + eng.fp.flat.numel() * 4:
-                return eng
+        """The step engine of this replica.  There is ONE FlatParams per model: the one passed in, else the one a
+        ``FlatParams(model)`` (e.g. an optimizer's) registered on the module, else a new one -- never a second flat
+        buffer behind the back of an optimizer.  Re-created only if the parameters moved (``.to()``, ``load``)."""
         from .engine import Engine
         from .train import FlatParams
 
-        self._engine = Engine(self, flat if flat is not None else FlatParams(self, bind_grads=False))
+        eng = self._engine
+        if flat is None:
+            if eng is not None and eng.fp.owns(self):
+                return eng
+            reg = self.__dict__.get("_flat_params")
+            flat = reg if (reg is not None and reg.owns(self)) else FlatParams(self, bind_grads=False)
+        if eng is not None and eng.fp is flat and flat.owns(self):
+            return eng
+        if not flat.owns(self):
+            raise RuntimeError("the FlatParams handed to model.engine() no longer holds this model's parameters "
+                               "(the model was moved or re-flattened after the optimizer was built)")
+        self._engine = Engine(self, flat)
         return self._engine
 
     def reset_parameters(self):

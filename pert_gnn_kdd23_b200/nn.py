@@ -15,8 +15,10 @@ from .index import GraphIndex, build_index, cached_index
 class Linear(torch.nn.Module):
     """torch_geometric.nn.Linear(in_channels, out_channels, bias=True): y = x W^T + b.
 
-    Lazy ``in_channels=-1`` (the reference's unused ``edge_linear``, model.py:68) is accepted and creates no
-    parameters, like PyG's UninitializedParameter that optimisers skip."""
+    Lazy ``in_channels=-1`` (the reference's unused ``edge_linear``, model.py:68): PyG 2.4.0 keeps the weight an
+    UninitializedParameter (optimisers skip it; not created here) but registers a real ``bias`` [out] -- kept, zero
+    filled (PyG leaves it uninitialised), so ``state_dict`` / ``parameters()`` carry ``edge_linear.bias`` like the
+    reference; it never receives a gradient."""
 
     def __init__(self, in_channels, out_channels, bias=True):
         super().__init__()
@@ -27,7 +29,7 @@ class Linear(torch.nn.Module):
             self.reset_parameters()
         else:
             self.weight = None
-            self.bias = None
+            self.bias = torch.nn.Parameter(torch.zeros(out_channels)) if bias else None
 
     def reset_parameters(self):
         if self.weight is None:

@@ -99,6 +99,7 @@ class _LinearFn(torch.autograd.Function):
     """y = x W^T + b (relu).  x: [M,K] or blocked [nb,M,cb]; y: [M,Nc] or blocked [out_blocks,M,Nc/out_blocks]."""
 
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, x, weight, bias, relu, out_blocks):
         _need_cuda(x, weight, bias)
         x, weight = _c(x), _c(weight)
@@ -116,6 +117,7 @@ class _LinearFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, dy):
         x, weight, y = ctx.saved_tensors
         dy = _c(dy)
@@ -144,6 +146,7 @@ def linear(x, weight, bias=None, relu=False, out_blocks=1):
 # ---------------------------------------------------------------------------------- embeddings
 class _EmbeddingFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, table, ids, col):
         """table [R,H]; ids int64 [N] or [N,C] (column ``col``) -> [N,H]."""
         _need_cuda(table, ids)
@@ -161,6 +164,7 @@ class _EmbeddingFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, dy):
         (ids,) = ctx.saved_tensors
         shape, col, stride = ctx.meta
@@ -183,6 +187,7 @@ class _EmbedConcatFn(torch.autograd.Function):
     embedding block is 16-byte aligned -- the first conv's weights are permuted to match (nn.py)."""
 
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, x, cat_X, *tables):
         _need_cuda(x, cat_X, *tables)
         x, cat_X = _c(x), _c(cat_X)
@@ -202,6 +207,7 @@ class _EmbedConcatFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, dout):
         (cat_X,) = ctx.saved_tensors
         shapes, F, H, ld = ctx.meta
@@ -230,6 +236,7 @@ class _TConvFn(torch.autograd.Function):
     """planes [4,N,H] (q,k,v,skip) or [3,N,H] (no skip), t_if [n_if,H], t_rpc [n_rpc,H] (or None) -> out [N,H]."""
 
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, planes, t_if, t_rpc, index):
         _need_cuda(planes, t_if, t_rpc)
         planes = _c(planes)
@@ -255,6 +262,7 @@ class _TConvFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, g):
         planes, t_if, t_rpc, alpha = ctx.saved_tensors
         index = ctx.index
@@ -262,6 +270,7 @@ class _TConvFn(torch.autograd.Function):
         P_, N, H = planes.shape
         dplanes = torch.empty_like(planes)
         dsp = torch.empty_like(alpha)
+        rpc_ws = torch.empty(16 * N, device=g.device, dtype=torch.float32) if ctx.has_e else None
         dt_if = dt_rpc = None
         if ctx.has_e:
             dt_if = torch.zeros_like(t_if)
@@ -271,7 +280,7 @@ class _TConvFn(torch.autograd.Function):
                  ptr(index.rowptr), ptr(index.csr_src), ptr(index.csr_if) if ctx.has_e else None,
                  ptr(index.csr_rpc) if ctx.has_e else None, ptr(index.colptr), ptr(index.csc_pos),
                  ptr(index.csc_dst), ptr(t_if), ptr(t_rpc), ptr(alpha), ptr(dplanes[0]), ptr(dplanes[1]),
-                 ptr(dplanes[2]), H, ptr(dsp), ptr(dt_if), ptr(dt_rpc), t_rpc.size(0) if ctx.has_e else 0, N,
+                 ptr(dplanes[2]), H, ptr(dsp), ptr(rpc_ws), ptr(dt_if), ptr(dt_rpc), t_rpc.size(0) if ctx.has_e else 0, N,
                  index.E, getattr(index, "num_graphs", 0), H, stream())
         LAUNCHES["n"] += 2
         if P_ == 4:
@@ -286,6 +295,7 @@ def tconv(planes, t_if, t_rpc, index):
 # ---------------------------------------------------------------------------------- batch norm (+relu)
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, eps, momentum, relu):
         _need_cuda(x, gamma, beta)
         x = _c(x)
@@ -303,6 +313,7 @@ class _BatchNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, dy):
         x, y, stats, gamma = ctx.saved_tensors
         training, relu = ctx.cfg
@@ -327,6 +338,7 @@ def batch_norm(x, gamma, beta, running_mean, running_var, num_batches_tracked, t
 # ---------------------------------------------------------------------------------- local head + pool
 class _PoolFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, x, probs, pnn, batch, w_local, b_local, num_graphs):
         _need_cuda(x, probs, pnn, batch)
         x = _c(x)
@@ -348,6 +360,7 @@ class _PoolFn(torch.autograd.Function):
         return pool, local
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, dpool, dlocal):
         x, probs, pnn, batch, w_local = ctx.saved_tensors
         N, H = x.shape
@@ -374,6 +387,7 @@ def pool_local(x, probs, pnn, batch, w_local, b_local, num_graphs):
 # ---------------------------------------------------------------------------------- segmented reduce
 class _SegReduceFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device_of
     def forward(ctx, msg, rowptr, perm, op):
         _need_cuda(msg, rowptr)
         msg = _c(msg)
@@ -387,6 +401,7 @@ class _SegReduceFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_device_of
     def backward(ctx, dout):
         msg, out, rowptr, perm = ctx.saved_tensors
         dout = _c(dout)

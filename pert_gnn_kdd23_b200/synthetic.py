@@ -178,8 +178,9 @@ def _powerlaw_nodes(rng, lo=20, hi=500, alpha=1.5):
     return int((a - u * (a - b)) ** (-1.0 / alpha))
 
 
-def make_data_list(cfg_id, num_graphs=None, seed=None, patterns=1, edge_attr_cols=2):
-    """List of ``Data`` for one BASELINE config; seed defaults to 1000+cfg_id."""
+def make_data_list(cfg_id, num_graphs=None, seed=None, patterns=1, edge_attr_cols=2, jitter=0.0):
+    """List of ``Data`` for one BASELINE config; seed defaults to 1000+cfg_id.  ``jitter`` j draws every graph's node
+    count uniformly from nodes*(1 +- j) (edges scale with it): BASELINE says "~200 nodes / ~600 edges"."""
     c = CONFIGS[cfg_id]
     rng = np.random.default_rng(1000 + cfg_id if seed is None else seed)
     out = []
@@ -190,5 +191,60 @@ def make_data_list(cfg_id, num_graphs=None, seed=None, patterns=1, edge_attr_col
             L = int(min(10, max(3, round(math.log2(n)))))
         else:
             n, m, L = c["nodes"], c["edges"], c["levels"]
+            if jitter > 0:
+                n = max(2, int(round(n * (1.0 + jitter * (2.0 * rng.random() - 1.0)))))
+                m = int(round(n * c["edges"] / c["nodes"]))
         out.append(make_graph(rng, n, m, L, patterns=patterns, edge_attr_cols=edge_attr_cols))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Synthetic "processed/" artefacts in the reference's own schema (what preprocess.py:378-381 writes and pert_gnn.py:
+# 297-305 loads): the inputs of get_entry_data / get_data_list (pert_gnn.py:134-188).  Used to run the reference's
+# own sample assembly + train/test loop (oracle/gen_golden_loop.py -> tests/golden/ref_loop.npz) and, with the same
+# seed, the device-side pattern store (store.py).
+def make_trace_artifacts(seed=7, n_ms=48, n_patterns=14, n_entries=6, n_traces=72, n_timestamps=5, n_if=32, n_rpc=6,
+                         nodes=(5, 40), resource_frac=0.7, y_max=10):
+    """-> dict(runtime2graph, entry2runtimes, tr2data, resource_index [(timestamp, msname)], resource_values [R,8],
+    n_ms, n_if, n_rpc).
+      runtime2graph[rt] = {edge_index [2,e] i64, edge_attr [e,4] i64, ms_id [n,1] i64, num_nodes int, node_depth [n,1] i64}
+      entry2runtimes[entry] = {rt: prob}        (probabilities of an entry's runtime patterns sum to 1)
+      tr2data[trace] = {entry_id int, timestamp int, y 0-dim i64 tensor}
+    Microservice ids repeat inside a pattern (PERT graphs have several stage nodes per microservice), which exercises
+    the last-occurrence rule of the reference's feature join (pert_gnn.py:54-65)."""
+    rng = np.random.default_rng(seed)
+    runtime2graph = {}
+    for rt in range(n_patterns):
+        n = int(rng.integers(nodes[0], nodes[1] + 1))
+        m = min(3 * n, n * (n - 1) // 2)
+        L = int(min(6, max(2, round(math.log2(n)))))
+        ei, _ = random_dag(rng, n, m, L)
+        e = ei.shape[1]
+        ea = np.stack([rng.integers(0, n_if, e), rng.integers(0, n_rpc, e), rng.integers(0, 2, e),
+                       rng.integers(0, 2, e)], axis=1).astype(np.int64)
+        ms = rng.integers(0, n_ms, size=(n, 1)).astype(np.int64)
+        if n >= 4:
+            ms[n - 1, 0] = ms[0, 0]                     # guaranteed duplicate microservice inside the pattern
+        runtime2graph[100 + rt] = {
+            "edge_index": torch.from_numpy(ei), "edge_attr": torch.from_numpy(ea), "ms_id": torch.from_numpy(ms),
+            "num_nodes": n, "node_depth": torch.from_numpy(_node_depth(bfs_min_depth(ei, n, 0))),
+        }
+    rts = list(runtime2graph.keys())
+    entry2runtimes = {}
+    for entry in range(n_entries):
+        k = int(rng.integers(1, 4))
+        chosen = [int(x) for x in rng.choice(rts, size=k, replace=False)]
+        p = rng.random(k) + 0.2
+        p = p / p.sum()
+        entry2runtimes[entry] = {rt: float(pp) for rt, pp in zip(chosen, p)}
+    timestamps = [int(60000 * (t + 1)) for t in range(n_timestamps)]
+    tr2data = {}
+    for tr in range(n_traces):
+        tr2data[f"trace{tr:04d}"] = {"entry_id": int(rng.integers(0, n_entries)),
+                                     "timestamp": int(timestamps[int(rng.integers(0, n_timestamps))]),
+                                     "y": torch.tensor(int(rng.integers(1, y_max)))}
+    with_res = np.sort(rng.choice(n_ms, size=max(1, int(resource_frac * n_ms)), replace=False))
+    index = [(t, int(ms)) for t in timestamps for ms in with_res]       # every resourced ms has every timestamp
+    values = rng.random((len(index), N_FEAT - 1)).astype(np.float64)     # read back from CSV as float64
+    return {"runtime2graph": runtime2graph, "entry2runtimes": entry2runtimes, "tr2data": tr2data,
+            "resource_index": index, "resource_values": values, "n_ms": n_ms, "n_if": n_if, "n_rpc": n_rpc}

@@ -45,6 +45,21 @@ class FlatParams:
             off += al(k)
         self.params = params
         self.numel = n
+        # ONE FlatParams per module: model.engine() adopts this one instead of re-pointing p.data into a second flat
+        # buffer (which would silently detach an optimizer built over this one)
+        if isinstance(module, torch.nn.Module):
+            module.__dict__["_flat_params"] = self
+
+    @property
+    def device(self):
+        return self.flat.device
+
+    def owns(self, module):
+        """True while every trainable parameter of ``module`` is still a view into this flat buffer."""
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        ps = [p for p in module.parameters() if p.requires_grad]
+        return len(ps) == len(self.params) and all(lo <= p.data_ptr() < hi for p in ps)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -60,9 +75,14 @@ class FusedAdam:
         self.v = torch.zeros_like(flat.flat)
         self.t = 0
 
+    @property
+    def device(self):
+        return self.fp.flat.device
+
     def zero_grad(self, set_to_none=False):
         self.fp.zero_grad()
 
+    @_lib.on_device_of
     def step(self, grad_scale=1.0):
         self.t += 1
         _lib.call("pert_adam_step", _lib.ptr(self.fp.flat), _lib.ptr(self.fp.grad), _lib.ptr(self.m),
@@ -138,6 +158,7 @@ class PeerAdam(FusedAdam):
         self._xbufs = (ctypes.c_void_p * self.world)(*ptrs)
         dist.barrier(group=group)      # every rank has mapped every buffer before the first step touches them
 
+    @_lib.on_device_of
     def step(self, grad_scale=1.0):
         if self.world == 1:
             return super().step(grad_scale)
@@ -184,21 +205,55 @@ class DataParallel:
         return 1.0 / self.world
 
 
+    def all_reduce_module_grads(self, model):
+        """Averages the gradients ATTACHED to the parameters (``p.grad``) over the ranks -- the torch-optimizer branch
+        of ``train_step``: ``torch.optim``'s ``zero_grad()`` defaults to ``set_to_none=True``, so the views FlatParams
+        bound to ``fp.grad`` are gone and autograd installs views of the engine's last gradient buffer instead.  One
+        all-reduce of that buffer when every gradient is a view of it, else flatten -> reduce -> scatter back."""
+        if self.world <= 1:
+            return
+        gs = [p.grad for p in model.parameters() if p.grad is not None]
+        if not gs:
+            return
+        gb = getattr(getattr(model, "_engine", None), "last_grad_buffer", None)
+        if gb is not None:
+            lo, hi = gb.data_ptr(), gb.data_ptr() + gb.numel() * gb.element_size()
+            if all(lo <= g.data_ptr() < hi for g in gs):
+                dist.all_reduce(gb, op=dist.ReduceOp.SUM, group=self.group)
+                gb.mul_(1.0 / self.world)
+                return
+        flat = torch.cat([g.reshape(-1) for g in gs])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.mul_(1.0 / self.world)
+        o = 0
+        for g in gs:
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()
+
+
 def train_step(model, optimizer, data, tau=0.5, dp: DataParallel | None = None):
     """One iteration of the loop body of reference pert_gnn.py:231-247 on a device-resident Batch.
     Returns the (device) loss tensor; no host sync."""
+    fused = isinstance(optimizer, FusedAdam)
+    if fused and hasattr(model, "engine"):
+        # the model must read the SAME flat buffer the optimizer updates, and its p.grad must be the views of fp.grad
+        eng = model.engine(optimizer.fp)
+        lo, hi = optimizer.fp.grad.data_ptr(), optimizer.fp.grad.data_ptr() + optimizer.fp.grad.numel() * 4
+        for p in optimizer.fp.params:
+            if p.grad is None or not (lo <= p.grad.data_ptr() < hi):
+                base = optimizer.fp.flat.data_ptr()
+                o = (p.data_ptr() - base) // 4
+                p.grad = optimizer.fp.grad[o:o + p.numel()].view_as(p)
     optimizer.zero_grad()
     global_pred, _ = model(*model_inputs(data))
     loss = torch_quantile_loss(data.y.float(), global_pred.flatten(), tau)
     loss.backward()
-    if isinstance(optimizer, FusedAdam):
+    if fused:
         scale = dp.all_reduce_grads(optimizer) if dp is not None else 1.0
         optimizer.step(grad_scale=scale)
     else:
         if dp is not None:
-            s = dp.all_reduce_grads()
-            if s != 1.0:
-                dp.fp.grad.mul_(s)
+            dp.all_reduce_module_grads(model)
         optimizer.step()
     return loss
 
@@ -214,6 +269,7 @@ def _side_stream(device):
     return st
 
 
+@_lib.on_device_of
 def _fused_fwd_bwd(model, optimizer: FusedAdam, data, tau, index, probe, use_index_cache=True):
     """Device work of one step up to the gradients: (index build) -> zero grads -> engine forward -> pinball loss +
     its gradient -> engine backward into the flat gradient buffer.  Returns (loss [1], index)."""
@@ -280,6 +336,7 @@ class GraphedTrainStep:
         self._seen = {}      # key -> "ran-once" | "failed" | entry dict
         self.capture_error = None
         self.replays = 0
+        self.invalidations = 0
 
     @staticmethod
     def _key(data):
@@ -304,6 +361,12 @@ class GraphedTrainStep:
             if ent == "unseen":
                 self._seen[key] = "ran-once"
             ent = None
+        if isinstance(ent, dict) and ent["ws_gen"] != ent["engine"].ws_generation:
+            # the engine re-allocated its workspace since the capture (a bigger batch came by): the captured kernels
+            # point into freed memory -> drop EVERY graph of that generation and start over on the eager path
+            self._seen = {k: "ran-once" for k in self._seen}
+            self.invalidations += 1
+            ent = None
         if not isinstance(ent, dict):          # eager: first visit, capture failed, or too many keys
             loss, _ = _fused_fwd_bwd(self.model, self.opt, data, self.tau, None, None)
             return self._finish(loss)
@@ -327,7 +390,9 @@ class GraphedTrainStep:
             return None
         n = ops.LAUNCHES["n"] - l0
         ops.LAUNCHES["n"] = l0
-        ent = {"graph": g, "loss": loss, "index": index, "data": data, "launches": n}
+        eng = self.model._engine
+        ent = {"graph": g, "loss": loss, "index": index, "data": data, "launches": n, "engine": eng,
+               "ws_gen": eng.ws_generation, "ws": eng.ws}       # "ws" keeps the captured workspace alive
         self._seen[key] = ent
         return ent
 
@@ -364,12 +429,58 @@ class AsyncLossReader:
         return v
 
 
+class EvalMetrics:
+    """Device-side accumulators of the reference's eval loop (pert_gnn.py:254-294): sum |pred - y|, sum |pred - y| / y
+    and sum of the per-graph pinball terms, kept in three doubles ON THE DEVICE (``pert_eval_metrics``) so that a
+    whole epoch needs ONE D2H read (``result()``) instead of the reference's per-batch syncs."""
+
+    def __init__(self, device, tau=0.5):
+        self.acc = torch.zeros(3, dtype=torch.float64, device=device)
+        self.tau = float(tau)
+        self.count = 0
+
+    @property
+    def device(self):
+        return self.acc.device
+
+    def reset(self):
+        self.acc.zero_()
+        self.count = 0
+
+    @_lib.on_device_of
+    def update(self, y, yhat):
+        y = y.contiguous()
+        yhat = yhat.reshape(-1).contiguous().float()
+        _lib.call("pert_eval_metrics", _lib.ptr(y), _lib.ptr(yhat), self.tau, y.numel(), _lib.ptr(self.acc),
+                  _lib.stream())
+        ops.LAUNCHES["n"] += 1
+        self.count += int(y.numel())
+
+    def result(self):
+        """-> (mae, mape, quantile loss), each divided by the number of graphs seen, like pert_gnn.py:290-294."""
+        a = self.acc.cpu()
+        n = max(self.count, 1)
+        return float(a[0]) / n, float(a[1]) / n, float(a[2]) / n
+
+
 @torch.no_grad()
-def eval_step(model, data, tau=0.5):
-    """Loop body of reference pert_gnn.py:260-289: returns device sums (mae, mape, quantile loss * B)."""
+def eval_step(model, data, tau=0.5, metrics: EvalMetrics | None = None):
+    """Loop body of reference pert_gnn.py:260-289 on a device-resident Batch: engine forward (eval mode: BatchNorm
+    running statistics), then the three sums on the device.  With ``metrics`` the sums are accumulated there and
+    nothing is returned to the host; without, returns the device tensor [3] (mae, mape, quantile loss * B)."""
     global_pred, _ = model(*model_inputs(data))
-    pred = global_pred.flatten()
-    mae = (pred - data.y).abs().sum()
-    mape = ((pred - data.y).abs() / data.y).sum()
-    q = torch_quantile_loss(data.y.float(), pred, tau) * data.y.shape[0]
-    return mae, mape, q
+    m = metrics if metrics is not None else EvalMetrics(global_pred.device, tau)
+    m.update(data.y, global_pred)
+    return m.acc if metrics is None else None
+
+
+@torch.no_grad()
+def evaluate(model, loader, device, tau=0.5):
+    """reference ``test(loader)`` (pert_gnn.py:254-294): model.eval(), every batch through eval_step, one read-back."""
+    was_training = model.training
+    model.eval()
+    m = EvalMetrics(device, tau)
+    for data in loader:
+        eval_step(model, data.to(device), tau, m)
+    model.train(was_training)
+    return m.result()
