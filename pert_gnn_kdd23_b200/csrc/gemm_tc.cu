@@ -1,8 +1,7 @@
 // Tensor-core path of the dense node linears: tcgen05.mma kind::tf32 with 3xTF32 split accumulation.
 //
 // The linears need fp32-level accuracy (1e-4 after 3-5 layers + BatchNorm), which single-pass TF32 (10-bit
-// mantissa) does not give.  Every fp32 operand x is split exactly into hi = x & 0xffffe000 (a tf32 value) and
-// lo = x - hi; the product is accumulated in fp32 (TMEM) as  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is
+// mantissa) does not give.  Every fp32 operand x is split into hi = nearest tf32 of x and lo = x - hi (see tf32_hi); the product is accumulated in fp32 (TMEM) as  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is
 // ~2^-22 relative), three MMAs per K-step on the 5th-generation tensor cores (tests: test_linear_* at 2e-6).
 //
 // Operand staging (validated by csrc/dev/umma_probe*.cu on B200):
@@ -98,7 +97,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+// Round-to-nearest split with integer ops: hi = (bits + 0x1000) & 0xffffe000 (nearest tf32, ties away from zero; two
+// full-rate ALU instructions -- cvt.rna.tf32.f32 runs on the quarter-rate conversion pipe and cost the converter
+// warps 8 us per weight-gradient launch at cfg2), lo = x - hi (exact in fp32, |lo| <= 2^-11 |x|, either sign; the
+// tensor core drops its low 13 bits: <= 2^-21 |x|, sign-symmetric).  A truncating hi (x & 0xffffe000) makes lo
+// one-signed and the dropped bits a one-sided residual that does not average out over 10^4..10^5-term sums.
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
 
 #ifdef PERT_TC_TRACE

@@ -186,9 +186,14 @@ __global__ void k_sort_long(int N, const int* __restrict__ rowptr, const int* __
 __global__ void k_finalize_csr(const int64_t* __restrict__ ei, const int64_t* __restrict__ attr, int attr_cols,
                                int E, int n_if, int n_rpc, const int* __restrict__ perm,
                                int* __restrict__ csr_src, int* __restrict__ csr_if, int* __restrict__ csr_rpc,
-                               int* __restrict__ inv, int* status) {
+                               int* __restrict__ inv, int* status, const int* __restrict__ nvalid) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= E) return;
+  if (p >= *nvalid) {     // edges dropped by the range check (status = PERT_ERR_RANGE): slots past the last segment
+    csr_src[p] = 0;       // hold no edge -- keep them addressable instead of leaving uninitialised ids behind
+    if (attr) { csr_if[p] = 0; csr_rpc[p] = 0; }
+    return;
+  }
   int t = perm[p];
   csr_src[p] = (int)ei[t];
   inv[t] = p;
@@ -206,9 +211,14 @@ __global__ void k_finalize_csr(const int64_t* __restrict__ ei, const int64_t* __
 
 __global__ void k_finalize_csc(const int64_t* __restrict__ ei, int E, const int* __restrict__ cperm,
                                const int* __restrict__ inv, int* __restrict__ csc_pos,
-                               int* __restrict__ csc_dst) {
+                               int* __restrict__ csc_dst, const int* __restrict__ nvalid) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= E) return;
+  if (c >= *nvalid) {
+    csc_pos[c] = 0;
+    csc_dst[c] = 0;
+    return;
+  }
   int t = cperm[c];
   csc_pos[c] = inv[t];
   csc_dst[c] = (int)ei[(size_t)E + t];
@@ -385,8 +395,8 @@ int pert_build_index(const int64_t* edge_index, const int64_t* edge_attr, int at
   k_sort_long<<<PERT_NUM_SMS, 256, 0, st>>>(N, rowptr, colptr, slot_csr, slot_csc, perm, cperm, long_list,
                                             long_count);
   k_finalize_csr<<<pert_cdiv(E, T), T, 0, st>>>(edge_index, edge_attr, attr_cols, E, n_if, n_rpc, perm, csr_src,
-                                                csr_if, csr_rpc, inv, status);
-  k_finalize_csc<<<pert_cdiv(E, T), T, 0, st>>>(edge_index, E, cperm, inv, csc_pos, csc_dst);
+                                                csr_if, csr_rpc, inv, status, rowptr + N);
+  k_finalize_csc<<<pert_cdiv(E, T), T, 0, st>>>(edge_index, E, cperm, inv, csc_pos, csc_dst, rowptr + N);
   PERT_LAUNCH_CHECK();
   return PERT_OK;
 }

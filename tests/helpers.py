@@ -94,5 +94,18 @@ def assert_grads_close(named_c, named_o, rtol, n_convs=None):
         if is_structural_zero_grad(n, n_convs):
             assert float(p.grad.abs().max()) <= 1e-5 * scale, f"grad {n} should be ~0"
             assert float(ref.abs().max()) <= 1e-5 * scale
+        elif n.endswith("lin_key.weight"):
+            # small BY CANCELLATION: the softmax is shift invariant (sum_t ds_t = 0 per target), so sum_j dk_j = 0 and
+            # dW_k = sum_j dk_j (x_j - mean)^T is 10-100x below its sibling dW_q while each of its 10^4..10^5 terms is
+            # not.  fp32 FMA sums (the oracle, cuBLAS sgemm) round to nearest and their error random-walks; the tcgen05
+            # accumulator truncates, so its error is a (tiny) fraction of sum |terms| -- 3e-3 of this tensor at cfg3-5
+            # (DESIGN.md section 6).  Judged element-wise against the query-gradient scale of the same layer.
+            sib = po[n.replace("lin_key", "lin_query")].grad
+            floor = sib.double().pow(2).mean().sqrt()
+            a, b = p.grad.detach().double().cpu(), ref.detach().double().cpu()
+            e = float(((a - b).abs() / (b.abs() + floor)).max())
+            _log(f"grad {n} (vs query-gradient scale)", a, b, e, rel_err(a, b))
+            assert e <= rtol, f"grad {n}: {e:.3e} > {rtol:.1e} relative to the lin_query gradient scale"
+            assert rel_err(a, b) <= 2e-2, f"grad {n}: norm-wise {rel_err(a, b):.3e}"
         else:
             assert_close(p.grad, ref, rtol=rtol, what=f"grad {n}")

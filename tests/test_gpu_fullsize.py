@@ -4,8 +4,8 @@
     fused bias column sums; only dispatched for M >= 1024 / R >= 4096) at M, R in {4096, 51200, 102400} x H in {64,128};
   * the whole model (outputs, loss, every gradient, BN statistics) on the FULL cfg2 / cfg3 / cfg5 batches and a cfg4
     per-GPU shard, against the CPU oracle.
-Bars: max bit-exact; sums / model 1e-4 element-wise (tests/helpers.py:elem_err); GEMMs 2e-6 norm-wise + 1e-5
-element-wise against fp64."""
+Bars: max bit-exact; sums / model 1e-4 element-wise (tests/helpers.py:elem_err); GEMMs 2e-6 (K <= 144) .. 8e-6
+(K = 512) norm-wise and 5x that element-wise, against fp64."""
 import math
 
 import pytest
@@ -91,8 +91,11 @@ def _planes_case(M, K, H, seed):
     planes = ops.linear(xc, Wc, bc, out_blocks=4)
     gx, gW, gb = torch.autograd.grad(planes, (xc, Wc, bc), g.cuda())
     tag = f"M={M} K={K} H={H}"
-    for got, want, what, tol in ((planes.permute(1, 0, 2).reshape(M, 4 * H), ref, "planes", 2e-6), (gx, rx, "dX", 2e-6),
-                                 (gW, rW, "dW4", 2e-5), (gb, rb, "db4", 2e-5)):
+    # bars (norm-wise, against fp64): the tcgen05 kind::tf32 accumulator truncates (round toward zero) on every MMA, so
+    # the error grows with the number of accumulation steps 3*K/8 (measured r2: 6e-7 at K=64, 2.5e-6 at K=256, 5e-6 at
+    # K=512 -- DESIGN.md section 3); planes: K <= 144; dX: K = 4H; dW4: rows / CTA
+    for got, want, what, tol in ((planes.permute(1, 0, 2).reshape(M, 4 * H), ref, "planes", 2e-6),
+                                 (gx, rx, "dX", 4e-6 if H <= 64 else 8e-6), (gW, rW, "dW4", 2e-5), (gb, rb, "db4", 2e-5)):
         assert_close(got, want, rtol=tol, what=f"{what} {tag}", norm_only=True)
         assert_close(got, want, rtol=5 * tol, what=f"{what} {tag} (element-wise)")
 
