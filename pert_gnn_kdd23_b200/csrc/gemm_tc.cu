@@ -143,6 +143,7 @@ struct NtArgs {
   int ldc, c_cb;
   long long c_cbs;
   int M, Nc, K, BN, relu;
+  int reduce;          // TMA kernel: leave through cp.reduce.async.bulk (+=) instead of a plain store
   unsigned int* ctr;   // this launch's ticket counters (one per blockIdx.y), see ticket_slot()
 };
 
@@ -670,7 +671,9 @@ struct TnTmaBars {
   int ring_meta[RING_MAX], op_meta[2];
 };
 
-template <int GMAX>   // B-converter items (row quad x 32-column group) per warp: 4 * ceil(NcP / 32)
+// GMAX: B-converter items (row quad x 32-column group) per warp = ceil((RCT / 4) * ceil(NcP / 32) / 4);
+// RCT: reduction rows per chunk (64; 32 when the 64-row operand + ring stages do not fit next to each other: Nc > 96)
+template <int GMAX, int RCT>
 __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t s_tmem;
@@ -678,11 +681,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   CTA_T(0);
   const int NcP = g.NcP, NS = g.NS;
-  const uint32_t LBO = 128, SBO = (RC / 4) * 128;
-  const size_t op_bytes = (size_t)NcP * RC * 4;           // one of hi / lo of one operand stage
+  const uint32_t LBO = 128, SBO = (RCT / 4) * 128;
+  const size_t op_bytes = (size_t)NcP * RCT * 4;           // one of hi / lo of one operand stage
   unsigned char* ring0 = smem + 4 * op_bytes;
-  const int a_stage = RC * 512;
-  const int ring_bytes = a_stage + RC * g.Nc * 4;
+  const int a_stage = RCT * 512;
+  const int ring_bytes = a_stage + RCT * g.Nc * 4;
   const int m0 = blockIdx.y * 128;
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -724,8 +727,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
         }
         break;
       }
-      const int r0 = (int)c * RC;
-      const int rows = min(RC, g.R - r0);
+      const int r0 = (int)c * RCT;
+      const int rows = min(RCT, g.R - r0);
       unsigned char* sA = ring0 + (size_t)rs * ring_bytes;
       unsigned char* sB = sA + a_stage;
       if (lane == 0) {
@@ -733,11 +736,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
         mbar_arrive_tx(&bars.ring_full[rs], (uint32_t)rows * (uint32_t)(vcols + g.Nc) * 4u);
       }
       __syncwarp();
-      // stage layout: A piece-major [npieces][RC][pw], B [RC][Nc]
+      // stage layout: A piece-major [npieces][RCT][pw], B [RCT][Nc]
       if (g.a_contig) {
         if (lane < npieces && lane * pw < vcols) {
           const int col = m0 + lane * pw;
-          bulk_g2s(sA + (size_t)lane * RC * pw * 4,
+          bulk_g2s(sA + (size_t)lane * RCT * pw * 4,
                    g.A + (size_t)(col / g.a_cb) * g.a_cbs + (col % g.a_cb) + (size_t)r0 * g.lda, rows * pw * 4,
                    &bars.ring_full[rs]);
         }
@@ -746,7 +749,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
           const int p = i / rows, r = i - p * rows;
           const int col = m0 + p * pw;
           if (p * pw < vcols)
-            bulk_g2s(sA + ((size_t)p * RC + r) * pw * 4,
+            bulk_g2s(sA + ((size_t)p * RCT + r) * pw * 4,
                      g.A + (size_t)(col / g.a_cb) * g.a_cbs + (col % g.a_cb) + (size_t)(r0 + r) * g.lda, pw * 4,
                      &bars.ring_full[rs]);
         }
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
     const int mcol = m0 + tid;
     const bool mok = mcol < g.Mc;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const int a_off = (tid / g.pw) * RC * g.pw + (tid % g.pw);   // piece-major stage layout
+    const int a_off = (tid / g.pw) * RCT * g.pw + (tid % g.pw);   // piece-major stage layout
     uint32_t rs = 0, rph = 0, stage = 0, ph = 0;
     int nproc = 0;
     float csum = 0.f;
@@ -773,19 +776,19 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
       const int rows = bars.ring_meta[rs];
       if (rows < 0) break;
       const float* sA = reinterpret_cast<const float*>(ring0 + (size_t)rs * ring_bytes) + a_off;
-      float av[RC];
+      float av[RCT];
 #pragma unroll
-      for (int i = 0; i < RC; ++i) {
+      for (int i = 0; i < RCT; ++i) {
         const float v = sA[i * g.pw];
         av[i] = (mok && i < rows) ? v : 0.f;
       }
 #pragma unroll
-      for (int i = 0; i < RC; ++i) csum += av[i];
+      for (int i = 0; i < RCT; ++i) csum += av[i];
       mbar_wait(&bars.op_empty[stage], ph ^ 1);
       fence_after();
       const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
 #pragma unroll
-      for (int grp = 0; grp < RC / 16; ++grp) {
+      for (int grp = 0; grp < RCT / 16; ++grp) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -793,7 +796,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
           lo[i] = tf32_lo(av[grp * 16 + i], hi[i]);
         }
         tmem_st16(t_hi + grp * 16, hi);
-        tmem_st16(t_hi + RC + grp * 16, lo);
+        tmem_st16(t_hi + RCT + grp * 16, lo);
       }
       tmem_wait_st();
       fence_before();
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
   } else if (warp < 8) {
     // ================= B converters: ring stage [rows, Nc] -> K-major (K = row) hi/lo operand stage =================
     const int w = warp - 4;
-    const int ngrp = (NcP + 31) / 32, items = (RC / 4) * ngrp;
+    const int ngrp = (NcP + 31) / 32, items = (RCT / 4) * ngrp;
     uint32_t rs = 0, rph = 0, stage = 0, ph = 0;
     while (true) {
       mbar_wait(&bars.ring_full[rs], rph);
@@ -889,12 +892,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
         const uint32_t blo0 = bhi0 + (uint32_t)op_bytes;
         const uint32_t t_hi = tmem + A_COL + stage * 128;
 #pragma unroll
-        for (int s = 0; s < RC / 8; ++s) {
+        for (int s = 0; s < RCT / 8; ++s) {
           const uint32_t koff = (uint32_t)s * 2 * LBO;
           const uint64_t bhi = make_desc(bhi0 + koff, LBO, SBO);
           const uint64_t blo = make_desc(blo0 + koff, LBO, SBO);
           mma_ts(tmem + D_COL, t_hi + s * 8, bhi, idesc, (n | s) ? 1u : 0u);
-          mma_ts(tmem + D_COL, t_hi + RC + s * 8, bhi, idesc, 1u);
+          mma_ts(tmem + D_COL, t_hi + RCT + s * 8, bhi, idesc, 1u);
           mma_ts(tmem + D_COL, t_hi + s * 8, blo, idesc, 1u);
         }
         mma_commit(&bars.op_empty[stage]);
@@ -935,6 +938,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int x, int y, int z) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(x),
                "r"(y), "r"(z), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, const void* src, int x, int y, int z) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm),
+               "r"(x), "r"(y), "r"(z), "r"(smem_u32(src))
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -1230,7 +1238,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
           __syncwarp();
           if (lane == 0) {
             const int col = n0 + c0;
-            tma_store_3d(&tmC, slab, col % g.c_cb, row0, col / g.c_cb);
+            if (g.reduce) tma_reduce_add_3d(&tmC, slab, col % g.c_cb, row0, col / g.c_cb);
+            else tma_store_3d(&tmC, slab, col % g.c_cb, row0, col / g.c_cb);
             bulk_commit();
           }
         }
@@ -1303,10 +1312,37 @@ static bool tc_enabled() {
 
 // Returns PERT_ERR_UNSUPPORTED when the shape / layout is outside what the tensor-core kernels handle (the caller
 // then uses the exact-fp32 SIMT kernels of gemm.cu).
+static int gemm_nt_tc_impl(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb,
+                           const float* bias, float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K,
+                           int relu, int reduce, cudaStream_t st);
+
 int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, const float* bias,
                     float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K, int relu,
                     cudaStream_t st) {
   if (!tc_enabled() || M < 1024) return PERT_ERR_UNSUPPORTED;
+  // Deep K over a column-blocked A (the data gradient dX = [dq|dk|dv|ds] . W4 at H = 128: K = 512): the whole [BN, K]
+  // weight block (hi + lo) no longer fits in shared memory next to the ring unless BN is narrowed to 32, which re-reads
+  // A four times.  Instead run ONE PASS PER COLUMN BLOCK (plane): K' = a_cb, B' = the plane's K-slice of the weights
+  // (resident, BN = Nc), the first pass stores, the following ones leave through TMA reduce-add stores
+  // (cp.reduce.async.bulk.tensor .add.f32: the accumulation happens in L2).  A is read once, each accumulator sees
+  // K' / 8 * 3 truncating steps instead of K / 8 * 3 (accuracy), C is written nblocks times.
+  if (tma_enabled() && a_cb > 0 && a_cb < K && K % a_cb == 0 && !relu && a_cb % KC == 0 && Nc <= 128 &&
+      (size_t)Nc * K * 8 + 1024 + 1024 + 2 * 32 * 1024 + 32 * 1024 > 226 * 1024 &&
+      (size_t)Nc * a_cb * 8 + 1024 + 1024 + 2 * 32 * 1024 + 32 * 1024 <= 226 * 1024 && encode_tiled_fn()) {
+    const int nb = K / a_cb;
+    for (int p = 0; p < nb; ++p) {
+      int rc = gemm_nt_tc_impl(A + (size_t)p * a_cbs, lda, 0, 0, B + (size_t)p * a_cb, ldb, p == 0 ? bias : nullptr, C,
+                               ldc, c_cb, c_cbs, M, Nc, a_cb, 0, p > 0 ? 1 : 0, st);
+      if (rc != PERT_OK) return p == 0 ? rc : (rc == PERT_ERR_UNSUPPORTED ? PERT_ERR_BADARG : rc);
+    }
+    return PERT_OK;
+  }
+  return gemm_nt_tc_impl(A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, M, Nc, K, relu, 0, st);
+}
+
+static int gemm_nt_tc_impl(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb,
+                           const float* bias, float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K,
+                           int relu, int reduce, cudaStream_t st) {
   if (a_cb <= 0) { a_cb = K; a_cbs = 0; }
   if (c_cb <= 0) { c_cb = Nc; c_cbs = 0; }
   if (K % 8 || K > 1024 || Nc % 16 || lda % 4 || ldb % 4 || ldc % 4 || c_cb % 16 || a_cbs % 4 || c_cbs % 4 ||
@@ -1328,7 +1364,7 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
     const size_t need = tma_enabled() ? (size_t)BN * K * 8 + 1024 + 1024 + 2 * 32 * 1024 + 32 * 1024 : smem;
     if (need <= 226 * 1024) break;
   }
-  NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu, nullptr};
+  NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu, reduce, nullptr};
   const int mtiles_all = (int)((M + 127) / 128);
   if (tma_enabled() && nblk <= 8 && encode_tiled_fn()) {
     // TMA-tiled kernel: A as a 2-D tensor [nblocks * row_blk, a_cb] with pitch lda (see k_gemm_nt_tma)
@@ -1378,6 +1414,7 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
       }
     }
   }
+  if (reduce) return PERT_ERR_UNSUPPORTED;   // only the TMA kernel has the reduce-add epilogue
   cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int mtiles = (int)((M + 127) / 128);
@@ -1394,7 +1431,7 @@ int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
   if (!tc_enabled() || R < 4096) return PERT_ERR_UNSUPPORTED;
   if (a_cb <= 0) { a_cb = Mc; a_cbs = 0; }
   if (b_cb > 0 && b_cb < Nc) return PERT_ERR_UNSUPPORTED;   // B must be a plain matrix
-  if (Nc % 4 || Nc > 128 || ldc % 4 || !al16(C)) return PERT_ERR_UNSUPPORTED;
+  if (Nc % 4 || Nc > 160 || ldc % 4 || !al16(C)) return PERT_ERR_UNSUPPORTED;   // D: <= 256 TMEM columns; B-converter items
   const int NcP = (Nc + 15) / 16 * 16;
   const int mblk = (Mc + 127) / 128;
   if (tma_enabled() && mblk <= 8) {
@@ -1402,12 +1439,19 @@ int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
     const int pw = a_cb < 128 ? a_cb : 128;
     const bool ok = pw >= 4 && 128 % pw == 0 && a_cb % pw == 0 && Mc % pw == 0 && lda % 4 == 0 && a_cbs % 4 == 0 &&
                     ldb % 4 == 0 && al16(A) && al16(B);
-    const size_t op = (size_t)NcP * RC * 4 * 2 * 2;
-    const size_t ring = (size_t)RC * 512 + (size_t)RC * Nc * 4;
-    int NS = (int)((226 * 1024 - op) / ring);
+    // chunk depth: 64 reduction rows when two operand stages + >= 2 ring stages fit, else 32 (H = 128: Nc = 128 / 144)
+    int rc = 64;
+    size_t op = 0, ring = 0;
+    int NS = 0;
+    for (; rc >= 32; rc >>= 1) {
+      op = (size_t)NcP * rc * 4 * 2 * 2;
+      ring = (size_t)rc * 512 + (size_t)rc * Nc * 4;
+      NS = op < 226 * 1024 ? (int)((226 * 1024 - op) / ring) : 0;
+      if (NS >= 2) break;
+    }
     if (NS > RING_MAX) NS = RING_MAX;
     if (ok && NS >= 2) {
-      const int nchunks = (int)((R + RC - 1) / RC);
+      const int nchunks = (int)((R + rc - 1) / rc);
       int gx = PERT_NUM_SMS / mblk;
       if (gx < 1) gx = 1;
       if (gx > nchunks) gx = nchunks;
@@ -1415,13 +1459,18 @@ int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
                   (int)R,   Mc,  Nc,   NcP,   nchunks, NS, pw, lda == pw ? 1 : 0, ldb == Nc ? 1 : 0, ticket_slot()};
       if (!g.ctr) return (int)cudaGetLastError();
       const size_t smem = op + ring * NS;
-      auto kern = NcP <= 64 ? k_gemm_tn_tma<8> : (NcP <= 96 ? k_gemm_tn_tma<12> : k_gemm_tn_tma<16>);
+      const int ngrp = (NcP + 31) / 32;
+      void (*kern)(TnTmaArgs) = nullptr;
+      if (rc == 64) kern = ngrp <= 2 ? k_gemm_tn_tma<8, 64> : (ngrp == 3 ? k_gemm_tn_tma<12, 64> : k_gemm_tn_tma<16, 64>);
+      else kern = ngrp <= 4 ? k_gemm_tn_tma<8, 32> : k_gemm_tn_tma<10, 32>;
+      if (rc == 64 && ngrp > 4) return PERT_ERR_UNSUPPORTED;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       kern<<<dim3(gx, mblk), TMA_THREADS, smem, st>>>(g);
       return PERT_OK;
     }
   }
+  if (Nc > 128) return PERT_ERR_UNSUPPORTED;   // the LDG-fed kernel below is instantiated for Nc <= 128 only
   int splits = PERT_NUM_SMS / mblk;
   if (splits < 1) splits = 1;
   int rps = (int)((R + splits - 1) / splits);

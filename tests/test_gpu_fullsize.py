@@ -95,7 +95,7 @@ def _planes_case(M, K, H, seed):
     # the error grows with the number of accumulation steps 3*K/8 (measured r2: 6e-7 at K=64, 2.5e-6 at K=256, 5e-6 at
     # K=512 -- DESIGN.md section 3); planes: K <= 144; dX: K = 4H; dW4: rows / CTA
     for got, want, what, tol in ((planes.permute(1, 0, 2).reshape(M, 4 * H), ref, "planes", 2e-6),
-                                 (gx, rx, "dX", 4e-6 if H <= 64 else 8e-6), (gW, rW, "dW4", 2e-5), (gb, rb, "db4", 2e-5)):
+                                 (gx, rx, "dX", 4e-6 if H <= 64 else 8e-6), (gW, rW, "dW4", 3e-5), (gb, rb, "db4", 2e-5)):
         assert_close(got, want, rtol=tol, what=f"{what} {tag}", norm_only=True)
         assert_close(got, want, rtol=5 * tol, what=f"{what} {tag} (element-wise)")
 
