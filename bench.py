@@ -260,8 +260,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "DAGs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg{cfg}: {B} DAGs x {c['nodes']} nodes/{c['edges']} edges, {c['hidden']}-dim, "
-                               f"num_layers={c['num_layers']}", "global_batch": B},
+        "config": {"workload": _workload_string(cfg, B_full), "global_batch": B_full, "graphs_per_timed_step": B},
         "cpu_baseline": {"value": val, "unit": "DAGs/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} train steps (fwd+bwd+Adam), each on {B} of the workload's {B_full} "
                                    f"graphs; {cores} of {cores_avail} host threads (fastest of a calibration sweep); "
@@ -319,7 +318,7 @@ def ncu_traffic(kernel):
     if _BENCH_CFG != 2:
         return None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")) as f:
             return json.load(f).get(kernel)
     except (OSError, ValueError):
         return None
@@ -382,14 +381,85 @@ def scatter_max_bench(batch_dev, H, peak_gbs, iters=40):
             "achieved_single_launch": bytes_alg / t_single / 1e9, "shape": {"E": E, "N": N, "H": H}}
 
 
+def _workload_string(cfg, B):
+    """config.workload -- the SAME string in both arms (the driver compares them)."""
+    from pert_gnn_kdd23_b200.synthetic import CONFIGS
+
+    c = CONFIGS[cfg]
+    nodes = c["nodes"] if c["nodes"] is not None else "20-500 (power law)"
+    edges = c["edges"] if c["edges"] is not None else "3x nodes"
+    return (f"cfg{cfg}: {B} DAGs x {nodes} nodes/{edges} edges per GPU, {c['hidden']}-dim, "
+            f"num_layers={c['num_layers']}, fwd+bwd+Adam")
+
+
+def timed_blocks(run_block, K, barrier, world, dev, min_region_s=0.6, max_blocks=300, min_blocks=5):
+    """Times R blocks of EXACTLY K steps each (barrier + synchronize on both sides of every block, CUDA events around
+    it, max over ranks per block) and returns (median seconds per block, list of block seconds).  R is chosen so that
+    the whole timed region lasts >= min_region_s: a 13 ms region (20 steps of 0.67 ms) gives NVML no samples and lets
+    one scheduler hiccup move the headline by percents."""
+    import torch.distributed as dist
+
+    def one():
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_block(K)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) * 1e-3
+
+    est = one()
+    if world > 1:
+        t = torch.tensor([est], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        est = float(t)
+    R = int(min(max_blocks, max(min_blocks, -(-min_region_s // max(est, 1e-6)))))
+    secs = [one() for _ in range(R)]
+    if world > 1:
+        t = torch.tensor(secs, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = t.tolist()
+    return statistics.median(secs), secs
+
+
+def first_step_parity(model, batch_host, dev, tau=0.5):
+    """The step's first forward against the oracle bench.py already ships for its CPU arm: same weights, same batch,
+    training-mode BatchNorm; asserts predictions (element-wise) and loss within 1e-4 before anything is timed."""
+    import copy
+
+    from oracle.model_oracle import OracleSAGEDeterministic, torch_quantile_loss
+    from pert_gnn_kdd23_b200.synthetic import model_args
+    from pert_gnn_kdd23_b200.train import model_inputs
+
+    m = copy.deepcopy(model)
+    oracle = OracleSAGEDeterministic(*model_args(_BENCH_CFG))
+    oracle.load_state_dict({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    oracle.train()
+    m.train()
+    with torch.no_grad():
+        go, _ = oracle(*model_inputs(batch_host))
+        gc, _ = m(*model_inputs(batch_host.to(dev)))
+    lo = float(torch_quantile_loss(batch_host.y.float(), go.flatten(), tau))
+    lc = float(torch_quantile_loss(batch_host.y.float().to(dev), gc.flatten(), tau))
+    d = (gc.cpu().double() - go.double()).abs()
+    rms = go.double().pow(2).mean().sqrt()
+    elem = float((d / (go.double().abs() + rms)).max())
+    out = {"loss_cuda": lc, "loss_oracle": lo, "loss_rel_err": abs(lc - lo) / max(abs(lo), 1e-30),
+           "pred_elementwise_rel_err": elem, "bar": 1e-4}
+    assert out["loss_rel_err"] <= 1e-4 and elem <= 1e-4, f"first-step parity vs the oracle failed: {out}"
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
 
     from pert_gnn_kdd23_b200 import ops
+    from pert_gnn_kdd23_b200.data import DevicePrefetcher
+    from pert_gnn_kdd23_b200.engine import PertProbe
     from pert_gnn_kdd23_b200.model import SAGEDeterministic
     from pert_gnn_kdd23_b200.synthetic import CONFIGS, model_args
-    from pert_gnn_kdd23_b200.train import (DataParallel, FlatParams, FusedAdam, fused_train_step, model_inputs,
-                                           torch_quantile_loss)
+    from pert_gnn_kdd23_b200.train import (AsyncLossReader, DataParallel, FlatParams, FusedAdam, GraphedTrainStep,
+                                           fused_train_step, model_inputs, torch_quantile_loss)
 
     train_step = fused_train_step
 
@@ -403,6 +473,33 @@ def run_b200(args, rank, world, local_rank):
     H = c["hidden"]
     peak, peak_kind = _peaks()
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_optimizer(fp):
+        # N > 1: the gradient all-reduce is fused with Adam in one kernel over NVLink peer memory (train.PeerAdam);
+        # PERT_BENCH_PEER=0 (or a failed IPC setup) falls back to one NCCL all_reduce of the flat gradient + fused Adam
+        opt, sync = None, "single GPU: fused Adam"
+        if world > 1 and os.environ.get("PERT_BENCH_PEER", "1") != "0":
+            from pert_gnn_kdd23_b200.train import PeerAdam
+
+            ok = torch.ones(1, device=dev)
+            try:
+                opt = PeerAdam(fp, lr=3e-4)
+                sync = "PeerAdam: gradient all-reduce fused with Adam in one kernel over NVLink peer memory (no NCCL)"
+            except Exception:  # noqa: BLE001
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) == 0.0:
+                opt = None
+        if opt is None:
+            opt = FusedAdam(fp, lr=3e-4)
+            if world > 1:
+                sync = "NCCL all_reduce of the flat gradient + fused Adam"
+        return opt, sync
+
     host_batches = [b.pin_memory() for b in make_batches(cfg, rank, N_ROT)]
     dev_batches = [b.to(dev) for b in host_batches]
     B = host_batches[0].num_graphs
@@ -411,95 +508,68 @@ def run_b200(args, rank, world, local_rank):
 
     torch.manual_seed(0)
     model = SAGEDeterministic(*model_args(cfg)).to(dev)
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        parity = first_step_parity(model, make_batches(cfg, rank, 1)[0], dev)
     fp = FlatParams(model)
-    # N > 1: the gradient all-reduce is fused with Adam in one kernel over NVLink peer memory (train.PeerAdam);
-    # PERT_BENCH_PEER=0 (or a failed IPC setup) falls back to one NCCL all_reduce of the flat gradient + fused Adam
-    opt, grad_sync = None, "single GPU: fused Adam"
-    if world > 1 and os.environ.get("PERT_BENCH_PEER", "1") != "0":
-        from pert_gnn_kdd23_b200.train import PeerAdam
-
-        ok = torch.ones(1, device=dev)
-        try:
-            opt = PeerAdam(fp, lr=3e-4)
-            grad_sync = "PeerAdam: gradient all-reduce fused with Adam in one kernel over NVLink peer memory (no NCCL)"
-        except Exception as e:  # noqa: BLE001
-            ok.zero_()
-            peer_err = repr(e)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok) == 0.0:
-            opt = None
-    if opt is None:
-        opt = FusedAdam(fp, lr=3e-4)
-        if world > 1:
-            grad_sync = "NCCL all_reduce of the flat gradient + fused Adam"
+    opt, grad_sync = make_optimizer(fp)
     dp = DataParallel(fp) if world > 1 else None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- kernel-only arm: inputs resident in HBM -------------------------------------------------
     # The step is replayed from a CUDA graph per resident batch (train.GraphedTrainStep: index build + forward +
     # loss + backward in one cudaGraphLaunch, then the eager all-reduce / Adam); PERT_BENCH_GRAPH=0 times the eager
     # fused step instead.  A key is captured on its second visit, so the warm-up visits every batch at least twice.
-    from pert_gnn_kdd23_b200.train import GraphedTrainStep
-
     use_graph = os.environ.get("PERT_BENCH_GRAPH", "1") != "0"
     gstep = GraphedTrainStep(model, opt, 0.5, dp)
 
     def stepper(d):
         return gstep(d) if use_graph else train_step(model, opt, d, 0.5, dp)
 
-    for i in range(max(args.warmup, 2 * N_ROT)):
-        stepper(dev_batches[i % N_ROT])
+    state = {"i": 0, "loss": None}
+
+    def resident_block(k):
+        for _ in range(k):
+            state["loss"] = stepper(dev_batches[state["i"] % N_ROT])
+            state["i"] += 1
+
+    resident_block(max(args.warmup, 2 * N_ROT))
     barrier()
+    if hasattr(opt, "phase_times_us"):
+        opt.phase_times_us(reset=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # in-step kernel durations: the engine records a caller-created CUDA event pair around ONE kernel family of the
-    # middle layer per step (include/pertgnn.h PertProbe); the families rotate over the timed steps.
-    from pert_gnn_kdd23_b200.engine import PertProbe
+    l0 = ops.LAUNCHES["n"]
+    s0 = state["i"]
+    t_wall = time.perf_counter()
+    secs, blocks = timed_blocks(resident_block, args.steps, barrier, world, dev)
+    t_wall = time.perf_counter() - t_wall
+    launches_per_step = (ops.LAUNCHES["n"] - l0) / max(1, state["i"] - s0)
+    clocks = sampler.stop() if rank == 0 else None
+    peer_phases = opt.phase_times_us(reset=True) if hasattr(opt, "phase_times_us") and world > 1 else None
+    loss = state["loss"]
+    value = world * B * args.steps / secs
 
+    # ---- in-step kernel durations: the engine records a caller-created CUDA event pair around ONE kernel family of
+    # the middle layer per step (include/pertgnn.h PertProbe), in eagerly issued steps right after the timed region
+    # (events inside a replayed graph cannot be timed)
     n_convs = len(model.convs)
     fams = ["tconv_bwd", "tconv_fwd", "gemm_fwd", "gemm_wgrad", "gemm_dgrad"]
-    l0 = ops.LAUNCHES["n"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        loss = stepper(dev_batches[i % N_ROT])
-    e1.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    launches = ops.LAUNCHES["n"] - l0
-    secs = e0.elapsed_time(e1) * 1e-3
-    clocks = sampler.stop() if rank == 0 else None
-    # probe phase (not timed as a whole): the same train steps issued eagerly so that the engine can bracket one
-    # kernel family per step with CUDA events (events inside a replayed graph cannot be timed)
     n_probe = max(2 * len(fams), min(args.steps, 40))
     probes = [PertProbe.create(fams[i % len(fams)], min(1, n_convs - 1)) for i in range(n_probe)]
     for i in range(n_probe):
         train_step(model, opt, dev_batches[i % N_ROT], 0.5, dp, probe=probes[i])
     barrier()
     kern = {}
-    launches_per_step = {"tconv_bwd": n_convs, "tconv_fwd": n_convs, "gemm_fwd": n_convs, "gemm_wgrad": n_convs,
-                         "gemm_dgrad": n_convs}
     for i, pr in enumerate(probes):
         kern.setdefault(fams[i % len(fams)], []).append(pr.elapsed_ms())
         pr.destroy()
-    if world > 1:
-        t = torch.tensor([secs], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs = float(t)
-    value = world * B * args.steps / secs
 
     # ---- end-to-end arm: the reference's loop body with host buffers ------------------------------
     model2 = SAGEDeterministic(*model_args(cfg)).to(dev)
     model2.load_state_dict(model.state_dict())
     opt2 = torch.optim.Adam(model2.parameters(), lr=3e-4)
-    if world > 1:
-        fp2 = None
+    dp2 = DataParallel(FlatParams(model2, bind_grads=False)) if world > 1 else None
 
     def e2e_step(hb):
         data = hb.to(dev, non_blocking=True)
@@ -507,59 +577,34 @@ def run_b200(args, rank, world, local_rank):
         gp, _ = model2(*model_inputs(data))
         l = torch_quantile_loss(data.y.float(), gp.flatten(), 0.5)
         l.backward()
-        if world > 1:
-            # the engine hands autograd ONE flat gradient buffer (every p.grad is a view of it): one all-reduce
-            gs = [p.grad for p in model2.parameters() if p.grad is not None]
-            gb = getattr(model2._engine, "last_grad_buffer", None)
-            if gb is not None:
-                lo, hi = gb.data_ptr(), gb.data_ptr() + gb.numel() * gb.element_size()
-            if gb is not None and all(lo <= g.data_ptr() < hi for g in gs):
-                dist.all_reduce(gb)
-                gb.div_(world)
-            else:                              # autograd copied the views: flatten, reduce, scatter back
-                flat = torch.cat([g.reshape(-1) for g in gs])
-                dist.all_reduce(flat)
-                flat.div_(world)
-                o = 0
-                for g in gs:
-                    g.copy_(flat[o:o + g.numel()].view_as(g))
-                    o += g.numel()
+        if dp2 is not None:
+            dp2.all_reduce_module_grads(model2)       # ONE all-reduce of the engine's flat gradient buffer
         opt2.step()
         return l.item()                       # D2H read of the step's result, like pert_gnn.py:248
 
-    for i in range(args.warmup):
-        e2e_step(host_batches[i % N_ROT])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        e2e_step(host_batches[i % N_ROT])
-    e1.record()
-    barrier()
-    secs2 = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        t = torch.tensor([secs2], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs2 = float(t)
+    st2 = {"i": 0}
+
+    def dropin_block(k):
+        for _ in range(k):
+            e2e_step(host_batches[st2["i"] % N_ROT])
+            st2["i"] += 1
+
+    dropin_block(args.warmup)
+    secs2, _ = timed_blocks(dropin_block, args.steps, barrier, world, dev, min_region_s=0.3, max_blocks=40)
     e2e_val = world * B * args.steps / secs2
 
-    # ---- end-to-end through the fused public API: pinned host batch -> device -> fused_train_step -> loss.item()
-    # every step's inputs still cross PCIe inside the timed region (one pinned slab -> one H2D copy per step), but the
-    # copy of batch i+1 is issued on a side stream while batch i trains (data.DevicePrefetcher); the loss is read back
-    # (D2H, 4 bytes) every step like pert_gnn.py:248.
-    from pert_gnn_kdd23_b200.data import DevicePrefetcher
-
+    # ---- end-to-end through the fused public API: pinned host batch -> device -> graph-replayed step -> loss read-back
+    # every step's inputs cross PCIe inside the timed region (one pinned slab -> one H2D copy per step), issued on a
+    # side stream while the previous batch trains (data.DevicePrefetcher); every step's loss is read back (4 B D2H into
+    # pinned memory + event, train.AsyncLossReader), consumed one step later so the GPU never idles on the read-back
     pf_ring = DevicePrefetcher([], dev)       # ONE prefetcher: its 3 device slabs (= 3 graph keys) persist across runs
-
-    from pert_gnn_kdd23_b200.train import AsyncLossReader
-
     reader = AsyncLossReader(dev)
+    st3 = {"i": 0}
 
-    def run_fused(nsteps):
-        # every step's loss is read back (4 B D2H into pinned memory + event, train.AsyncLossReader); the host
-        # consumes the value of step i-1 after it has enqueued step i, so the GPU never idles on the read-back
+    def fused_block(nsteps):
         total = 0.0
-        pf_ring.batches = [host_batches[i % N_ROT] for i in range(nsteps)]
+        pf_ring.batches = [host_batches[(st3["i"] + j) % N_ROT] for j in range(nsteps)]
+        st3["i"] += nsteps
         for data in pf_ring:
             v = reader.push(stepper(data))
             if v is not None:
@@ -567,19 +612,12 @@ def run_b200(args, rank, world, local_rank):
         v = reader.flush()
         return total + (v if v is not None else 0.0)
 
-    run_fused(max(args.warmup, 9))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_fused(args.steps)
-    e1.record()
-    barrier()
-    secs3 = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        t = torch.tensor([secs3], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs3 = float(t)
+    fused_block(max(args.warmup, 9))
+    secs3, _ = timed_blocks(fused_block, args.steps, barrier, world, dev)
     e2e_fused_val = world * B * args.steps / secs3
+
+    # ---- BASELINE.json configs[3] (4096 graphs over 8 GPUs = 512 graphs / GPU, 128-dim, 3 layers) beside the headline
+    cfg4 = run_cfg4_block(args, rank, world, dev, barrier, make_optimizer) if (args.cfg == 2 and not args.no_cfg4) else None
 
     if hasattr(opt, "check"):
         opt.check()
@@ -593,8 +631,8 @@ def run_b200(args, rank, world, local_rank):
         "gemm_fwd": 4 * Nn * Kin + 16 * Nn * H, "gemm_dgrad": 4 * Nn * Kin + 16 * Nn * H,
         "gemm_wgrad": 4 * Nn * Kin + 16 * Nn * H,
     }
-    names = {"tconv_fwd": "k_tile_fwd (fused conv forward)",
-             "tconv_bwd": "k_tile_bwd_dst + k_tile_bwd_src (fused conv backward, 2 launches)",
+    names = {"tconv_fwd": "fused conv forward (csrc/tconv_tile.cu)",
+             "tconv_bwd": "fused conv backward: target pass + source pass (csrc/tconv_tile.cu, 2 launches)",
              "gemm_fwd": "k_gemm_nt_tma (node linears, tcgen05 3xTF32, TMA-tiled)",
              "gemm_dgrad": "k_gemm_nt_tma (data gradient)", "gemm_wgrad": "k_gemm_tn_tma (weight + bias gradient)"}
     kernels = {}
@@ -603,15 +641,18 @@ def run_b200(args, rank, world, local_rank):
         if not ts:
             continue
         med = statistics.median(ts)
-        kernels[name] = {"us_per_launch": 1e3 * med, "launches_per_step": launches_per_step[name],
-                         "ms_per_step": med * launches_per_step[name], "samples": len(ts),
+        kernels[name] = {"us_per_launch": 1e3 * med, "launches_per_step": n_convs,
+                         "ms_per_step": med * n_convs, "samples": len(ts),
                          "GBs": alg[name] / (med * 1e-3) / 1e9, "frac_of_hbm_peak": alg[name] / (med * 1e-3) / 1e9 / peak}
     roof = None
     if kernels:
         top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         ach = kernels[top]["GBs"]
         roof = {"kernel": names[top], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": ncu_traffic(top), "peak_source": peak_kind, "algorithmic_bytes": alg[top],
+                "frac": ach / peak, "traffic": ncu_traffic(top),
+                "traffic_source": "committed ncu --set full capture of this command (profiles/r2_traffic.json), "
+                                  "NOT measured in this run; below the algorithmic bytes when outputs stay dirty in L2",
+                "peak_source": peak_kind, "algorithmic_bytes": alg[top],
                 "us_per_launch": kernels[top]["us_per_launch"],
                 "share_of_step": kernels[top]["ms_per_step"] / (1e3 * secs / args.steps),
                 "how": "CUDA event pair recorded by the engine around the launch(es) inside eagerly issued train "
@@ -622,13 +663,16 @@ def run_b200(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "DAGs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg{cfg}: {B} DAGs x {c['nodes']} nodes/{c['edges']} edges per GPU, {H}-dim, "
-                               f"num_layers={c['num_layers']} ({n_convs} TransformerConv), fwd+bwd+Adam",
+        "config": {"workload": _workload_string(cfg, B),
                    "global_batch": world * B, "nodes_per_gpu": Nn, "edges_per_gpu": Ee,
-                   "parallelism": f"dp{world}", "grad_sync": grad_sync,
+                   "convs": n_convs, "parallelism": f"dp{world}", "grad_sync": grad_sync,
                    "step_issue": ("CUDA-graph replay per batch buffer (index build + forward + loss + backward), eager "
                                   f"all-reduce + Adam; {gstep.replays} replays, capture_error={gstep.capture_error}")
                    if use_graph else "eager fused_train_step (5 C calls per step)",
+                   "timing": f"{len(blocks)} blocks of exactly {args.steps} steps, each bracketed by barrier + "
+                             "synchronize and a CUDA event pair, max over ranks per block; value = median block "
+                             f"(min {min(blocks) * 1e3:.3f} / max {max(blocks) * 1e3:.3f} ms per block, timed region "
+                             f"{sum(blocks):.2f} s)",
                    "l2": f"rotating {N_ROT} distinct resident batches; ~{(n_convs * 8 * Nn * H * 4) >> 20} MB of "
                          "activations written+read per step (> 126 MB L2 for cfg2+): no explicit flush in the step "
                          "loop; scatter_max is timed with an explicit 512 MB L2 flush"},
@@ -643,9 +687,66 @@ def run_b200(args, rank, world, local_rank):
                               "the previous step) + train.GraphedTrainStep (graph replay of index build, engine fwd, "
                               "pinball kernel, engine bwd; eager fused Adam) + the loss of EVERY step read back "
                               "(train.AsyncLossReader: 4-byte D2H + event behind each step, consumed one step later)"},
-        "gpu_launches": launches, "wall_s": t_wall, "clocks": clocks, "final_loss": float(loss),
+        "gpu_launches": int(round(launches_per_step * args.steps)),
+        "gpu_launches_how": "kernels launched per step through the C-ABI (counted at every binding call: the engine's "
+                            "launch list mirrored from csrc/engine.cu + index build + loss + Adam) x steps of one block; "
+                            "cross-check: profiles/r2_launches_step.csv (ncu launch list of the same command)",
+        "wall_s": t_wall, "clocks": clocks, "final_loss": float(loss), "parity_first_step": parity,
+        "peer": peer_phases, "cfg4": cfg4,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_cfg4_block(args, rank, world, dev, barrier, make_optimizer):
+    """BASELINE.json configs[3]: the 4096-graph batch sharded data-parallel over 8 GPUs = 512 graphs per GPU, 128-dim,
+    3 layers, gradient all-reduce fused with Adam.  Measured beside the cfg2 headline (which stays the weak-scaling
+    curve): every rank trains on its own 512-graph shard; at N < 8 it is the same per-GPU shard on fewer GPUs."""
+    from pert_gnn_kdd23_b200.model import SAGEDeterministic
+    from pert_gnn_kdd23_b200.synthetic import model_args
+    from pert_gnn_kdd23_b200.train import DataParallel, FlatParams, GraphedTrainStep
+
+    import torch.distributed as dist
+
+    from pert_gnn_kdd23_b200.data import Batch
+    from pert_gnn_kdd23_b200.synthetic import make_data_list
+
+    n_rot, per_gpu = 3, 512
+    batches = []
+    for r in range(n_rot):
+        dl = make_data_list(4, num_graphs=per_gpu, seed=1000 + 4 + 7919 * rank + 131 * r)
+        for d in dl:
+            d._store.pop("level", None)
+            d._store.pop("min_depth", None)
+        batches.append(Batch.from_data_list(dl).pin_memory().to(dev))
+    torch.manual_seed(0)
+    model = SAGEDeterministic(*model_args(4)).to(dev)
+    fp = FlatParams(model)
+    opt, sync = make_optimizer(fp)
+    dp = DataParallel(fp) if world > 1 else None
+    gstep = GraphedTrainStep(model, opt, 0.5, dp)
+    st = {"i": 0}
+
+    def block(k):
+        for _ in range(k):
+            gstep(batches[st["i"] % n_rot])
+            st["i"] += 1
+
+    block(max(3, 2 * n_rot + 1))
+    barrier()
+    if hasattr(opt, "phase_times_us"):
+        opt.phase_times_us(reset=True)
+    K = max(5, min(args.steps, 20))
+    secs, blocks = timed_blocks(block, K, barrier, world, dev, min_region_s=0.4, max_blocks=60)
+    phases = opt.phase_times_us(reset=True) if hasattr(opt, "phase_times_us") and world > 1 else None
+    if hasattr(opt, "check"):
+        opt.check()
+    Nn, Ee = batches[0].x.size(0), batches[0].edge_index.size(1)
+    return {"workload": f"BASELINE configs[3] shard: {per_gpu} DAGs x 200 nodes/600 edges per GPU (4096 over 8 GPUs), "
+                        "128-dim, num_layers=3, fwd+bwd+Adam, resident batches, graph replay",
+            "value": world * per_gpu * K / secs, "unit": "DAGs/s", "global_batch": world * per_gpu,
+            "ms_per_step": 1e3 * secs / K, "steps_per_block": K, "blocks": len(blocks), "nodes_per_gpu": Nn,
+            "edges_per_gpu": Ee, "grad_sync": sync, "peer": phases, "replays": gstep.replays,
+            "capture_error": gstep.capture_error}
 
 
 def main():
@@ -656,6 +757,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cfg", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true")
     args = ap.parse_args()
     global _BENCH_CFG
     _BENCH_CFG = args.cfg

@@ -197,7 +197,10 @@ int pert_peer_close(void* ptr);
 int pert_peer_free(void* ptr);
 int pert_allreduce_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, long long step, float grad_scale, void* const* xbufs, int rank,
-                        int world, int* status, void* stream);
+                        int world, int* status, long long* timing, void* stream);
+/* timing (optional device int64[4]): CTA 0 adds the nanoseconds (%globaltimer) it spent in (0) publishing the gradient
+ * + grid arrival, (1) waiting for the peers' flags -- the slowest rank's skew plus the flag round trip --, (2) the
+ * rank-ordered reduce + Adam, and (3) += 1 per call: the per-phase evidence behind the scaling curve (bench.py `peer`). */
 
 /* ---- whole-model step engine --------------------------------------------------------------------------
  * SAGEDeterministic.forward (model.py:76-114) and its backward as one call each: the same kernels as above,

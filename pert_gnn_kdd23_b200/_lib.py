@@ -52,7 +52,7 @@ SIGNATURES = {
     "pert_peer_open": (I, [P, P]),
     "pert_peer_close": (I, [P]),
     "pert_peer_free": (I, [P]),
-    "pert_allreduce_adam": (I, [P, P, P, P, LL, F, F, F, F, F, LL, F, P, I, I, P, P]),
+    "pert_allreduce_adam": (I, [P, P, P, P, LL, F, F, F, F, F, LL, F, P, I, I, P, P, P]),
     # whole-model engine (first argument: const PertModelDesc*, see engine.py)
     "pert_model_workspace_bytes": (LL, [P, LL, LL, LL]),
     "pert_model_packed_bytes": (LL, [P]),

@@ -144,6 +144,7 @@ struct NtArgs {
   long long c_cbs;
   int M, Nc, K, BN, relu;
   int reduce;          // TMA kernel: leave through cp.reduce.async.bulk (+=) instead of a plain store
+  int kplanes;         // > 1: gridDim.z column blocks of A, each a K-wide GEMM against its own K-slice of B
   unsigned int* ctr;   // this launch's ticket counters (one per blockIdx.y), see ticket_slot()
 };
 
@@ -968,6 +969,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   CTA_T(0);
   const int K = g.K, BN = g.BN;
   const int n0 = blockIdx.y * BN;
+  const int kz = blockIdx.z;                                // K plane (column block of A) of this CTA
+  const int ctr_i = blockIdx.y + gridDim.y * kz;            // ticket counter of this (N block, K plane)
   const uint32_t LBO = 128, SBO = (uint32_t)(K / 4) * 128;
   const int kq = K / 4;
   unsigned char* sBhi = smem;
@@ -1007,9 +1010,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       uint32_t rs = 0, rph = 0;
       int tr_i = 0;
       while (true) {
-        const unsigned int c = atomicAdd(&g.ctr[blockIdx.y], 1u);
+        const unsigned int c = atomicAdd(&g.ctr[ctr_i], 1u);
         if (c >= (unsigned int)mtiles) {
-          if (c == (unsigned int)mtiles + gridDim.x - 1) g.ctr[blockIdx.y] = 0;   // last ticket of the launch
+          if (c == (unsigned int)mtiles + gridDim.x - 1) g.ctr[ctr_i] = 0;   // last ticket of the launch
           mbar_wait(&bars.ring_empty[rs], rph ^ 1);
           bars.ring_meta[rs] = -1;
           mbar_arrive(&bars.ring_full[rs]);
@@ -1018,7 +1021,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         for (int ch = 0; ch < nchunks; ++ch) {
           const int k0 = ch * KC;
           const int kw = min(KC, K - k0);
-          const int x0 = k0 % g.a_cb, y0 = (k0 / g.a_cb) * row_blk + (int)c * 128;
+          const int x0 = k0 % g.a_cb, y0 = (k0 / g.a_cb + kz) * row_blk + (int)c * 128;
           TRACE(0, tr_i, 0);
           mbar_wait(&bars.ring_empty[rs], rph ^ 1);
           TRACE(0, tr_i, 1);
@@ -1102,8 +1105,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const int n = n8l * 8 + nlo, kc = kbl * 4 + klo;
-          v[u] = (b0 + u * 5 < nblk8 && kc < kq && n0 + n < g.Nc) ? ldg4(g.B + (size_t)(n0 + n) * g.ldb + kc * 4)
-                                                                   : f4zero();
+          v[u] = (b0 + u * 5 < nblk8 && kc < kq && n0 + n < g.Nc)
+                     ? ldg4(g.B + (size_t)(n0 + n) * g.ldb + (size_t)kz * K + kc * 4)
+                     : f4zero();
           kbl += 5;
           while (kbl >= kqb) { kbl -= kqb; ++n8l; }
         }
@@ -1127,7 +1131,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
     if (warp == 5) TRACE(5, 0, 2);
     if (tid - 128 < 128) {
       const int c = tid - 128;
-      s_bias[c] = (g.bias && c < BN && n0 + c < g.Nc) ? __ldg(g.bias + n0 + c) : 0.f;
+      s_bias[c] = (g.bias && kz == 0 && c < BN && n0 + c < g.Nc) ? __ldg(g.bias + n0 + c) : 0.f;
     }
     fence_async_smem();
     asm volatile("bar.sync 3, 160;" ::: "memory");
@@ -1314,7 +1318,7 @@ static bool tc_enabled() {
 // then uses the exact-fp32 SIMT kernels of gemm.cu).
 static int gemm_nt_tc_impl(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb,
                            const float* bias, float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K,
-                           int relu, int reduce, cudaStream_t st);
+                           int relu, int reduce, int kplanes, cudaStream_t st);
 
 int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb, const float* bias,
                     float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K, int relu,
@@ -1330,19 +1334,28 @@ int pert_gemm_nt_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
       (size_t)Nc * K * 8 + 1024 + 1024 + 2 * 32 * 1024 + 32 * 1024 > 226 * 1024 &&
       (size_t)Nc * a_cb * 8 + 1024 + 1024 + 2 * 32 * 1024 + 32 * 1024 <= 226 * 1024 && encode_tiled_fn()) {
     const int nb = K / a_cb;
+    if (nb <= 8 && (c_cb <= 0 || c_cb >= Nc)) {
+      // all planes in ONE launch (gridDim.z = planes, each with its own resident K-slice of the weights and its own
+      // share of the SMs); C is zeroed first and every plane leaves through reduce-add stores
+      cudaError_t me = (ldc == Nc) ? cudaMemsetAsync(C, 0, (size_t)M * Nc * sizeof(float), st)
+                                   : cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Nc * 4, (size_t)M, st);
+      if (me != cudaSuccess) return (int)me;
+      int rc = gemm_nt_tc_impl(A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, M, Nc, a_cb, 0, 1, nb, st);
+      if (rc != PERT_ERR_UNSUPPORTED) return rc;
+    }
     for (int p = 0; p < nb; ++p) {
       int rc = gemm_nt_tc_impl(A + (size_t)p * a_cbs, lda, 0, 0, B + (size_t)p * a_cb, ldb, p == 0 ? bias : nullptr, C,
-                               ldc, c_cb, c_cbs, M, Nc, a_cb, 0, p > 0 ? 1 : 0, st);
+                               ldc, c_cb, c_cbs, M, Nc, a_cb, 0, p > 0 ? 1 : 0, 1, st);
       if (rc != PERT_OK) return p == 0 ? rc : (rc == PERT_ERR_UNSUPPORTED ? PERT_ERR_BADARG : rc);
     }
     return PERT_OK;
   }
-  return gemm_nt_tc_impl(A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, M, Nc, K, relu, 0, st);
+  return gemm_nt_tc_impl(A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, M, Nc, K, relu, 0, 1, st);
 }
 
 static int gemm_nt_tc_impl(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb,
                            const float* bias, float* C, int ldc, int c_cb, long long c_cbs, long long M, int Nc, int K,
-                           int relu, int reduce, cudaStream_t st) {
+                           int relu, int reduce, int kplanes, cudaStream_t st) {
   if (a_cb <= 0) { a_cb = K; a_cbs = 0; }
   if (c_cb <= 0) { c_cb = Nc; c_cbs = 0; }
   if (K % 8 || K > 1024 || Nc % 16 || lda % 4 || ldb % 4 || ldc % 4 || c_cb % 16 || a_cbs % 4 || c_cbs % 4 ||
@@ -1364,11 +1377,11 @@ static int gemm_nt_tc_impl(const float* A, int lda, int a_cb, long long a_cbs, c
     const size_t need = tma_enabled() ? (size_t)BN * K * 8 + 1024 + 1024 + 2 * 32 * 1024 + 32 * 1024 : smem;
     if (need <= 226 * 1024) break;
   }
-  NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu, reduce, nullptr};
+  NtArgs g{A, lda, a_cb, a_cbs, B, ldb, bias, C, ldc, c_cb, c_cbs, (int)M, Nc, K, BN, relu, reduce, kplanes, nullptr};
   const int mtiles_all = (int)((M + 127) / 128);
   if (tma_enabled() && nblk <= 8 && encode_tiled_fn()) {
     // TMA-tiled kernel: A as a 2-D tensor [nblocks * row_blk, a_cb] with pitch lda (see k_gemm_nt_tma)
-    const int nblocks = (K + a_cb - 1) / a_cb;
+    const int nblocks = kplanes > 1 ? kplanes : (K + a_cb - 1) / a_cb;
     const bool blocked = nblocks > 1;
     const bool ok = (!blocked || (a_cbs % lda == 0 && a_cb % KC == 0)) && (size_t)lda * 4 % 16 == 0;
     const size_t bbytes = ((size_t)BN * K * 8 + 1023) & ~(size_t)1023;
@@ -1406,15 +1419,16 @@ static int gemm_nt_tc_impl(const float* A, int lda, int a_cb, long long a_cbs, c
         if (e2 != cudaSuccess) return (int)e2;
         g.ctr = ticket_slot();
         if (!g.ctr) return (int)cudaGetLastError();
-        int gx2 = PERT_NUM_SMS / nblk;
+        if (nblk * kplanes > 8) return PERT_ERR_UNSUPPORTED;          // 8 ticket counters per slot
+        int gx2 = PERT_NUM_SMS / (nblk * kplanes);
         if (gx2 < 1) gx2 = 1;
         if (gx2 > mtiles_all) gx2 = mtiles_all;
-        k_gemm_nt_tma<<<dim3(gx2, nblk), TMA_THREADS, smem2, st>>>(tm, tc, g, NS, (int)row_blk);
+        k_gemm_nt_tma<<<dim3(gx2, nblk, kplanes), TMA_THREADS, smem2, st>>>(tm, tc, g, NS, (int)row_blk);
         return PERT_OK;
       }
     }
   }
-  if (reduce) return PERT_ERR_UNSUPPORTED;   // only the TMA kernel has the reduce-add epilogue
+  if (reduce || kplanes > 1) return PERT_ERR_UNSUPPORTED;   // only the TMA kernel has the reduce-add epilogue / K planes
   cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int mtiles = (int)((M + 127) / 128);

@@ -35,6 +35,7 @@ struct PeerArgs {
   unsigned long long step;     // 1, 2, 3, ... (same on every rank)
   unsigned int arrive_target;  // value of the grid counter that identifies the last CTA of this launch
   int* status;
+  long long* timing;           // optional [4]: += ns spent in publish / wait / reduce+Adam by CTA 0, += 1 (calls)
 };
 
 __device__ __forceinline__ unsigned long long* flags_of(float* xbuf, long long n_al) {
@@ -49,8 +50,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(256) k_allreduce_adam(PeerArgs a) {
   __shared__ int s_last;
+  const bool stamp = a.timing && blockIdx.x == 0 && threadIdx.x == 0;
+  long long ts0 = 0, ts1 = 0, ts2 = 0;
+  if (stamp) ts0 = gtime_ns();
   const long long n4 = a.n >> 2;                 // n is padded to a multiple of 4 by the caller's layout (n_al)
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,6 +78,7 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(PeerArgs a) {
     __threadfence_system();
     st_release_sys(flags_of(a.xbuf[threadIdx.x], a.n_al) + a.rank, a.step);
   }
+  if (stamp) ts1 = gtime_ns();
   // ---- 2. wait for every rank's gradient of this step
   if (threadIdx.x < a.world) {
     const long long t_start = clock64();
@@ -79,6 +90,7 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(PeerArgs a) {
     }
   }
   __syncthreads();
+  if (stamp) ts2 = gtime_ns();
   // ---- 3. reduce in rank order + Adam
   const long long off = (a.step & 1ull) * a.n_al;
   for (long long i = t0; i < n4; i += stride) {
@@ -110,6 +122,13 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(PeerArgs a) {
     a.m[i] = mi;
     a.v[i] = vi;
     a.p[i] = pi - (a.lr / a.bc1) * (mi / (sqrtf(vi) / a.bc2_sqrt + a.eps));
+  }
+  if (stamp) {   // phase times of CTA 0 (publish incl. the grid arrival; wait = slowest rank's skew + flag latency)
+    const long long ts3 = gtime_ns();
+    a.timing[0] += ts1 - ts0;
+    a.timing[1] += ts2 - ts1;
+    a.timing[2] += ts3 - ts2;
+    a.timing[3] += 1;
   }
 }
 
@@ -159,7 +178,7 @@ int pert_peer_free(void* ptr) {
 // number of calls so far (it also is Adam's bias-correction step).  All ranks must call once per step.
 int pert_allreduce_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, long long step, float grad_scale, void* const* xbufs, int rank,
-                        int world, int* status, void* stream) {
+                        int world, int* status, long long* timing, void* stream) {
   if (!p || !g || !m || !v || n < 0 || step < 1 || !xbufs || world < 1 || world > PEER_MAX || rank < 0 || rank >= world)
     return PERT_ERR_BADARG;
   if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return PERT_ERR_BADARG;
@@ -173,7 +192,7 @@ int pert_allreduce_adam(float* p, const float* g, float* m, float* v, long long 
   for (int r = 0; r < PEER_MAX; ++r) a.xbuf[r] = r < world ? (float*)xbufs[r] : nullptr;
   for (int r = 0; r < world; ++r)
     if (!a.xbuf[r]) return PERT_ERR_BADARG;
-  a.rank = rank; a.world = world; a.step = (unsigned long long)step; a.status = status;
+  a.rank = rank; a.world = world; a.step = (unsigned long long)step; a.status = status; a.timing = timing;
   long long blocks = pert_cdiv(n / 4 + 1, 256);
   if (blocks > PERT_NUM_SMS) blocks = PERT_NUM_SMS;   // all CTAs co-resident: they wait on each other's arrival
   if (blocks < 1) blocks = 1;

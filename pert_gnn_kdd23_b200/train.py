@@ -110,6 +110,7 @@ class PeerAdam(FusedAdam):
         self._own = None
         self._peers = []
         self.status = torch.zeros(1, dtype=torch.int32, device=flat.flat.device)
+        self.timing = torch.zeros(4, dtype=torch.int64, device=flat.flat.device)   # ns in publish / wait / reduce, calls
         if self.world == 1:
             return
         if self.world > 8:
@@ -165,8 +166,18 @@ class PeerAdam(FusedAdam):
         self.t += 1
         _lib.call("pert_allreduce_adam", _lib.ptr(self.fp.flat), _lib.ptr(self.fp.grad), _lib.ptr(self.m),
                   _lib.ptr(self.v), self.fp.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t,
-                  float(grad_scale), self._xbufs, self.rank, self.world, _lib.ptr(self.status), _lib.stream())
+                  float(grad_scale), self._xbufs, self.rank, self.world, _lib.ptr(self.status), _lib.ptr(self.timing),
+                  _lib.stream())
         ops.LAUNCHES["n"] += 1
+
+    def phase_times_us(self, reset=True):
+        """Mean microseconds CTA 0 of the fused kernel spent publishing, waiting for the peers, and reducing + Adam
+        (synchronising read; the wait phase is the slowest rank's skew plus the flag round trip over NVLink)."""
+        t = self.timing.cpu().tolist()
+        if reset:
+            self.timing.zero_()
+        n = max(t[3], 1)
+        return {"publish_us": t[0] / n / 1e3, "wait_us": t[1] / n / 1e3, "reduce_adam_us": t[2] / n / 1e3, "calls": t[3]}
 
     def check(self):
         """Synchronising check of the device status word (a peer that never arrived sets PERT_ERR_PEER_TIMEOUT)."""

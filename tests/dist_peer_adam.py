@@ -51,10 +51,35 @@ def main():
     ref = flat.clone()
     dist.broadcast(ref, 0)
     assert torch.equal(flat, ref), "PeerAdam replicas diverged"
+    phases = opt_b.phase_times_us()
     opt_b.close()
+    # drop-in loop under data parallelism: torch.optim.Adam + DataParallel.all_reduce_module_grads (one all-reduce of the
+    # engine's flat gradient buffer) keeps the replicas bit-identical
+    from pert_gnn_kdd23_b200.train import train_step
+
+    torch.manual_seed(1)
+    model_c = SAGEDeterministic(*model_args(1)).to(dev)
+    for p_ in model_c.parameters():
+        dist.broadcast(p_.data, 0)
+    dp_c = DataParallel(FlatParams(model_c, bind_grads=False))
+    opt_c = torch.optim.Adam(model_c.parameters(), lr=1e-3)
+    for it in range(4):
+        train_step(model_c, opt_c, batches[it % 2], 0.5, dp_c)
+    flat_c = torch.cat([p_.detach().reshape(-1) for p_ in model_c.parameters()])
+    ref_c = flat_c.clone()
+    dist.broadcast(ref_c, 0)
+    assert torch.equal(flat_c, ref_c), "drop-in DP replicas diverged"
+    # a model on this rank's device while ANOTHER device is current (device guard of the bindings)
+    other = (lr_ + 1) % torch.cuda.device_count()
+    torch.cuda.set_device(other)
+    gp, _ = model_c(batches[0].x, batches[0].cat_X, batches[0].edge_index, batches[0].edge_attr,
+                    batches[0].pattern_num_nodes, batches[0].rt_probs, batches[0].entry_id, batches[0].batch)
+    assert gp.device == dev and torch.isfinite(gp).all()
+    torch.cuda.set_device(lr_)
     dist.barrier()
     if rank == 0:
-        print(f"PEER_ADAM_OK world={world} worst_rel={worst:.2e} replays={gstep.replays}")
+        print(f"PEER_ADAM_OK world={world} worst_rel={worst:.2e} replays={gstep.replays} phases_us={phases} "
+              f"dropin_dp_replicas_identical=True device_guard=True")
     dist.destroy_process_group()
 
 
