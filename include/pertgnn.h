@@ -264,6 +264,60 @@ int pert_model_backward(const PertModelDesc* desc, const float* params, float* g
                         const int* csc_dst, void* workspace, long long workspace_bytes, int training,
                         const float* d_global, const float* d_local, const PertProbe* probe, void* stream);
 
+/* ---- device-side batch assembly from a resident pattern store (csrc/store.cu) ---------------------------------------
+ * Replaces the host-side sample assembly + collation + per-step probability expansion of the reference:
+ * get_entry_data / get_x / get_cat_X / get_node_depth / get_edge_index / get_edge_attr / get_pattern_num_nodes
+ * (pert_gnn.py:40-173), torch_geometric DataLoader collation (:201-209) and transform_pattern_probs (:122-131,
+ * :220-230).  All pointers are caller-owned device arrays, built once from the reference's artefacts
+ * (runtime2graph, entry2runtimes, resource_df, tr2data -- pert_gnn.py:297-305) by pert_gnn_kdd23_b200/store.py.
+ *   patterns p = 0..n_pat-1 (the runtime ids in the order the store assigned):
+ *     pat_nptr/pat_eptr [n_pat+1] node / edge offsets into the concatenated arrays;  pat_ms [sum n] = ms_id (cat_X);
+ *     pat_depth [sum n] = node_depth;  pat_last [sum n] = 1 iff the node is the LAST one of its ms inside the pattern
+ *     (get_x's ms2nid dict, pert_gnn.py:54-65);  pat_src/pat_dst [sum e] pattern-local edge_index;  pat_attr [sum e, attr_cols]
+ *   entries: ent_ptr [n_ent+1] into ent_pat (pattern index) / ent_prob (float32 probability), in the dict order of
+ *     entry2runtimes[entry];  ent_nodes / ent_edges [n_ent] totals over the entry's patterns
+ *   resources: res_keys [n_res] sorted int64 = timestamp * n_ms + ms, res_vals [n_res, 8] float32,
+ *     ms_has_res [n_ms] = 1 iff ms has a row at ANY timestamp (pert_gnn.py:138)
+ *   traces: trace_entry [n_traces] int32, trace_ts [n_traces] int64, trace_y [n_traces] int64. */
+typedef struct PertStore {
+  int32_t n_pat, n_ent, n_res, n_ms, attr_cols;
+  long long n_traces;
+  const int32_t *pat_nptr, *pat_eptr;
+  const int64_t *pat_ms, *pat_depth;
+  const uint8_t* pat_last;
+  const int32_t *pat_src, *pat_dst;
+  const int64_t* pat_attr;
+  const int32_t *ent_ptr, *ent_pat;
+  const float* ent_prob;
+  const int32_t *ent_nodes, *ent_edges;
+  const int64_t* res_keys;
+  const float* res_vals;
+  const uint8_t* ms_has_res;
+  const int32_t* trace_entry;
+  const int64_t *trace_ts, *trace_y;
+} PertStore;
+/* Output = the collated Batch of pert_gnn.py:163-173 + PyG collate + the per-node probability of :220-230. */
+typedef struct PertBatchOut {
+  float* x;                  /* [N, 9]  */
+  int64_t* cat_X;            /* [N, 1]  */
+  int64_t* node_depth;       /* [N, 1]  */
+  float* pattern_num_nodes;  /* [N, 1]  */
+  float* rt_probs;           /* [N, 1]  per-node pattern probability (transform_pattern_probs) */
+  int64_t* batch;            /* [N]     */
+  int64_t* edge_index;       /* [2, E]  */
+  int64_t* edge_attr;        /* [E, attr_cols] */
+  int64_t* entry_id;         /* [B]     */
+  int64_t* y;                /* [B]     */
+  int64_t* ptr;              /* [B+1]   */
+  float* pattern_probs;      /* [sum_b patterns(entry_b), 1] */
+} PertBatchOut;
+/* trace_ids [B] int64 (device): which traces form the batch.  N, E = node / edge totals of the batch (the caller sizes
+ * the outputs from its host copy of ent_nodes / ent_edges -- no device sync); offsets: int32 scratch of 3 * (B + 1).
+ * status: PERT_ERR_RANGE for a trace id out of range or a (timestamp, ms) row missing for a resourced ms (the
+ * reference raises KeyError there). */
+int pert_store_assemble(const PertStore* store, const int64_t* trace_ids, long long B, long long N, long long E,
+                        int* offsets, const PertBatchOut* out, int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

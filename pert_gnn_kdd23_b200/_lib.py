@@ -53,6 +53,8 @@ SIGNATURES = {
     "pert_peer_close": (I, [P]),
     "pert_peer_free": (I, [P]),
     "pert_allreduce_adam": (I, [P, P, P, P, LL, F, F, F, F, F, LL, F, P, I, I, P, P, P]),
+    # device-side batch assembly from the pattern store (first / 7th argument: struct pointers, see store.py)
+    "pert_store_assemble": (I, [P, P, LL, LL, LL, P, P, P, P]),
     # whole-model engine (first argument: const PertModelDesc*, see engine.py)
     "pert_model_workspace_bytes": (LL, [P, LL, LL, LL]),
     "pert_model_packed_bytes": (LL, [P]),
