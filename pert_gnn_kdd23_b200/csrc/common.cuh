@@ -51,3 +51,13 @@ __device__ __forceinline__ float group_sum(float v, unsigned gmask) {
   for (int off = LPR >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(gmask, v, off);
   return v;
 }
+
+// engine-internal entry points (not part of the C-ABI)
+int pert_tconv_fwd_stats(const float* q, const float* k, const float* v, const float* s, int ld, const int* rowptr,
+                         const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if,
+                         const float* t_rpc, float* out, int ld_out, float* alpha, int n_rpc, long long N, long long E,
+                         long long B_hint, int H, double* bn_acc, int* fused, void* stream);
+int pert_bn_fwd_ex(const float* x, int ld_x, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, long long* num_batches_tracked, float eps, float momentum, int training,
+                   int relu, float* mean, float* rstd, float* y, int ld_y, long long N, int H, void* workspace,
+                   long long workspace_bytes, int stats_ready, void* stream);

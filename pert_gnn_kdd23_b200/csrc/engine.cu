@@ -481,6 +481,14 @@ std::mutex& engine_mutex() {
   static std::mutex m;
   return m;
 }
+bool bn_fuse_enabled() {   // PERT_BN_FUSE=0: statistics by the separate k_bn_partial pass (debug A/B)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PERT_BN_FUSE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 AuxStream* aux_stream() {
   static AuxStream aux[64];
   static int enabled = -1;
@@ -614,17 +622,26 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
       cudaError_t we = cudaStreamWaitEvent(st, (cudaEvent_t)index_ready, 0);
       if (we != cudaSuccess) return (int)we;
     }
+    // BatchNorm statistics of out[l] are produced by the conv kernel's epilogue (training, staged tile path)
+    int stats_fused = 0;
+    double* bn_acc = nullptr;
+    if (l + 1 < L && training && bn_fuse_enabled()) {
+      bn_acc = (double*)w.bn_part;
+      cudaError_t me = cudaMemsetAsync(bn_acc, 0, (size_t)2 * H * sizeof(double), st);
+      if (me != cudaSuccess) return (int)me;
+    }
     PROBE_START(1, l);
-    TRY(pert_tconv_fwd(pl, pl + N * H, pl + 2 * N * H, pl + 3 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, w.t_if[l],
-                       w.t_rpc[l], w.out[l], H, w.alpha[l], d->n_rpc, N, E, B, H, st));
+    TRY(pert_tconv_fwd_stats(pl, pl + N * H, pl + 2 * N * H, pl + 3 * N * H, H, rowptr, csr_src, csr_if, csr_rpc,
+                             w.t_if[l], w.t_rpc[l], w.out[l], H, w.alpha[l], d->n_rpc, N, E, B, H, bn_acc, &stats_fused,
+                             st));
     PROBE_STOP(1, l);
     if (l + 1 < L) {
       float* rm = bn_running ? bn_running + (size_t)l * 2 * H : nullptr;
       float* rv = rm ? rm + H : nullptr;
-      TRY(pert_bn_fwd(w.out[l], H, params + d->off_bn_g[l], params + d->off_bn_b[l], rm, rv,
-                      (training && bn_nbt) ? bn_nbt + l : nullptr, d->bn_eps, d->bn_momentum, training, 1,
-                      w.bn_stats[l], w.bn_stats[l] + H, w.x[l + 1], H, N, H, w.bn_part,
-                      pert_bn_workspace_bytes(N, H), st));
+      TRY(pert_bn_fwd_ex(w.out[l], H, params + d->off_bn_g[l], params + d->off_bn_b[l], rm, rv,
+                         (training && bn_nbt) ? bn_nbt + l : nullptr, d->bn_eps, d->bn_momentum, training, 1,
+                         w.bn_stats[l], w.bn_stats[l] + H, w.x[l + 1], H, N, H, w.bn_part,
+                         pert_bn_workspace_bytes(N, H), stats_fused, st));
     }
   }
   // 4. local head + weighted add-pool, global head

@@ -555,6 +555,18 @@ int pert_bn_fwd(const float* x, int ld_x, const float* gamma, const float* beta,
                 float* running_var, long long* num_batches_tracked, float eps, float momentum, int training,
                 int relu, float* mean, float* rstd, float* y, int ld_y, long long N, int H, void* workspace,
                 long long workspace_bytes, void* stream) {
+  return pert_bn_fwd_ex(x, ld_x, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, training,
+                        relu, mean, rstd, y, ld_y, N, H, workspace, workspace_bytes, 0, stream);
+}
+
+}  // extern "C"
+
+// stats_ready != 0 (training): the fp64 column sums / sums of squares already sit in `workspace` (written by the producer
+// of x, csrc/tconv_tile.cu) -- only the apply pass runs.
+int pert_bn_fwd_ex(const float* x, int ld_x, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, long long* num_batches_tracked, float eps, float momentum, int training,
+                   int relu, float* mean, float* rstd, float* y, int ld_y, long long N, int H, void* workspace,
+                   long long workspace_bytes, int stats_ready, void* stream) {
   if (N < 0 || H <= 0 || H % 4 || H > 1024 || ld_x % 4 || ld_y % 4 || !x || !gamma || !beta || !mean || !rstd || !y)
     return PERT_ERR_BADARG;
   if (!al16(x) || !al16(gamma) || !al16(beta) || !al16(mean) || !al16(rstd) || !al16(y)) return PERT_ERR_BADARG;
@@ -573,9 +585,11 @@ int pert_bn_fwd(const float* x, int ld_x, const float* gamma, const float* beta,
     if (smem > 48 * 1024) return PERT_ERR_UNSUPPORTED;
     if ((uintptr_t)workspace & 7) return PERT_ERR_BADARG;
     acc = (double*)workspace;
-    cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)2 * H * sizeof(double), st);
-    if (e != cudaSuccess) return (int)e;
-    k_bn_partial<<<chunks, threads, smem, st>>>(x, ld_x, N, H, acc);
+    if (!stats_ready) {
+      cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)2 * H * sizeof(double), st);
+      if (e != cudaSuccess) return (int)e;
+      k_bn_partial<<<chunks, threads, smem, st>>>(x, ld_x, N, H, acc);
+    }
   } else {
     if (!running_mean || !running_var) return PERT_ERR_BADARG;
     k_bn_eval_stats<<<pert_cdiv(H, 128), 128, 0, st>>>(running_mean, running_var, eps, H, mean, rstd);
@@ -590,6 +604,8 @@ int pert_bn_fwd(const float* x, int ld_x, const float* gamma, const float* beta,
   PERT_LAUNCH_CHECK();
   return PERT_OK;
 }
+
+extern "C" {
 
 // sums: [2H] scratch (zeroed here).  dgamma/dbeta accumulate (+=).
 int pert_bn_bwd(const float* dy, int ld_dy, const float* y, int ld_y, const float* x, int ld_x, const float* mean,

@@ -70,6 +70,7 @@ struct TileArgs {
   float* alpha;     // fwd: written; bwd: read
   float* dsp;       // bwd_dst: written; bwd_src: read
   float *dt_if, *dt_rpc;
+  double* bn_acc;   // fwd: optional [2][H] column sums / sums of squares of `out` (BatchNorm statistics), +=
   float* rpc_ws;    // [N][2][RPC_FAST] per-target sums over in-edges of (alpha, ds) by rpc type, or null (see bwd_src)
   int N, tile_nodes, edge_cap;
   float inv_sqrt_c;
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
     q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
     if (a.s) s_n = ldg4(a.s + (size_t)(n0 + loc) * H + lig * 4);
   }
+  float4 bsum = f4zero(), bsq = f4zero();   // this lane's 4 columns over its nodes (fused BatchNorm statistics)
   auto run = [&](auto fast_c) {
     constexpr bool FAST = decltype(fast_c)::value;
     for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {   // warp-uniform: the warp's first group still has a node
@@ -284,7 +286,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
         m = mn;
       }
       const float invZ = 1.0f / (Z + 1e-16f);
-      if (valid) st4(a.out + (size_t)i * H + lig * 4, f4add(f4scale(invZ, acc), skip));
+      if (valid) {
+        const float4 o = f4add(f4scale(invZ, acc), skip);
+        st4(a.out + (size_t)i * H + lig * 4, o);
+        bsum = f4add(bsum, o);
+        bsq.x = fmaf(o.x, o.x, bsq.x); bsq.y = fmaf(o.y, o.y, bsq.y);
+        bsq.z = fmaf(o.z, o.z, bsq.z); bsq.w = fmaf(o.w, o.w, bsq.w);
+      }
       __syncwarp();
       for (int p = p0 + lig; p < p1; p += LPR) {
         const int le = p - e_lo;
@@ -295,6 +303,25 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
   };
   if (all_in) run(std::true_type{});
   else run(std::false_type{});
+  if (a.bn_acc) {
+    // BatchNorm statistics of this layer's output, fused: column sums and sums of squares of the tile (per-lane fp32
+    // partials over <= a handful of nodes, combined in fp64) -> one fp64 atomic per column and tile into bn_acc, the
+    // accumulator k_bn_apply derives mean / rstd from (nodeops.cu).  Saves the separate statistics pass over `out`.
+    __syncthreads();                                   // every warp is done with the staged tiles
+    double* sc = reinterpret_cast<double*>(S.ta);
+    for (int x = tid; x < 2 * H; x += TILE_THREADS) sc[x] = 0.0;
+    __syncthreads();
+    float vals[8] = {bsum.x, bsum.y, bsum.z, bsum.w, bsq.x, bsq.y, bsq.z, bsq.w};
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      float v = vals[kk];
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);   // the warp's groups
+      if (grp == 0) atomicAdd(&sc[(kk < 4 ? 0 : H) + lig * 4 + (kk & 3)], (double)v);
+    }
+    __syncthreads();
+    for (int x = tid; x < 2 * H; x += TILE_THREADS) atomicAdd(a.bn_acc + x, sc[x]);
+  }
 }
 
 // ============================================================== backward, target pass (dq, ds)
@@ -634,13 +661,13 @@ int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool h
 int pert_tile_fwd(const float* q, const float* k, const float* v, const float* s, int ld, const int* rowptr,
                   const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if, const float* t_rpc,
                   int n_rpc, float* out, int ld_out, float* alpha, long long N, long long E, long long B, int H,
-                  cudaStream_t st) {
+                  double* bn_acc, cudaStream_t st) {
   if (ld != H || ld_out != H || (t_if && ((size_t)n_rpc * H * 4 > 16 * 1024 || n_rpc > 1023)))
     return PERT_ERR_UNSUPPORTED;
   TileArgs a{};
   a.q = q; a.k = k; a.v = v; a.s = s;
   a.rowptr = rowptr; a.csr_src = csr_src; a.csr_if = csr_if; a.csr_rpc = csr_rpc;
-  a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc; a.out = out; a.alpha = alpha;
+  a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc; a.out = out; a.alpha = alpha; a.bn_acc = bn_acc;
   a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
   switch (H) {
     case 32: return launch_fwd<8>(a, N, E, B, t_if != nullptr, st);

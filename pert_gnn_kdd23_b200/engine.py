@@ -173,9 +173,10 @@ class Engine:
 
     def launches_forward(self):
         """Kernels pert_model_forward launches (memsets not counted): pack, edge tables (6 layers per launch),
-        embeddings + copy, per conv GEMM + attention, per BatchNorm partial + apply, pool, head."""
+        embeddings + copy, per conv GEMM + attention (whose epilogue also produces the BatchNorm statistics), per
+        BatchNorm one apply kernel, pool, head."""
         L = self.n_convs
-        return self._pack_launches() + (L + 5) // 6 + self.desc.n_cat + 1 + 2 * L + 2 * (L - 1) + 1 + 1
+        return self._pack_launches() + (L + 5) // 6 + self.desc.n_cat + 1 + 2 * L + (L - 1) + 1 + 1
 
     def launches_backward(self):
         """head, pool, per conv (target pass, source pass, weight GEMM, data GEMM), per BatchNorm reduce + apply,

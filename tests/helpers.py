@@ -94,8 +94,8 @@ def assert_grads_close(named_c, named_o, rtol, n_convs=None):
         if is_structural_zero_grad(n, n_convs):
             assert float(p.grad.abs().max()) <= 1e-5 * scale, f"grad {n} should be ~0"
             assert float(ref.abs().max()) <= 1e-5 * scale
-        elif n.endswith("lin_key.weight") or n.endswith("lin_query.weight"):
-            # Gradients of the ATTENTION-LOGIT path.  ds_t = alpha_t (dalpha_t - sum alpha dalpha) cancels inside every
+        elif ".lin_key." in n or ".lin_query." in n or n.startswith(("lin_key.", "lin_query.")):
+            # Gradients of the ATTENTION-LOGIT path (lin_query / lin_key weights and the query bias).  ds_t = alpha_t (dalpha_t - sum alpha dalpha) cancels inside every
             # target's neighbourhood (softmax shift invariance: sum_t ds_t = 0, hence sum_j dk_j = 0), and
             # dW_{q,k} = sum_nodes d{q,k} x^T sums 10^4..10^5 such terms: at cfg3-5, conv 0, the result is as small as a
             # few terms (conditioning kappa = sum|terms| / |result| ~ 10^2..10^4) and 500x below the step's largest
