@@ -618,6 +618,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- BASELINE.json configs[3] (4096 graphs over 8 GPUs = 512 graphs / GPU, 128-dim, 3 layers) beside the headline
     cfg4 = run_cfg4_block(args, rank, world, dev, barrier, make_optimizer) if (args.cfg == 2 and not args.no_cfg4) else None
+    cfg2j = run_jitter_block(args, rank, world, dev, barrier, make_optimizer) if (args.cfg == 2 and not args.no_cfg4) else None
 
     if hasattr(opt, "check"):
         opt.check()
@@ -692,34 +693,29 @@ def run_b200(args, rank, world, local_rank):
                             "launch list mirrored from csrc/engine.cu + index build + loss + Adam) x steps of one block; "
                             "cross-check: profiles/r2_launches_step.csv (ncu launch list of the same command)",
         "wall_s": t_wall, "clocks": clocks, "final_loss": float(loss), "parity_first_step": parity,
-        "peer": peer_phases, "cfg4": cfg4,
+        "peer": peer_phases, "cfg4": cfg4, "cfg2_jittered": cfg2j,
     }
     print(json.dumps(line), flush=True)
 
 
-def run_cfg4_block(args, rank, world, dev, barrier, make_optimizer):
-    """BASELINE.json configs[3]: the 4096-graph batch sharded data-parallel over 8 GPUs = 512 graphs per GPU, 128-dim,
-    3 layers, gradient all-reduce fused with Adam.  Measured beside the cfg2 headline (which stays the weak-scaling
-    curve): every rank trains on its own 512-graph shard; at N < 8 it is the same per-GPU shard on fewer GPUs."""
+def run_extra_block(args, rank, world, dev, barrier, make_optimizer, cfg, per_gpu, jitter, workload):
+    """A second workload measured beside the headline (same step machinery: resident batches, graph replay, fused
+    Adam / PeerAdam): every rank trains on its own `per_gpu`-graph batches of config `cfg`."""
+    from pert_gnn_kdd23_b200.data import Batch
     from pert_gnn_kdd23_b200.model import SAGEDeterministic
-    from pert_gnn_kdd23_b200.synthetic import model_args
+    from pert_gnn_kdd23_b200.synthetic import make_data_list, model_args
     from pert_gnn_kdd23_b200.train import DataParallel, FlatParams, GraphedTrainStep
 
-    import torch.distributed as dist
-
-    from pert_gnn_kdd23_b200.data import Batch
-    from pert_gnn_kdd23_b200.synthetic import make_data_list
-
-    n_rot, per_gpu = 3, 512
+    n_rot = 3
     batches = []
     for r in range(n_rot):
-        dl = make_data_list(4, num_graphs=per_gpu, seed=1000 + 4 + 7919 * rank + 131 * r)
+        dl = make_data_list(cfg, num_graphs=per_gpu, seed=1000 + cfg + 7919 * rank + 131 * r, jitter=jitter)
         for d in dl:
             d._store.pop("level", None)
             d._store.pop("min_depth", None)
         batches.append(Batch.from_data_list(dl).pin_memory().to(dev))
     torch.manual_seed(0)
-    model = SAGEDeterministic(*model_args(4)).to(dev)
+    model = SAGEDeterministic(*model_args(cfg)).to(dev)
     fp = FlatParams(model)
     opt, sync = make_optimizer(fp)
     dp = DataParallel(fp) if world > 1 else None
@@ -740,13 +736,30 @@ def run_cfg4_block(args, rank, world, dev, barrier, make_optimizer):
     phases = opt.phase_times_us(reset=True) if hasattr(opt, "phase_times_us") and world > 1 else None
     if hasattr(opt, "check"):
         opt.check()
+    if hasattr(opt, "close"):
+        opt.close()
     Nn, Ee = batches[0].x.size(0), batches[0].edge_index.size(1)
-    return {"workload": f"BASELINE configs[3] shard: {per_gpu} DAGs x 200 nodes/600 edges per GPU (4096 over 8 GPUs), "
-                        "128-dim, num_layers=3, fwd+bwd+Adam, resident batches, graph replay",
-            "value": world * per_gpu * K / secs, "unit": "DAGs/s", "global_batch": world * per_gpu,
+    return {"workload": workload, "value": world * per_gpu * K / secs, "unit": "DAGs/s", "global_batch": world * per_gpu,
             "ms_per_step": 1e3 * secs / K, "steps_per_block": K, "blocks": len(blocks), "nodes_per_gpu": Nn,
             "edges_per_gpu": Ee, "grad_sync": sync, "peer": phases, "replays": gstep.replays,
             "capture_error": gstep.capture_error}
+
+
+def run_cfg4_block(args, rank, world, dev, barrier, make_optimizer):
+    """BASELINE.json configs[3]: the 4096-graph batch sharded data-parallel over 8 GPUs = 512 graphs per GPU, 128-dim,
+    3 layers, gradient all-reduce fused with Adam.  Measured beside the cfg2 headline (which stays the weak-scaling
+    curve): every rank trains on its own 512-graph shard; at N < 8 it is the same per-GPU shard on fewer GPUs."""
+    return run_extra_block(args, rank, world, dev, barrier, make_optimizer, 4, 512, 0.0,
+                           "BASELINE configs[3] shard: 512 DAGs x 200 nodes/600 edges per GPU (4096 over 8 GPUs), "
+                           "128-dim, num_layers=3, fwd+bwd+Adam, resident batches, graph replay")
+
+
+def run_jitter_block(args, rank, world, dev, barrier, make_optimizer):
+    """cfg2 with graph sizes 200 +- 20 % nodes (edges scale along): BASELINE says "~200 nodes / ~600 edges"; the headline
+    batch is exactly uniform, real batches are not (graph-aligned tiles, csrc/tconv_tile.cu:k_build_tiles)."""
+    return run_extra_block(args, rank, world, dev, barrier, make_optimizer, 2, 256, 0.2,
+                           "cfg2j: 256 DAGs x 200 +- 20 % nodes (3 edges per node) per GPU, 64-dim, num_layers=3, "
+                           "fwd+bwd+Adam, resident batches, graph replay")
 
 
 def main():

@@ -351,6 +351,7 @@ struct Ws {
   float *bn_part, *pool, *z, *h1;
   // backward temporaries
   float *dplanes, *dx, *dsp, *rpc_ws, *sums, *dpool, *dzent, *dh1;
+  int* tiles;      // graph-aligned tile list of the batch (pert_tile_list_ints ints), built in forward, reused in backward
   long long total;  // floats
   long long packed_floats;
 };
@@ -401,6 +402,7 @@ Ws carve(const PertModelDesc* d, long long N, long long E, long long B, float* b
     w.bn_stats[l] = take(2LL * H);
   }
   w.bn_part = take(pert_bn_workspace_bytes(N, H) / 4 + 16);
+  w.tiles = (int*)take(pert_tile_list_ints(N, B));
   w.pool = take(B * H);
   w.z = take(B * 2 * H);
   w.h1 = take(B * H);
@@ -480,6 +482,14 @@ struct AuxStream {
 std::mutex& engine_mutex() {
   static std::mutex m;
   return m;
+}
+bool tiles_enabled() {   // PERT_TILE_LIST=0: fixed-size tiles (round-1 behaviour; debug A/B)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PERT_TILE_LIST");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 bool bn_fuse_enabled() {   // PERT_BN_FUSE=0: statistics by the separate k_bn_partial pass (debug A/B)
   static int on = -1;
@@ -612,6 +622,8 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
   TRY(pert_copy_cols(x, d->F, w.x[0], d->k0, H, N, s2));
   if (forked) TRY(aux_join(ax, st));
   // 3. conv stack
+  PertTiles tiles{};
+  bool have_tiles = false;
   for (int l = 0; l < L; ++l) {
     const int K = k_of(d, l);
     PROBE_START(3, l);
@@ -621,6 +633,11 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
     if (l == 0 && index_ready) {      // the graph index was built on another stream: first use is here
       cudaError_t we = cudaStreamWaitEvent(st, (cudaEvent_t)index_ready, 0);
       if (we != cudaSuccess) return (int)we;
+    }
+    if (l == 0 && tiles_enabled() && E > 0) {   // graph-aligned tile list (whole graphs per tile), once per batch
+      int trc = pert_tile_list_build(batch, N, E, B, rowptr, H, d->n_rpc, w.tiles, &tiles, st);
+      have_tiles = trc == PERT_OK;
+      if (!have_tiles && trc != PERT_ERR_UNSUPPORTED) return trc;
     }
     // BatchNorm statistics of out[l] are produced by the conv kernel's epilogue (training, staged tile path)
     int stats_fused = 0;
@@ -633,7 +650,7 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
     PROBE_START(1, l);
     TRY(pert_tconv_fwd_stats(pl, pl + N * H, pl + 2 * N * H, pl + 3 * N * H, H, rowptr, csr_src, csr_if, csr_rpc,
                              w.t_if[l], w.t_rpc[l], w.out[l], H, w.alpha[l], d->n_rpc, N, E, B, H, bn_acc, &stats_fused,
-                             st));
+                             have_tiles ? &tiles : nullptr, st));
     PROBE_STOP(1, l);
     if (l + 1 < L) {
       float* rm = bn_running ? bn_running + (size_t)l * 2 * H : nullptr;
@@ -722,13 +739,16 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
   };
   AuxStream* ax = aux_stream();
   bool forked = false;
+  PertTiles tiles{};            // the list forward built for this batch (same geometry: a pure function of the sizes)
+  const bool have_tiles = tiles_enabled() && E > 0 &&
+                          pert_tile_list_view(N, E, B, H, d->n_rpc, w.tiles, &tiles) == PERT_OK;
   for (int l = L - 1; l >= 0; --l) {
     const int K = k_of(d, l);
     float* pl = w.planes[l];
     PROBE_START(2, l);
-    TRY(pert_tconv_bwd(dskip, H, pl, pl + N * H, pl + 2 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos,
-                       csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.rpc_ws, w.dt_if[l], w.dt_rpc[l],
-                       d->n_rpc, N, E, B, H, st));
+    TRY(pert_tconv_bwd_tiles(dskip, H, pl, pl + N * H, pl + 2 * N * H, H, rowptr, csr_src, csr_if, csr_rpc, colptr,
+                             csc_pos, csc_dst, w.t_if[l], w.t_rpc[l], w.alpha[l], dq, dk, dv, H, w.dsp, w.rpc_ws,
+                             w.dt_if[l], w.dt_rpc[l], d->n_rpc, N, E, B, H, have_tiles ? &tiles : nullptr, st));
     PROBE_STOP(2, l);
     if (l == 0) {                       // every dT table is complete now
       forked = aux_fork(ax, st);

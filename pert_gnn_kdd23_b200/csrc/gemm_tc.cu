@@ -1314,6 +1314,8 @@ static bool tc_enabled() {
 
 }  // namespace
 
+unsigned int* pert_ticket_slot() { return ticket_slot(); }
+
 // Returns PERT_ERR_UNSUPPORTED when the shape / layout is outside what the tensor-core kernels handle (the caller
 // then uses the exact-fp32 SIMT kernels of gemm.cu).
 static int gemm_nt_tc_impl(const float* A, int lda, int a_cb, long long a_cbs, const float* B, int ldb,

@@ -432,12 +432,12 @@ inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 int pert_tile_fwd(const float* q, const float* k, const float* v, const float* s, int ld, const int* rowptr,
                   const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if, const float* t_rpc,
                   int n_rpc, float* out, int ld_out, float* alpha, long long N, long long E, long long B, int H,
-                  double* bn_acc, cudaStream_t st);
+                  double* bn_acc, const PertTiles* tiles, cudaStream_t st);
 int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, const float* v, int ld, const int* rowptr,
                   const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr, const int* csc_pos,
                   const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha, float* dq, float* dk,
                   float* dv, int ld_d, float* dsp, float* rpc_ws, float* dt_if, float* dt_rpc, int n_rpc, long long N,
-                  long long E, long long B, int H, cudaStream_t st);
+                  long long E, long long B, int H, const PertTiles* tiles, cudaStream_t st);
 static bool tile_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -461,15 +461,15 @@ int pert_tconv_supported_width(int H) {
 int pert_tconv_fwd_stats(const float* q, const float* k, const float* v, const float* s, int ld, const int* rowptr,
                          const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if,
                          const float* t_rpc, float* out, int ld_out, float* alpha, int n_rpc, long long N, long long E,
-                         long long B_hint, int H, double* bn_acc, int* fused, void* stream) {
+                         long long B_hint, int H, double* bn_acc, int* fused, const PertTiles* tiles, void* stream) {
   *fused = 0;
-  if (bn_acc && N > 0 && tile_enabled() && ld_out == H && q && k && v && rowptr && out && !(ld % 4) && aligned16(q) &&
+  if ((bn_acc || tiles) && N > 0 && tile_enabled() && ld_out == H && q && k && v && rowptr && out && !(ld % 4) && aligned16(q) &&
       aligned16(k) && aligned16(v) && aligned16(out) && (!s || aligned16(s)) &&
       (!t_if || (aligned16(t_if) && t_rpc && aligned16(t_rpc) && csr_if && csr_rpc))) {
     int rt = pert_tile_fwd(q, k, v, s, ld, rowptr, csr_src, csr_if, csr_rpc, t_if, t_rpc, n_rpc, out, ld_out, alpha, N, E,
-                           B_hint, H, bn_acc, (cudaStream_t)stream);
+                           B_hint, H, bn_acc, tiles, (cudaStream_t)stream);
     if (rt == PERT_OK) {
-      *fused = 1;
+      *fused = bn_acc ? 1 : 0;
       PERT_LAUNCH_CHECK();
       return PERT_OK;
     }
@@ -477,6 +477,30 @@ int pert_tconv_fwd_stats(const float* q, const float* k, const float* v, const f
   }
   return pert_tconv_fwd(q, k, v, s, ld, rowptr, csr_src, csr_if, csr_rpc, t_if, t_rpc, out, ld_out, alpha, n_rpc, N, E,
                         B_hint, H, stream);
+}
+
+// Engine-internal form of pert_tconv_bwd with a graph-aligned tile list (falls back to the public entry without one).
+int pert_tconv_bwd_tiles(const float* g, int ld_g, const float* q, const float* k, const float* v, int ld,
+                         const int* rowptr, const int* csr_src, const int* csr_if, const int* csr_rpc,
+                         const int* colptr, const int* csc_pos, const int* csc_dst, const float* t_if,
+                         const float* t_rpc, const float* alpha, float* dq, float* dk, float* dv, int ld_d, float* dsp,
+                         float* rpc_ws, float* dt_if, float* dt_rpc, int n_rpc, long long N, long long E,
+                         long long B_hint, int H, const PertTiles* tiles, void* stream) {
+  if (tiles && N > 0 && tile_enabled() && ld_d == H && g && q && k && v && rowptr && colptr && dq && dk && dv &&
+      !(ld % 4) && !(ld_g % 4) && aligned16(g) && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(dq) &&
+      aligned16(dk) && aligned16(dv) &&
+      (!t_if || (t_rpc && dt_if && dt_rpc && csr_if && csr_rpc && aligned16(dt_if) && aligned16(dt_rpc)))) {
+    int rt = pert_tile_bwd(g, ld_g, q, k, v, ld, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos, csc_dst, t_if, t_rpc,
+                           alpha, dq, dk, dv, ld_d, dsp, rpc_ws, dt_if, dt_rpc, n_rpc, N, E, B_hint, H, tiles,
+                           (cudaStream_t)stream);
+    if (rt == PERT_OK) {
+      PERT_LAUNCH_CHECK();
+      return PERT_OK;
+    }
+    if (rt != PERT_ERR_UNSUPPORTED) return rt;
+  }
+  return pert_tconv_bwd(g, ld_g, q, k, v, ld, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos, csc_dst, t_if, t_rpc,
+                        alpha, dq, dk, dv, ld_d, dsp, rpc_ws, dt_if, dt_rpc, n_rpc, N, E, B_hint, H, stream);
 }
 
 extern "C" {
@@ -492,7 +516,7 @@ int pert_tconv_fwd(const float* q, const float* k, const float* v, const float* 
   if (N == 0) return PERT_OK;
   if (tile_enabled() && ld_out == H) {
     int rt = pert_tile_fwd(q, k, v, s, ld, rowptr, csr_src, csr_if, csr_rpc, t_if, t_rpc, n_rpc, out, ld_out, alpha, N, E,
-                           B_hint, H, nullptr, (cudaStream_t)stream);
+                           B_hint, H, nullptr, nullptr, (cudaStream_t)stream);
     if (rt != PERT_ERR_UNSUPPORTED) {
       if (rt) return rt;
       PERT_LAUNCH_CHECK();
@@ -527,7 +551,7 @@ int pert_tconv_bwd(const float* g, int ld_g, const float* q, const float* k, con
   if (N == 0) return PERT_OK;
   if (tile_enabled() && ld_d == H) {
     int rt = pert_tile_bwd(g, ld_g, q, k, v, ld, rowptr, csr_src, csr_if, csr_rpc, colptr, csc_pos, csc_dst, t_if, t_rpc,
-                           alpha, dq, dk, dv, ld_d, dsp, rpc_ws, dt_if, dt_rpc, n_rpc, N, E, B_hint, H, (cudaStream_t)stream);
+                           alpha, dq, dk, dv, ld_d, dsp, rpc_ws, dt_if, dt_rpc, n_rpc, N, E, B_hint, H, nullptr, (cudaStream_t)stream);
     if (rt != PERT_ERR_UNSUPPORTED) {
       if (rt) return rt;
       PERT_LAUNCH_CHECK();

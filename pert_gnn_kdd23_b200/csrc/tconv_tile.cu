@@ -74,6 +74,11 @@ struct TileArgs {
   float* rpc_ws;    // [N][2][RPC_FAST] per-target sums over in-edges of (alpha, ds) by rpc type, or null (see bwd_src)
   int N, tile_nodes, edge_cap;
   float inv_sqrt_c;
+  // graph-aligned tile list (csrc: k_build_tiles): tile t = nodes [tile_ptr[t], tile_ptr[t+1]); null = fixed tiles of
+  // tile_nodes nodes, one per CTA.  CTAs draw tiles from `ticket` (self-resetting counter) until it exceeds *ntiles.
+  const int* tile_ptr;
+  const int* ntiles;
+  unsigned int* ticket;
 };
 
 // Gradient of the (tiny, hot) rpc-type table without per-edge atomics: for an edge t -> i of rpc type b the table row
@@ -94,6 +99,7 @@ struct Smem {
   uint64_t* bar;
   float *ta, *tb, *rpc;
   int *ptr, *e0, *e1;
+  unsigned short* ord;   // node slots in descending-degree order (tile-local ids, T <= 65535)
   float *f0, *f1;
 };
 __device__ __forceinline__ Smem carve_smem(unsigned char* base, int T, int H, int n_rpc, int ecap) {
@@ -104,6 +110,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base, int T, int H, in
   s.tb = f; f += (size_t)T * H;
   s.rpc = f; f += (size_t)n_rpc * H;
   s.ptr = reinterpret_cast<int*>(f); f += ((T + 1 + 3) / 4) * 4;
+  s.ord = reinterpret_cast<unsigned short*>(f); f += ((T + 7) / 8) * 4;
   s.e0 = reinterpret_cast<int*>(f); f += ecap;
   s.e1 = reinterpret_cast<int*>(f); f += ecap;
   s.f0 = f; f += ecap;       // only the first NA arrays are backed by memory (see smem_bytes)
@@ -111,26 +118,74 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base, int T, int H, in
   return s;
 }
 static size_t smem_bytes(int T, int H, int n_rpc, int ecap, int n_edge_arrays) {
-  return 16 + sizeof(float) * ((size_t)2 * T * H + (size_t)n_rpc * H + ((T + 1 + 3) / 4) * 4 +
+  return 16 + sizeof(float) * ((size_t)2 * T * H + (size_t)n_rpc * H + ((T + 1 + 3) / 4) * 4 + ((T + 7) / 8) * 4 +
                                (size_t)n_edge_arrays * ecap);
 }
 
-// stage the two operand tiles + the node-pointer slice; returns after the pointers are visible (tiles: mbar_wait)
+// Tile scheduling shared by the three kernels: with a tile list the CTA draws tile ids from a self-resetting ticket
+// (the draw that returns ntiles + gridDim.x - 1 is the last of the launch and zeroes the counter), else it owns the one
+// fixed tile blockIdx.x.  Returns false when there is no more work.  Contains CTA barriers: call from all threads.
+__device__ __forceinline__ bool next_tile(const TileArgs& a, bool first, int& n0, int& nt) {
+  __shared__ int s_tile;
+  if (!a.tile_ptr) {
+    if (!first) return false;
+    n0 = blockIdx.x * a.tile_nodes;
+    nt = min(a.tile_nodes, a.N - n0);
+    return nt > 0;
+  }
+  __syncthreads();                       // every reader of the previous tile's shared memory (and of s_tile) is done
+  if (threadIdx.x == 0) {
+    const unsigned int total = (unsigned int)*a.ntiles;
+    const unsigned int c = atomicAdd(a.ticket, 1u);
+    if (c >= total && c == total + gridDim.x - 1) *a.ticket = 0;
+    s_tile = c < total ? (int)c : -1;
+  }
+  __syncthreads();
+  const int t = s_tile;
+  if (t < 0) return false;
+  n0 = a.tile_ptr[t];
+  nt = a.tile_ptr[t + 1] - n0;
+  return true;
+}
+
+// stage the two operand tiles + the node-pointer slice + the degree-sorted node order; returns after the pointers and
+// the order are visible (tiles: mbar_wait on the caller's phase).  The mbarrier is initialised once by the caller.
+// Lane groups of a warp walk their nodes' edges in lockstep (trip count = the largest degree in the warp): handing the
+// nodes out in DESCENDING DEGREE order puts equal degrees side by side (no idle lockstep iterations: E[max of 2 degrees]
+// is 3.8 against a mean of 3.0 at cfg2) and starts the long rows first.  Counting sort over degrees clamped to 32.
 template <int H>
 __device__ __forceinline__ void stage_tiles(const Smem& S, const float* pa, const float* pb, const int* nodeptr,
                                             int n0, int nt, int tid) {
-  if (tid == 0) {
-    mbar_init(S.bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
+  __shared__ int s_hist[34];
   if (tid == 0) {
     const uint32_t tile_bytes = (uint32_t)nt * H * 4;
     mbar_expect_tx(S.bar, 2 * tile_bytes);
     bulk_g2s(S.ta, pa + (size_t)n0 * H, tile_bytes, S.bar);
     bulk_g2s(S.tb, pb + (size_t)n0 * H, tile_bytes, S.bar);
   }
+  if (tid < 34) s_hist[tid] = 0;
   for (int x = tid; x <= nt; x += TILE_THREADS) S.ptr[x] = __ldg(nodeptr + n0 + x);
+  __syncthreads();
+  for (int x = tid; x < nt; x += TILE_THREADS) atomicAdd(&s_hist[32 - min(S.ptr[x + 1] - S.ptr[x], 32)], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int b = 0; b < 33; ++b) {
+      const int c = s_hist[b];
+      s_hist[b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int x = tid; x < nt; x += TILE_THREADS)
+    S.ord[atomicAdd(&s_hist[32 - min(S.ptr[x + 1] - S.ptr[x], 32)], 1)] = (unsigned short)x;
+  __syncthreads();
+}
+__device__ __forceinline__ void tile_barrier_init(const Smem& S, int tid) {
+  if (tid == 0) {
+    mbar_init(S.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 }
 
@@ -146,6 +201,11 @@ __device__ __forceinline__ int ldsi(uint32_t a) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ int ldsu16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return (int)v;
+}
 __device__ __forceinline__ float ldsf(uint32_t a) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -159,11 +219,12 @@ __device__ __forceinline__ float gsum_full(float v) {   // butterfly inside each
   return v;
 }
 struct SAddr {   // shared-space byte addresses of the staged arrays
-  uint32_t ta, tb, rpc, ptr, e0, e1, f0, f1;
+  uint32_t ta, tb, rpc, ptr, ord, e0, e1, f0, f1;
 };
 __device__ __forceinline__ SAddr saddr_of(const Smem& S) {
   SAddr s;
   s.ta = smem_u32(S.ta); s.tb = smem_u32(S.tb); s.rpc = smem_u32(S.rpc); s.ptr = smem_u32(S.ptr);
+  s.ord = smem_u32(S.ord);
   s.e0 = smem_u32(S.e0); s.e1 = smem_u32(S.e1); s.f0 = smem_u32(S.f0); s.f1 = smem_u32(S.f1);
   return s;
 }
@@ -176,137 +237,141 @@ template <int LPR, bool HAS_E>
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
   constexpr int H = 4 * LPR;
   constexpr int GPW = 32 / LPR;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int T = a.tile_nodes;
-  const Smem S = carve_smem(smem_raw, T, H, 0, a.edge_cap);
-  const int n0 = blockIdx.x * T;
-  const int nt = min(T, a.N - n0);
-  const int tid = threadIdx.x;
-  stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
-  const int e_lo = S.ptr[0];
-  const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
-  int bad = 0;   // a staged neighbour outside this tile
-  for (int x = tid; x < ne_s; x += TILE_THREADS) {
-    const int nb_id = __ldg(a.csr_src + e_lo + x);
-    S.e0[x] = nb_id;
-    bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
-    if (HAS_E) S.e1[x] = PACK_ID(__ldg(a.csr_if + e_lo + x), __ldg(a.csr_rpc + e_lo + x));
-  }
-  // fast variant of the edge loops when every edge of the tile is staged and every neighbour row is in the tile
-  // (whole-graph tiles): no global-memory fallbacks are compiled into it
-  const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - e_lo <= a.edge_cap);
-  mbar_wait(S.bar, 0);
-
-  const SAddr sa = saddr_of(S);
-  const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
   constexpr int GPC = TILE_THREADS / LPR;  // lane groups per CTA
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const Smem S = carve_smem(smem_raw, a.tile_nodes, H, 0, a.edge_cap);
+  const SAddr sa = saddr_of(S);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
   const float qscale = a.inv_sqrt_c * 1.4426950408889634f;   // logits kept in log2 units: exp(x) = 2^(x*log2 e)
   const uint32_t lane4 = lig * 16;
-  const int g0 = (tid >> 5) * GPW;          // first group of this warp
-  // q / skip rows of the next node are requested one node ahead
-  int loc = g0 + grp;
-  float4 q_n = f4zero(), s_n = f4zero();
-  if (loc < nt) {
-    q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
-    if (a.s) s_n = ldg4(a.s + (size_t)(n0 + loc) * H + lig * 4);
-  }
+  const int g0 = (tid >> 5) * GPW;          // first group slot of this warp
   float4 bsum = f4zero(), bsq = f4zero();   // this lane's 4 columns over its nodes (fused BatchNorm statistics)
-  auto run = [&](auto fast_c) {
-    constexpr bool FAST = decltype(fast_c)::value;
-    for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {   // warp-uniform: the warp's first group still has a node
-      const bool valid = loc < nt;
-      const int i = n0 + loc;
-      const float4 q = f4scale(qscale, q_n);
-      const float4 skip = s_n;
-      if (loc + GPC < nt) {
-        q_n = ldg4(a.q + (size_t)(i + GPC) * H + lig * 4);
-        if (a.s) s_n = ldg4(a.s + (size_t)(i + GPC) * H + lig * 4);
-      }
-      const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
-      const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
-      const int deg = p1 - p0;
-      const int degmax = __reduce_max_sync(0xffffffffu, deg);
-      float4 acc = f4zero();
-      float m = -INFINITY, Z = 0.f;
-      // software pipeline over edges: ids + table rows of edge t+1 are requested before edge t is consumed
-      int j = n0, id = 0;
-      float4 eif = f4zero(), erp = f4zero();
-      auto fetch = [&](int p, bool on) {
-        j = n0;
-        id = 0;
-        if (on) {
-          const int le = p - e_lo;
-          if (FAST || le < ne_s) {
-            j = ldsi(sa.e0 + le * 4);
-            if (HAS_E) id = ldsi(sa.e1 + le * 4);
-          } else {
-            j = __ldg(a.csr_src + p);
-            if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
-          }
-        }
-        if (HAS_E) {
-          eif = ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4);
-          erp = ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4);
-        }
-      };
-      fetch(p0, 0 < deg);
-      for (int t = 0; t < degmax; ++t) {
-        const bool on = t < deg;
-        const int p = p0 + t;
-        const int cj = j;
-        const float4 e = f4add(eif, erp);
-        fetch(p + 1, t + 1 < deg);
-        float4 kk, vv;
-        const unsigned sl = (unsigned)(cj - n0);
-        if (FAST || sl < (unsigned)nt) {
-          kk = lds4s(sa.ta + sl * (H * 4) + lane4);
-          vv = lds4s(sa.tb + sl * (H * 4) + lane4);
-        } else {
-          kk = ldg4(a.k + (size_t)cj * H + lig * 4);
-          vv = ldg4(a.v + (size_t)cj * H + lig * 4);
-        }
-        if (HAS_E) {
-          kk = f4add(kk, e);
-          vv = f4add(vv, e);
-        }
-        const float s = gsum_full<LPR>(f4dot(q, kk));
-        if (on && lig == 0) {
-          const int le = p - e_lo;
-          if (FAST || le < ne_s) stsf(sa.f0 + le * 4, s);
-          else a.alpha[p] = s;
-        }
-        const float mn = on ? fmaxf(m, s) : m;
-        const float sc = on ? ex2(m - mn) : 1.f;
-        const float pz = on ? ex2(s - mn) : 0.f;
-        Z = fmaf(Z, sc, pz);
-        acc.x = fmaf(pz, vv.x, acc.x * sc);
-        acc.y = fmaf(pz, vv.y, acc.y * sc);
-        acc.z = fmaf(pz, vv.z, acc.z * sc);
-        acc.w = fmaf(pz, vv.w, acc.w * sc);
-        m = mn;
-      }
-      const float invZ = 1.0f / (Z + 1e-16f);
-      if (valid) {
-        const float4 o = f4add(f4scale(invZ, acc), skip);
-        st4(a.out + (size_t)i * H + lig * 4, o);
-        bsum = f4add(bsum, o);
-        bsq.x = fmaf(o.x, o.x, bsq.x); bsq.y = fmaf(o.y, o.y, bsq.y);
-        bsq.z = fmaf(o.z, o.z, bsq.z); bsq.w = fmaf(o.w, o.w, bsq.w);
-      }
-      __syncwarp();
-      for (int p = p0 + lig; p < p1; p += LPR) {
-        const int le = p - e_lo;
-        const float s = (FAST || le < ne_s) ? ldsf(sa.f0 + le * 4) : a.alpha[p];
-        a.alpha[p] = ex2(s - m) * invZ;
-      }
+  tile_barrier_init(S, tid);
+  uint32_t phase = 0;
+  int n0, nt;
+  for (bool first = true; next_tile(a, first, n0, nt); first = false, phase ^= 1) {
+    stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
+    const int e_lo = S.ptr[0];
+    const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
+    int bad = 0;   // a staged neighbour outside this tile
+    for (int x = tid; x < ne_s; x += TILE_THREADS) {
+      const int nb_id = __ldg(a.csr_src + e_lo + x);
+      S.e0[x] = nb_id;
+      bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
+      if (HAS_E) S.e1[x] = PACK_ID(__ldg(a.csr_if + e_lo + x), __ldg(a.csr_rpc + e_lo + x));
     }
-  };
-  if (all_in) run(std::true_type{});
-  else run(std::false_type{});
+    // fast variant of the edge loops when every edge of the tile is staged and every neighbour row is in the tile
+    // (whole-graph tiles): no global-memory fallbacks are compiled into it
+    const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - e_lo <= a.edge_cap);
+    mbar_wait(S.bar, phase);
+
+    // node slots are handed out in descending-degree order (S.ord); q / skip rows are requested one node ahead
+    int slot = g0 + grp;
+    int loc = slot < nt ? ldsu16(sa.ord + slot * 2) : 0;
+    float4 q_n = f4zero(), s_n = f4zero();
+    if (slot < nt) {
+      q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
+      if (a.s) s_n = ldg4(a.s + (size_t)(n0 + loc) * H + lig * 4);
+    }
+    auto run = [&](auto fast_c) {
+      constexpr bool FAST = decltype(fast_c)::value;
+      for (; slot - grp < nt; slot += GPC) {   // warp-uniform: the warp's first group still has a node
+        const bool valid = slot < nt;
+        const int i = n0 + loc;
+        const float4 q = f4scale(qscale, q_n);
+        const float4 skip = s_n;
+        const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
+        const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
+        if (slot + GPC < nt) {
+          loc = ldsu16(sa.ord + (slot + GPC) * 2);
+          q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
+          if (a.s) s_n = ldg4(a.s + (size_t)(n0 + loc) * H + lig * 4);
+        }
+        const int deg = p1 - p0;
+        const int degmax = __reduce_max_sync(0xffffffffu, deg);
+        float4 acc = f4zero();
+        float m = -INFINITY, Z = 0.f;
+        // software pipeline over edges: ids + table rows of edge t+1 are requested before edge t is consumed
+        int j = n0, id = 0;
+        float4 eif = f4zero(), erp = f4zero();
+        auto fetch = [&](int p, bool on) {
+          j = n0;
+          id = 0;
+          if (on) {
+            const int le = p - e_lo;
+            if (FAST || le < ne_s) {
+              j = ldsi(sa.e0 + le * 4);
+              if (HAS_E) id = ldsi(sa.e1 + le * 4);
+            } else {
+              j = __ldg(a.csr_src + p);
+              if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+            }
+          }
+          if (HAS_E) {
+            eif = ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4);
+            erp = ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4);
+          }
+        };
+        fetch(p0, 0 < deg);
+        for (int t = 0; t < degmax; ++t) {
+          const bool on = t < deg;
+          const int p = p0 + t;
+          const int cj = j;
+          const float4 e = f4add(eif, erp);
+          fetch(p + 1, t + 1 < deg);
+          float4 kk, vv;
+          const unsigned sl = (unsigned)(cj - n0);
+          if (FAST || sl < (unsigned)nt) {
+            kk = lds4s(sa.ta + sl * (H * 4) + lane4);
+            vv = lds4s(sa.tb + sl * (H * 4) + lane4);
+          } else {
+            kk = ldg4(a.k + (size_t)cj * H + lig * 4);
+            vv = ldg4(a.v + (size_t)cj * H + lig * 4);
+          }
+          if (HAS_E) {
+            kk = f4add(kk, e);
+            vv = f4add(vv, e);
+          }
+          const float s = gsum_full<LPR>(f4dot(q, kk));
+          if (on && lig == 0) {
+            const int le = p - e_lo;
+            if (FAST || le < ne_s) stsf(sa.f0 + le * 4, s);
+            else a.alpha[p] = s;
+          }
+          const float mn = on ? fmaxf(m, s) : m;
+          const float sc = on ? ex2(m - mn) : 1.f;
+          const float pz = on ? ex2(s - mn) : 0.f;
+          Z = fmaf(Z, sc, pz);
+          acc.x = fmaf(pz, vv.x, acc.x * sc);
+          acc.y = fmaf(pz, vv.y, acc.y * sc);
+          acc.z = fmaf(pz, vv.z, acc.z * sc);
+          acc.w = fmaf(pz, vv.w, acc.w * sc);
+          m = mn;
+        }
+        const float invZ = 1.0f / (Z + 1e-16f);
+        if (valid) {
+          const float4 o = f4add(f4scale(invZ, acc), skip);
+          st4(a.out + (size_t)i * H + lig * 4, o);
+          bsum = f4add(bsum, o);
+          bsq.x = fmaf(o.x, o.x, bsq.x); bsq.y = fmaf(o.y, o.y, bsq.y);
+          bsq.z = fmaf(o.z, o.z, bsq.z); bsq.w = fmaf(o.w, o.w, bsq.w);
+        }
+        __syncwarp();
+        for (int p = p0 + lig; p < p1; p += LPR) {
+          const int le = p - e_lo;
+          const float s = (FAST || le < ne_s) ? ldsf(sa.f0 + le * 4) : a.alpha[p];
+          a.alpha[p] = ex2(s - m) * invZ;
+        }
+      }
+    };
+    if (all_in) run(std::true_type{});
+    else run(std::false_type{});
+  }
   if (a.bn_acc) {
-    // BatchNorm statistics of this layer's output, fused: column sums and sums of squares of the tile (per-lane fp32
-    // partials over <= a handful of nodes, combined in fp64) -> one fp64 atomic per column and tile into bn_acc, the
-    // accumulator k_bn_apply derives mean / rstd from (nodeops.cu).  Saves the separate statistics pass over `out`.
+    // BatchNorm statistics of this layer's output, fused: column sums and sums of squares over the CTA's tiles (per-lane
+    // fp32 partials, combined in fp64) -> one fp64 atomic per column and CTA into bn_acc, the accumulator k_bn_apply
+    // derives mean / rstd from (nodeops.cu).  Saves the separate statistics pass over `out`.
     __syncthreads();                                   // every warp is done with the staged tiles
     double* sc = reinterpret_cast<double*>(S.ta);
     for (int x = tid; x < 2 * H; x += TILE_THREADS) sc[x] = 0.0;
@@ -320,7 +385,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
       if (grp == 0) atomicAdd(&sc[(kk < 4 ? 0 : H) + lig * 4 + (kk & 3)], (double)v);
     }
     __syncthreads();
-    for (int x = tid; x < 2 * H; x += TILE_THREADS) atomicAdd(a.bn_acc + x, sc[x]);
+    for (int x = tid; x < 2 * H; x += TILE_THREADS)
+      if (sc[x] != 0.0) atomicAdd(a.bn_acc + x, sc[x]);
   }
 }
 
@@ -330,128 +396,134 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
   constexpr int H = 4 * LPR;
   constexpr int GPW = 32 / LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int T = a.tile_nodes;
-  const Smem S = carve_smem(smem_raw, T, H, 0, a.edge_cap);
-  const int n0 = blockIdx.x * T;
-  const int nt = min(T, a.N - n0);
-  const int tid = threadIdx.x;
-  stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
-  const int e_lo = S.ptr[0];
-  const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
-  int bad = 0;   // a staged neighbour outside this tile
-  for (int x = tid; x < ne_s; x += TILE_THREADS) {
-    const int nb_id = __ldg(a.csr_src + e_lo + x);
-    S.e0[x] = nb_id;
-    bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
-    S.f0[x] = __ldg(a.alpha + e_lo + x);
-    if (HAS_E) S.e1[x] = PACK_ID(__ldg(a.csr_if + e_lo + x), __ldg(a.csr_rpc + e_lo + x));
-  }
-  // fast variant of the edge loops when every edge of the tile is staged and every neighbour row is in the tile
-  // (whole-graph tiles): no global-memory fallbacks are compiled into it
-  const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - e_lo <= a.edge_cap);
-  mbar_wait(S.bar, 0);
-
-  const SAddr sa = saddr_of(S);
-  const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
   constexpr int GPC = TILE_THREADS / LPR;
+  const Smem S = carve_smem(smem_raw, a.tile_nodes, H, 0, a.edge_cap);
+  const SAddr sa = saddr_of(S);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
   const uint32_t lane4 = lig * 16;
   const int g0 = (tid >> 5) * GPW;
-  int loc = g0 + grp;
-  float4 g_n = f4zero();
-  if (loc < nt) g_n = ldg4(a.g + (size_t)(n0 + loc) * H + lig * 4);
-  auto run = [&](auto fast_c) {
-    constexpr bool FAST = decltype(fast_c)::value;
-    for (; g0 + (loc - g0 - grp) < nt; loc += GPC) {
-      const bool valid = loc < nt;
-      const int i = n0 + loc;
-      const float4 g = g_n;
-      if (loc + GPC < nt) g_n = ldg4(a.g + (size_t)(i + GPC) * H + lig * 4);
-      const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
-      const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
-      const int deg = p1 - p0;
-      const int degmax = __reduce_max_sync(0xffffffffu, deg);
-      // one edge record: source row offsets + e = T_if[a] + T_rpc[b]
-      auto edge = [&](int p, bool on, int& j, float& al, float4& e, int& rid) {
-        j = n0;
-        al = 0.f;
-        int id = 0;
-        if (on) {
-          const int le = p - e_lo;
-          if (FAST || le < ne_s) {
-            j = ldsi(sa.e0 + le * 4);
-            al = ldsf(sa.f0 + le * 4);
-            if (HAS_E) id = ldsi(sa.e1 + le * 4);
+  tile_barrier_init(S, tid);
+  uint32_t phase = 0;
+  int n0, nt;
+  for (bool first = true; next_tile(a, first, n0, nt); first = false, phase ^= 1) {
+    stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
+    const int e_lo = S.ptr[0];
+    const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
+    int bad = 0;   // a staged neighbour outside this tile
+    for (int x = tid; x < ne_s; x += TILE_THREADS) {
+      const int nb_id = __ldg(a.csr_src + e_lo + x);
+      S.e0[x] = nb_id;
+      bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
+      S.f0[x] = __ldg(a.alpha + e_lo + x);
+      if (HAS_E) S.e1[x] = PACK_ID(__ldg(a.csr_if + e_lo + x), __ldg(a.csr_rpc + e_lo + x));
+    }
+    // fast variant of the edge loops when every edge of the tile is staged and every neighbour row is in the tile
+    // (whole-graph tiles): no global-memory fallbacks are compiled into it
+    const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - e_lo <= a.edge_cap);
+    mbar_wait(S.bar, phase);
+
+    int slot = g0 + grp;
+    int loc = slot < nt ? ldsu16(sa.ord + slot * 2) : 0;
+    float4 g_n = f4zero();
+    if (slot < nt) g_n = ldg4(a.g + (size_t)(n0 + loc) * H + lig * 4);
+    auto run = [&](auto fast_c) {
+      constexpr bool FAST = decltype(fast_c)::value;
+      for (; slot - grp < nt; slot += GPC) {
+        const bool valid = slot < nt;
+        const int i = n0 + loc;
+        const float4 g = g_n;
+        const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
+        const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
+        if (slot + GPC < nt) {
+          loc = ldsu16(sa.ord + (slot + GPC) * 2);
+          g_n = ldg4(a.g + (size_t)(n0 + loc) * H + lig * 4);
+        }
+        const int deg = p1 - p0;
+        const int degmax = __reduce_max_sync(0xffffffffu, deg);
+        // one edge record: source row offsets + e = T_if[a] + T_rpc[b]
+        auto edge = [&](int p, bool on, int& j, float& al, float4& e, int& rid) {
+          j = n0;
+          al = 0.f;
+          int id = 0;
+          if (on) {
+            const int le = p - e_lo;
+            if (FAST || le < ne_s) {
+              j = ldsi(sa.e0 + le * 4);
+              al = ldsf(sa.f0 + le * 4);
+              if (HAS_E) id = ldsi(sa.e1 + le * 4);
+            } else {
+              j = __ldg(a.csr_src + p);
+              al = __ldg(a.alpha + p);
+              if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+            }
+          }
+          e = f4zero();
+          if (HAS_E)
+            e = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4), ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4));
+          rid = ID_RPC(id);
+        };
+        // ONE pass over the in-edges.  With d_t = <g_i, v_j + e_t> (shifted by the first edge's value c, which cancels
+        // exactly: sum_t ds_t = 0), w_t = alpha_t (d_t - c) and dot = sum_t w_t:
+        //   ds_t = alpha_t (d_t - c - dot) / sqrt(C)
+        //   dq_i = sum_t ds_t (k_j + e_t) = (P - dot Q) / sqrt(C),   P = sum_t w_t (k_j + e_t),  Q = sum_t alpha_t (k_j + e_t)
+        // so k_j, v_j and the table rows of an edge are fetched once (the two-pass form fetched the edge record and
+        // its table rows twice); ds_t is written by a scalar post-pass with the lanes spread over the node's edges.
+        float dot = 0.f, c_shift = 0.f;
+        float4 P = f4zero(), Q = f4zero();
+        float sumA = 0.f, sumW = 0.f;          // lane b: sums of alpha / w over this node's in-edges of rpc type b
+        for (int t = 0; t < degmax; ++t) {
+          const bool on = t < deg;
+          const int p = p0 + t;
+          int j, rid;
+          float al;
+          float4 e;
+          edge(p, on, j, al, e, rid);
+          float4 kk, vv;
+          const unsigned sl = (unsigned)(j - n0);
+          if (FAST || sl < (unsigned)nt) {
+            kk = lds4s(sa.ta + sl * (H * 4) + lane4);
+            vv = lds4s(sa.tb + sl * (H * 4) + lane4);
           } else {
-            j = __ldg(a.csr_src + p);
-            al = __ldg(a.alpha + p);
-            if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
+            kk = ldg4(a.k + (size_t)j * H + lig * 4);
+            vv = ldg4(a.v + (size_t)j * H + lig * 4);
+          }
+          const float da = gsum_full<LPR>(f4dot(g, f4add(vv, e)));
+          if (t == 0) c_shift = da;
+          const float dc = da - c_shift;
+          const float w = al * dc;             // alpha is 0 on finished groups
+          dot += w;
+          const float4 ke = f4add(kk, e);
+          P = f4fma(w, ke, P);
+          Q = f4fma(al, ke, Q);
+          if (HAS_E && on && lig == rid) { sumA += al; sumW += w; }
+          if (on && lig == 0) {
+            const int le = p - e_lo;
+            if (FAST || le < ne_s) stsf(sa.f1 + le * 4, dc);
+            else a.dsp[p] = dc;
           }
         }
-        e = f4zero();
-        if (HAS_E)
-          e = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4), ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4));
-        rid = ID_RPC(id);
-      };
-      // ONE pass over the in-edges.  With d_t = <g_i, v_j + e_t> (shifted by the first edge's value c, which cancels
-      // exactly: sum_t ds_t = 0), w_t = alpha_t (d_t - c) and dot = sum_t w_t:
-      //   ds_t = alpha_t (d_t - c - dot) / sqrt(C)
-      //   dq_i = sum_t ds_t (k_j + e_t) = (P - dot Q) / sqrt(C),   P = sum_t w_t (k_j + e_t),  Q = sum_t alpha_t (k_j + e_t)
-      // so k_j, v_j and the table rows of an edge are fetched once (the two-pass form fetched the edge record and
-      // its table rows twice); ds_t is written by a scalar post-pass with the lanes spread over the node's edges.
-      float dot = 0.f, c_shift = 0.f;
-      float4 P = f4zero(), Q = f4zero();
-      float sumA = 0.f, sumW = 0.f;          // lane b: sums of alpha / w over this node's in-edges of rpc type b
-      for (int t = 0; t < degmax; ++t) {
-        const bool on = t < deg;
-        const int p = p0 + t;
-        int j, rid;
-        float al;
-        float4 e;
-        edge(p, on, j, al, e, rid);
-        float4 kk, vv;
-        const unsigned sl = (unsigned)(j - n0);
-        if (FAST || sl < (unsigned)nt) {
-          kk = lds4s(sa.ta + sl * (H * 4) + lane4);
-          vv = lds4s(sa.tb + sl * (H * 4) + lane4);
-        } else {
-          kk = ldg4(a.k + (size_t)j * H + lig * 4);
-          vv = ldg4(a.v + (size_t)j * H + lig * 4);
-        }
-        const float da = gsum_full<LPR>(f4dot(g, f4add(vv, e)));
-        if (t == 0) c_shift = da;
-        const float dc = da - c_shift;
-        const float w = al * dc;             // alpha is 0 on finished groups
-        dot += w;
-        const float4 ke = f4add(kk, e);
-        P = f4fma(w, ke, P);
-        Q = f4fma(al, ke, Q);
-        if (HAS_E && on && lig == rid) { sumA += al; sumW += w; }
-        if (on && lig == 0) {
+        float4 dq;
+        dq.x = (P.x - dot * Q.x) * a.inv_sqrt_c; dq.y = (P.y - dot * Q.y) * a.inv_sqrt_c;
+        dq.z = (P.z - dot * Q.z) * a.inv_sqrt_c; dq.w = (P.w - dot * Q.w) * a.inv_sqrt_c;
+        const float sumS = (sumW - dot * sumA) * a.inv_sqrt_c;
+        __syncwarp();
+        for (int p = p0 + lig; p < p1; p += LPR) {
           const int le = p - e_lo;
-          if (FAST || le < ne_s) stsf(sa.f1 + le * 4, dc);
-          else a.dsp[p] = dc;
+          const float dc = (FAST || le < ne_s) ? ldsf(sa.f1 + le * 4) : a.dsp[p];
+          const float al = (FAST || le < ne_s) ? ldsf(sa.f0 + le * 4) : __ldg(a.alpha + p);
+          a.dsp[p] = al * (dc - dot) * a.inv_sqrt_c;
+        }
+        if (valid) st4(a.out + (size_t)i * H + lig * 4, dq);
+        if (HAS_E && a.rpc_ws && valid && lig < RPC_FAST) {
+          a.rpc_ws[(size_t)i * 2 * RPC_FAST + lig] = sumA;
+          a.rpc_ws[(size_t)i * 2 * RPC_FAST + RPC_FAST + lig] = sumS;
         }
       }
-      float4 dq;
-      dq.x = (P.x - dot * Q.x) * a.inv_sqrt_c; dq.y = (P.y - dot * Q.y) * a.inv_sqrt_c;
-      dq.z = (P.z - dot * Q.z) * a.inv_sqrt_c; dq.w = (P.w - dot * Q.w) * a.inv_sqrt_c;
-      const float sumS = (sumW - dot * sumA) * a.inv_sqrt_c;
-      __syncwarp();
-      for (int p = p0 + lig; p < p1; p += LPR) {
-        const int le = p - e_lo;
-        const float dc = (FAST || le < ne_s) ? ldsf(sa.f1 + le * 4) : a.dsp[p];
-        const float al = (FAST || le < ne_s) ? ldsf(sa.f0 + le * 4) : __ldg(a.alpha + p);
-        a.dsp[p] = al * (dc - dot) * a.inv_sqrt_c;
-      }
-      if (valid) st4(a.out + (size_t)i * H + lig * 4, dq);
-      if (HAS_E && a.rpc_ws && valid && lig < RPC_FAST) {
-        a.rpc_ws[(size_t)i * 2 * RPC_FAST + lig] = sumA;
-        a.rpc_ws[(size_t)i * 2 * RPC_FAST + RPC_FAST + lig] = sumS;
-      }
-    }
-  };
-  if (all_in) run(std::true_type{});
-  else run(std::false_type{});
+    };
+    if (all_in) run(std::true_type{});
+    else run(std::false_type{});
+  }
 }
 
 // ============================================================== backward, source pass (dk, dv, table grads)
@@ -460,14 +532,20 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   constexpr int H = 4 * LPR;
   constexpr int GPW = 32 / LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int T = a.tile_nodes;
-  const Smem S = carve_smem(smem_raw, T, H, HAS_E ? a.n_rpc : 0, a.edge_cap);
-  const int n0 = blockIdx.x * T;
-  const int nt = min(T, a.N - n0);
+  constexpr int GPC = TILE_THREADS / LPR;
+  const Smem S = carve_smem(smem_raw, a.tile_nodes, H, HAS_E ? a.n_rpc : 0, a.edge_cap);
+  const SAddr sa = saddr_of(S);
   const int tid = threadIdx.x;
+  const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
+  const uint32_t lane4 = lig * 16;
+  const int g0 = (tid >> 5) * GPW;
   float* s_drpc = S.rpc;   // privatised gradient of the rpc-type table (few hot rows), flushed once per CTA
   if (HAS_E)
     for (int x = tid; x < a.n_rpc * H; x += TILE_THREADS) s_drpc[x] = 0.f;
+  tile_barrier_init(S, tid);
+  uint32_t phase = 0;
+  int n0, nt;
+  for (bool first = true; next_tile(a, first, n0, nt); first = false, phase ^= 1) {
   stage_tiles<H>(S, a.g, a.q, a.colptr, n0, nt, tid);   // targets of a node's out-edges live in the same graph
   const int c_lo = S.ptr[0];
   const int ne_s = min(S.ptr[nt] - c_lo, a.edge_cap);
@@ -485,17 +563,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   // fast variant of the edge loops when every edge of the tile is staged and every neighbour row is in the tile
   // (whole-graph tiles): no global-memory fallbacks are compiled into it
   const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - c_lo <= a.edge_cap);
-  mbar_wait(S.bar, 0);
+  mbar_wait(S.bar, phase);
 
-  const SAddr sa = saddr_of(S);
-  const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
-  constexpr int GPC = TILE_THREADS / LPR;
-  const uint32_t lane4 = lig * 16;
-  const int g0 = (tid >> 5) * GPW;
   auto run = [&](auto fast_c) {
     constexpr bool FAST = decltype(fast_c)::value;
-    for (int loc = g0 + grp; g0 + (loc - g0 - grp) < nt; loc += GPC) {
-      const bool valid = loc < nt;
+    for (int slot = g0 + grp; slot - grp < nt; slot += GPC) {
+      const bool valid = slot < nt;
+      const int loc = valid ? ldsu16(sa.ord + slot * 2) : 0;
       const int jn = n0 + loc;
       const int c0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
       const int c1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
@@ -570,6 +644,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
     for (int b = 0; b < RPC_FAST; ++b)
       if (b < a.n_rpc && acc[b] != 0.f) atomicAdd(s_drpc + b * H + col, acc[b]);
   }
+  }   // tile loop
   if (HAS_E) {
     __syncthreads();
     for (int x = tid; x < a.n_rpc * H; x += TILE_THREADS) {
@@ -579,29 +654,86 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   }
 }
 
-// tile geometry for a launch: nodes per tile and staged-edge capacity within the per-CTA smem budget
-// (two CTAs per SM: (233472 / 2) - 1024 reserved).  When the batch holds B equally sized graphs the tile is a
-// whole number of graphs, so no edge ever crosses a tile boundary.
+// Tile geometry: nodes per tile (T) and staged-edge capacity (ecap) within the per-CTA shared-memory budget -- two CTAs
+// per SM ((233472 / 2) - 1024 reserved each) unless the average graph does not fit, then one.  ONE geometry serves the
+// three kernels of a layer (sized for the most demanding one: 4 per-edge arrays + the privatised rpc table), so one
+// tile list does too.
 struct TileGeom {
   int T, ecap;
-  size_t bytes;
 };
-TileGeom tile_geom(int H, int n_rpc, long long N, long long E, long long B, int n_edge_arrays) {
-  const double budget2 = 115712.0, budget1 = 231424.0;
+constexpr int STATIC_SMEM = 160;   // s_tile + s_hist[34] of the kernels' static shared memory, rounded up
+TileGeom tile_geom(int H, int n_rpc, long long N, long long E, long long B) {
+  const double budget2 = 115712.0 - STATIC_SMEM, budget1 = 231424.0 - STATIC_SMEM;
   const double deg = N > 0 ? (double)E / (double)N : 1.0;
-  const double per_node = 4.0 * (2.0 * H + 1.0 + n_edge_arrays * deg * 1.02);
-  const double fixed = 64.0 + 4.0 * n_rpc * H + 4.0 * n_edge_arrays * 20.0;
+  const double per_node = 4.0 * (2.0 * H + 1.0 + 0.5 + 4.0 * deg);
+  const double fixed = 64.0 + 4.0 * n_rpc * H + 4.0 * 4.0 * 12.0;
   auto fit = [&](double b) { return (long long)((b - fixed) / per_node); };
   long long T = fit(budget2);
-  const long long G = (B > 0 && N % B == 0) ? N / B : 0;   // uniform graph size, if any
-  if ((G > 0 && T < G) || T < 64) T = fit(budget1);        // wide rows / big graphs: one CTA per SM
-  if (G > 0 && G <= T) T = T / G * G;
+  const double avg = B > 0 ? (double)N / (double)B : 0.0;
+  if ((avg > 0 && (double)T < avg) || T < 64) T = fit(budget1);   // wide rows / big graphs: one CTA per SM
   if (T > N) T = N;
+  if (T > 65535) T = 65535;
   if (T < 1) T = 1;
-  int ecap = (int)(deg * 1.02 * (double)T) + 20;
+  int ecap = (int)(deg * (double)T + 0.999) + 8;
   ecap = (ecap + 3) / 4 * 4;
-  TileGeom g{(int)T, ecap, smem_bytes((int)T, H, n_rpc, ecap, n_edge_arrays)};
-  return g;
+  return TileGeom{(int)T, ecap};
+}
+
+// ---- graph-aligned tile list: greedy packing of WHOLE graphs (never cut while a graph fits a tile) up to T nodes /
+// ecap edges; a graph that alone exceeds a tile is cut into T-node pieces (those tiles run the global-gather variant).
+// One CTA: graph boundaries by binary search in the sorted `batch` vector (gptr), then a serial packing pass over the
+// B graphs out of shared memory (B <= a few thousand; ~10 cycles per graph).  batch == nullptr: fixed T-node tiles.
+__global__ void __launch_bounds__(1024) k_build_tiles(const int64_t* __restrict__ batch, int N, int B,
+                                                      const int* __restrict__ rowptr, int T, int ecap,
+                                                      int* __restrict__ gptr, int* __restrict__ tile_ptr,
+                                                      int* __restrict__ ntiles, int max_tiles) {
+  extern __shared__ int sg[];   // gptr copy [B+1] | edge offset of every graph start [B+1]   (when it fits)
+  const int tid = threadIdx.x;
+  if (!batch || B <= 0) {
+    const int nt = (N + T - 1) / T;
+    for (int t = tid; t <= nt && t <= max_tiles; t += blockDim.x) tile_ptr[t] = min(t * T, N);
+    if (tid == 0) *ntiles = min(nt, max_tiles);
+    return;
+  }
+  for (int g = tid; g <= B; g += blockDim.x) {
+    int lo = 0, hi = N;               // first node whose graph id >= g
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (batch[mid] < g) lo = mid + 1;
+      else hi = mid;
+    }
+    gptr[g] = lo;
+    sg[g] = lo;
+    sg[B + 1 + g] = rowptr[lo];
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  int nt = 0, cur = sg[0], cur_e = sg[B + 1];
+  tile_ptr[0] = cur;
+  auto close_at = [&](int node) {
+    if (node > tile_ptr[nt] && nt < max_tiles) tile_ptr[++nt] = node;
+  };
+  for (int g = 0; g < B; ++g) {
+    const int a0 = sg[g], a1 = sg[g + 1];
+    const int e0 = sg[B + 1 + g], e1 = sg[B + 1 + g + 1];
+    const int n = a1 - a0, m = e1 - e0;
+    if (n == 0) continue;
+    if (n > T || m > ecap) {            // does not fit a tile on its own: cut it (cross-tile neighbours -> global variant)
+      close_at(a0);
+      for (int x = a0; x < a1; x += T) close_at(min(x + T, a1));
+      cur = a1;
+      cur_e = e1;
+      continue;
+    }
+    if (a1 - cur > T || e1 - cur_e > ecap) {   // adding g would overflow the open tile: close it before g
+      close_at(a0);
+      cur = a0;
+      cur_e = e0;
+    }
+  }
+  close_at(sg[B]);
+  if (tile_ptr[nt] < N) close_at(N);           // nodes after the last graph boundary (defensive)
+  *ntiles = nt;
 }
 
 template <typename K>
@@ -610,46 +742,67 @@ int set_smem(K kernel, size_t bytes) {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-template <int LPR>
-int launch_fwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, cudaStream_t st) {
-  constexpr int H = 4 * LPR;
-  const TileGeom g = tile_geom(H, 0, N, E, B, 3);   // src, packed ids, logit staging
-  TileArgs a = a0;
+// grid + tile fields of a launch: with a tile list, persistent CTAs (as many as fit the SMs) draw tiles by ticket
+int plan_launch(TileArgs& a, const PertTiles* tl, const TileGeom& g, size_t bytes, long long N) {
   a.tile_nodes = g.T;
   a.edge_cap = g.ecap;
-  const int grid = pert_cdiv(N, g.T);
+  a.tile_ptr = nullptr;
+  a.ntiles = nullptr;
+  a.ticket = nullptr;
+  if (!tl) return pert_cdiv(N, g.T);
+  a.tile_ptr = tl->tile_ptr;
+  a.ntiles = tl->ntiles;
+  a.ticket = pert_ticket_slot();
+  if (!a.ticket) return -1;
+  const int per_sm = bytes + STATIC_SMEM + 1024 <= 233472 / 2 ? 2 : 1;
+  int grid = PERT_NUM_SMS * per_sm;
+  if (grid > tl->max_tiles) grid = tl->max_tiles;
+  return grid < 1 ? 1 : grid;
+}
+
+template <int LPR>
+int launch_fwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, const PertTiles* tl,
+               cudaStream_t st) {
+  constexpr int H = 4 * LPR;
+  const TileGeom g = tl ? TileGeom{tl->T, tl->ecap} : tile_geom(H, a0.n_rpc, N, E, B);
+  const size_t bytes = smem_bytes(g.T, H, 0, g.ecap, 3);   // src, packed ids, logit staging
+  TileArgs a = a0;
+  const int grid = plan_launch(a, tl, g, bytes, N);
+  if (grid < 0) return (int)cudaGetLastError();
   int rc;
   if (has_e) {
-    if ((rc = set_smem(k_tile_fwd<LPR, true>, g.bytes))) return rc;
-    k_tile_fwd<LPR, true><<<grid, TILE_THREADS, g.bytes, st>>>(a);
+    if ((rc = set_smem(k_tile_fwd<LPR, true>, bytes))) return rc;
+    k_tile_fwd<LPR, true><<<grid, TILE_THREADS, bytes, st>>>(a);
   } else {
-    if ((rc = set_smem(k_tile_fwd<LPR, false>, g.bytes))) return rc;
-    k_tile_fwd<LPR, false><<<grid, TILE_THREADS, g.bytes, st>>>(a);
+    if ((rc = set_smem(k_tile_fwd<LPR, false>, bytes))) return rc;
+    k_tile_fwd<LPR, false><<<grid, TILE_THREADS, bytes, st>>>(a);
   }
   return PERT_OK;
 }
 template <int LPR>
-int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, cudaStream_t st) {
+int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, const PertTiles* tl,
+               cudaStream_t st) {
   constexpr int H = 4 * LPR;
-  const TileGeom gd = tile_geom(H, 0, N, E, B, 4);                      // src, ids, alpha, dalpha staging
-  const TileGeom gs = tile_geom(H, has_e ? a0.n_rpc : 0, N, E, B, 4);   // dst, ids, alpha, ds
+  const TileGeom g = tl ? TileGeom{tl->T, tl->ecap} : tile_geom(H, a0.n_rpc, N, E, B);
+  const size_t bd = smem_bytes(g.T, H, 0, g.ecap, 4);                      // src, ids, alpha, dalpha staging
+  const size_t bs = smem_bytes(g.T, H, has_e ? a0.n_rpc : 0, g.ecap, 4);   // dst, ids, alpha, ds
   TileArgs ad = a0, as = a0;
-  ad.tile_nodes = gd.T; ad.edge_cap = gd.ecap;
-  as.tile_nodes = gs.T; as.edge_cap = gs.ecap;
+  const int gd = plan_launch(ad, tl, g, bd, N), gs = plan_launch(as, tl, g, bs, N);
+  if (gd < 0 || gs < 0) return (int)cudaGetLastError();
   int rc;
   // per-target rpc sums (see RPC_FAST) live in caller scratch; without it the general atomics path runs
   float* ws = (has_e && a0.n_rpc <= RPC_FAST && LPR >= RPC_FAST && TILE_THREADS % H == 0) ? a0.rpc_ws : nullptr;
   ad.rpc_ws = as.rpc_ws = ws;
   if (has_e) {
-    if ((rc = set_smem(k_tile_bwd_dst<LPR, true>, gd.bytes))) return rc;
-    if ((rc = set_smem(k_tile_bwd_src<LPR, true>, gs.bytes))) return rc;
-    k_tile_bwd_dst<LPR, true><<<pert_cdiv(N, gd.T), TILE_THREADS, gd.bytes, st>>>(ad);
-    k_tile_bwd_src<LPR, true><<<pert_cdiv(N, gs.T), TILE_THREADS, gs.bytes, st>>>(as);
+    if ((rc = set_smem(k_tile_bwd_dst<LPR, true>, bd))) return rc;
+    if ((rc = set_smem(k_tile_bwd_src<LPR, true>, bs))) return rc;
+    k_tile_bwd_dst<LPR, true><<<gd, TILE_THREADS, bd, st>>>(ad);
+    k_tile_bwd_src<LPR, true><<<gs, TILE_THREADS, bs, st>>>(as);
   } else {
-    if ((rc = set_smem(k_tile_bwd_dst<LPR, false>, gd.bytes))) return rc;
-    if ((rc = set_smem(k_tile_bwd_src<LPR, false>, gs.bytes))) return rc;
-    k_tile_bwd_dst<LPR, false><<<pert_cdiv(N, gd.T), TILE_THREADS, gd.bytes, st>>>(ad);
-    k_tile_bwd_src<LPR, false><<<pert_cdiv(N, gs.T), TILE_THREADS, gs.bytes, st>>>(as);
+    if ((rc = set_smem(k_tile_bwd_dst<LPR, false>, bd))) return rc;
+    if ((rc = set_smem(k_tile_bwd_src<LPR, false>, bs))) return rc;
+    k_tile_bwd_dst<LPR, false><<<gd, TILE_THREADS, bd, st>>>(ad);
+    k_tile_bwd_src<LPR, false><<<gs, TILE_THREADS, bs, st>>>(as);
   }
   return PERT_OK;
 }
@@ -661,7 +814,7 @@ int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool h
 int pert_tile_fwd(const float* q, const float* k, const float* v, const float* s, int ld, const int* rowptr,
                   const int* csr_src, const int* csr_if, const int* csr_rpc, const float* t_if, const float* t_rpc,
                   int n_rpc, float* out, int ld_out, float* alpha, long long N, long long E, long long B, int H,
-                  double* bn_acc, cudaStream_t st) {
+                  double* bn_acc, const PertTiles* tiles, cudaStream_t st) {
   if (ld != H || ld_out != H || (t_if && ((size_t)n_rpc * H * 4 > 16 * 1024 || n_rpc > 1023)))
     return PERT_ERR_UNSUPPORTED;
   TileArgs a{};
@@ -670,9 +823,9 @@ int pert_tile_fwd(const float* q, const float* k, const float* v, const float* s
   a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc; a.out = out; a.alpha = alpha; a.bn_acc = bn_acc;
   a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
   switch (H) {
-    case 32: return launch_fwd<8>(a, N, E, B, t_if != nullptr, st);
-    case 64: return launch_fwd<16>(a, N, E, B, t_if != nullptr, st);
-    case 128: return launch_fwd<32>(a, N, E, B, t_if != nullptr, st);
+    case 32: return launch_fwd<8>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 64: return launch_fwd<16>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 128: return launch_fwd<32>(a, N, E, B, t_if != nullptr, tiles, st);
     default: return PERT_ERR_UNSUPPORTED;
   }
 }
@@ -681,7 +834,7 @@ int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, con
                   const int* csr_src, const int* csr_if, const int* csr_rpc, const int* colptr, const int* csc_pos,
                   const int* csc_dst, const float* t_if, const float* t_rpc, const float* alpha, float* dq, float* dk,
                   float* dv, int ld_d, float* dsp, float* rpc_ws, float* dt_if, float* dt_rpc, int n_rpc, long long N,
-                  long long E, long long B, int H, cudaStream_t st) {
+                  long long E, long long B, int H, const PertTiles* tiles, cudaStream_t st) {
   if (ld != H || ld_g != H || ld_d != H || (t_if && ((size_t)n_rpc * H * 4 > 16 * 1024 || n_rpc > 1023)))
     return PERT_ERR_UNSUPPORTED;
   TileArgs a{};
@@ -693,9 +846,45 @@ int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, con
   a.dt_if = dt_if; a.dt_rpc = dt_rpc; a.rpc_ws = rpc_ws;
   a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
   switch (H) {
-    case 32: return launch_bwd<8>(a, N, E, B, t_if != nullptr, st);
-    case 64: return launch_bwd<16>(a, N, E, B, t_if != nullptr, st);
-    case 128: return launch_bwd<32>(a, N, E, B, t_if != nullptr, st);
+    case 32: return launch_bwd<8>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 64: return launch_bwd<16>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 128: return launch_bwd<32>(a, N, E, B, t_if != nullptr, tiles, st);
     default: return PERT_ERR_UNSUPPORTED;
   }
+}
+
+// Plans (host) and builds (device, stream-ordered) the graph-aligned tile list of a batch for row width H.
+// tiles_mem: int32 scratch of pert_tile_list_ints(N, B) (layout: ntiles | gptr [B+1] | tile_ptr [max_tiles+1]).
+long long pert_tile_list_ints(long long N, long long B) { return 1 + (B + 1) + (B + N / 32 + 8) + 1; }
+// fills `out` (geometry + pointers into tiles_mem) without launching anything: what backward uses after forward built it
+int pert_tile_list_view(long long N, long long E, long long B, int H, int n_rpc, int* tiles_mem, PertTiles* out) {
+  if (!tiles_mem || !out || N <= 0) return PERT_ERR_BADARG;
+  if (H != 32 && H != 64 && H != 128) return PERT_ERR_UNSUPPORTED;
+  const TileGeom g = tile_geom(H, n_rpc, N, E, B);
+  out->T = g.T;
+  out->ecap = g.ecap;
+  out->max_tiles = (int)(B + N / 32 + 8);
+  if ((long long)B + pert_cdiv(N, g.T) + 2 > out->max_tiles) return PERT_ERR_UNSUPPORTED;
+  if ((size_t)2 * (B + 1) * sizeof(int) > 200 * 1024) return PERT_ERR_UNSUPPORTED;   // builder's shared-memory copy
+  out->ntiles = tiles_mem;
+  out->tile_ptr = tiles_mem + 1 + (B + 1);
+  return PERT_OK;
+}
+int pert_tile_list_build(const int64_t* batch, long long N, long long E, long long B, const int* rowptr, int H,
+                         int n_rpc, int* tiles_mem, PertTiles* out, cudaStream_t st) {
+  if (!rowptr) return PERT_ERR_BADARG;
+  int rc = pert_tile_list_view(N, E, B, H, n_rpc, tiles_mem, out);
+  if (rc) return rc;
+  int* ntiles = tiles_mem;
+  int* gptr = tiles_mem + 1;
+  int* tile_ptr = gptr + (B + 1);
+  const size_t sm = batch && B > 0 ? (size_t)2 * (B + 1) * sizeof(int) : 0;
+  if (sm > 200 * 1024) return PERT_ERR_UNSUPPORTED;
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_build_tiles<<<1, 1024, sm, st>>>(batch, (int)N, (int)B, rowptr, out->T, out->ecap, gptr, tile_ptr, ntiles,
+                                     out->max_tiles);
+  return PERT_OK;
 }
