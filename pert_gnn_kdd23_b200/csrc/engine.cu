@@ -620,6 +620,9 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
     TRY(pert_embedding_fwd(params + d->off_cat[i], d->cat_rows[i], cat_X + i, d->n_cat, w.x[0], d->k0, N, H, i > 0,
                            status, s2));
   TRY(pert_copy_cols(x, d->F, w.x[0], d->k0, H, N, s2));
+  // graph boundaries of the batch for the tile list (needs only the batch vector): beside the prologue as well
+  const bool want_tiles = tiles_enabled() && E > 0 && N > 0;
+  if (want_tiles) TRY(pert_tile_list_bounds(batch, N, B, w.tiles, s2));
   if (forked) TRY(aux_join(ax, st));
   // 3. conv stack
   PertTiles tiles{};
@@ -634,8 +637,8 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
       cudaError_t we = cudaStreamWaitEvent(st, (cudaEvent_t)index_ready, 0);
       if (we != cudaSuccess) return (int)we;
     }
-    if (l == 0 && tiles_enabled() && E > 0) {   // graph-aligned tile list (whole graphs per tile), once per batch
-      int trc = pert_tile_list_build(batch, N, E, B, rowptr, H, d->n_rpc, w.tiles, &tiles, st);
+    if (l == 0 && want_tiles) {   // graph-aligned tile list (whole graphs per tile), once per batch
+      int trc = pert_tile_list_build(batch != nullptr && B > 0, N, E, B, rowptr, H, d->n_rpc, w.tiles, &tiles, st);
       have_tiles = trc == PERT_OK;
       if (!have_tiles && trc != PERT_ERR_UNSUPPORTED) return trc;
     }

@@ -20,7 +20,8 @@
 
 namespace {
 
-constexpr int TILE_THREADS = 512;
+// CTA size: 512 threads when two CTAs share an SM (tiles <= ~113 KB), 1024 when a tile needs the whole SM's shared memory
+// (the same 32 resident warps per SM either way; 64 registers per thread in both)
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -153,7 +154,7 @@ __device__ __forceinline__ bool next_tile(const TileArgs& a, bool first, int& n0
 // Lane groups of a warp walk their nodes' edges in lockstep (trip count = the largest degree in the warp): handing the
 // nodes out in DESCENDING DEGREE order puts equal degrees side by side (no idle lockstep iterations: E[max of 2 degrees]
 // is 3.8 against a mean of 3.0 at cfg2) and starts the long rows first.  Counting sort over degrees clamped to 32.
-template <int H>
+template <int H, int NT>
 __device__ __forceinline__ void stage_tiles(const Smem& S, const float* pa, const float* pb, const int* nodeptr,
                                             int n0, int nt, int tid) {
   __shared__ int s_hist[34];
@@ -164,9 +165,9 @@ __device__ __forceinline__ void stage_tiles(const Smem& S, const float* pa, cons
     bulk_g2s(S.tb, pb + (size_t)n0 * H, tile_bytes, S.bar);
   }
   if (tid < 34) s_hist[tid] = 0;
-  for (int x = tid; x <= nt; x += TILE_THREADS) S.ptr[x] = __ldg(nodeptr + n0 + x);
+  for (int x = tid; x <= nt; x += NT) S.ptr[x] = __ldg(nodeptr + n0 + x);
   __syncthreads();
-  for (int x = tid; x < nt; x += TILE_THREADS) atomicAdd(&s_hist[32 - min(S.ptr[x + 1] - S.ptr[x], 32)], 1);
+  for (int x = tid; x < nt; x += NT) atomicAdd(&s_hist[32 - min(S.ptr[x + 1] - S.ptr[x], 32)], 1);
   __syncthreads();
   if (tid == 0) {
     int run = 0;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void stage_tiles(const Smem& S, const float* pa, cons
     }
   }
   __syncthreads();
-  for (int x = tid; x < nt; x += TILE_THREADS)
+  for (int x = tid; x < nt; x += NT)
     S.ord[atomicAdd(&s_hist[32 - min(S.ptr[x + 1] - S.ptr[x], 32)], 1)] = (unsigned short)x;
   __syncthreads();
 }
@@ -233,11 +234,11 @@ __device__ __forceinline__ SAddr saddr_of(const Smem& S) {
 // contribute zeros), so shuffles use the full mask and no per-group branch divergence bookkeeping is generated.
 
 // ============================================================== forward
-template <int LPR, bool HAS_E>
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
+template <int LPR, bool HAS_E, int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) {
   constexpr int H = 4 * LPR;
   constexpr int GPW = 32 / LPR;
-  constexpr int GPC = TILE_THREADS / LPR;  // lane groups per CTA
+  constexpr int GPC = NT / LPR;  // lane groups per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Smem S = carve_smem(smem_raw, a.tile_nodes, H, 0, a.edge_cap);
   const SAddr sa = saddr_of(S);
@@ -251,11 +252,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
   uint32_t phase = 0;
   int n0, nt;
   for (bool first = true; next_tile(a, first, n0, nt); first = false, phase ^= 1) {
-    stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
+    stage_tiles<H, NT>(S, a.k, a.v, a.rowptr, n0, nt, tid);
     const int e_lo = S.ptr[0];
     const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
     int bad = 0;   // a staged neighbour outside this tile
-    for (int x = tid; x < ne_s; x += TILE_THREADS) {
+    for (int x = tid; x < ne_s; x += NT) {
       const int nb_id = __ldg(a.csr_src + e_lo + x);
       S.e0[x] = nb_id;
       bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
     // derives mean / rstd from (nodeops.cu).  Saves the separate statistics pass over `out`.
     __syncthreads();                                   // every warp is done with the staged tiles
     double* sc = reinterpret_cast<double*>(S.ta);
-    for (int x = tid; x < 2 * H; x += TILE_THREADS) sc[x] = 0.0;
+    for (int x = tid; x < 2 * H; x += NT) sc[x] = 0.0;
     __syncthreads();
     float vals[8] = {bsum.x, bsum.y, bsum.z, bsum.w, bsq.x, bsq.y, bsq.z, bsq.w};
 #pragma unroll
@@ -385,18 +386,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_fwd(TileArgs a) {
       if (grp == 0) atomicAdd(&sc[(kk < 4 ? 0 : H) + lig * 4 + (kk & 3)], (double)v);
     }
     __syncthreads();
-    for (int x = tid; x < 2 * H; x += TILE_THREADS)
+    for (int x = tid; x < 2 * H; x += NT)
       if (sc[x] != 0.0) atomicAdd(a.bn_acc + x, sc[x]);
   }
 }
 
 // ============================================================== backward, target pass (dq, ds)
-template <int LPR, bool HAS_E>
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
+template <int LPR, bool HAS_E, int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs a) {
   constexpr int H = 4 * LPR;
   constexpr int GPW = 32 / LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int GPC = TILE_THREADS / LPR;
+  constexpr int GPC = NT / LPR;
   const Smem S = carve_smem(smem_raw, a.tile_nodes, H, 0, a.edge_cap);
   const SAddr sa = saddr_of(S);
   const int tid = threadIdx.x;
@@ -407,11 +408,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
   uint32_t phase = 0;
   int n0, nt;
   for (bool first = true; next_tile(a, first, n0, nt); first = false, phase ^= 1) {
-    stage_tiles<H>(S, a.k, a.v, a.rowptr, n0, nt, tid);
+    stage_tiles<H, NT>(S, a.k, a.v, a.rowptr, n0, nt, tid);
     const int e_lo = S.ptr[0];
     const int ne_s = min(S.ptr[nt] - e_lo, a.edge_cap);
     int bad = 0;   // a staged neighbour outside this tile
-    for (int x = tid; x < ne_s; x += TILE_THREADS) {
+    for (int x = tid; x < ne_s; x += NT) {
       const int nb_id = __ldg(a.csr_src + e_lo + x);
       S.e0[x] = nb_id;
       bad |= (unsigned)(nb_id - n0) >= (unsigned)nt;
@@ -527,12 +528,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_dst(TileArgs a) {
 }
 
 // ============================================================== backward, source pass (dk, dv, table grads)
-template <int LPR, bool HAS_E>
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
+template <int LPR, bool HAS_E, int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_src(TileArgs a) {
   constexpr int H = 4 * LPR;
   constexpr int GPW = 32 / LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int GPC = TILE_THREADS / LPR;
+  constexpr int GPC = NT / LPR;
   const Smem S = carve_smem(smem_raw, a.tile_nodes, H, HAS_E ? a.n_rpc : 0, a.edge_cap);
   const SAddr sa = saddr_of(S);
   const int tid = threadIdx.x;
@@ -541,17 +542,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   const int g0 = (tid >> 5) * GPW;
   float* s_drpc = S.rpc;   // privatised gradient of the rpc-type table (few hot rows), flushed once per CTA
   if (HAS_E)
-    for (int x = tid; x < a.n_rpc * H; x += TILE_THREADS) s_drpc[x] = 0.f;
+    for (int x = tid; x < a.n_rpc * H; x += NT) s_drpc[x] = 0.f;
   tile_barrier_init(S, tid);
   uint32_t phase = 0;
   int n0, nt;
   for (bool first = true; next_tile(a, first, n0, nt); first = false, phase ^= 1) {
-  stage_tiles<H>(S, a.g, a.q, a.colptr, n0, nt, tid);   // targets of a node's out-edges live in the same graph
+  stage_tiles<H, NT>(S, a.g, a.q, a.colptr, n0, nt, tid);   // targets of a node's out-edges live in the same graph
   const int c_lo = S.ptr[0];
   const int ne_s = min(S.ptr[nt] - c_lo, a.edge_cap);
   // per out-edge (CSC order): target, and through the CSR slot its alpha, ds and attribute ids
   int bad = 0;   // a staged neighbour outside this tile
-  for (int x = tid; x < ne_s; x += TILE_THREADS) {
+  for (int x = tid; x < ne_s; x += NT) {
     const int p = __ldg(a.csc_pos + c_lo + x);
     const int nb_id = __ldg(a.csc_dst + c_lo + x);
     S.e0[x] = nb_id;
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   else run(std::false_type{});
   if (HAS_E && a.rpc_ws) {
     // dT_rpc tile contribution: thread = (column, node slice); the per-target scalars are warp-uniform loads
-    constexpr int NSL = TILE_THREADS / H;
+    constexpr int NSL = NT / H;
     const int col = tid % H, slc = tid / H;
     float acc[RPC_FAST];
 #pragma unroll
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_tile_bwd_src(TileArgs a) {
   }   // tile loop
   if (HAS_E) {
     __syncthreads();
-    for (int x = tid; x < a.n_rpc * H; x += TILE_THREADS) {
+    for (int x = tid; x < a.n_rpc * H; x += NT) {
       const float v = s_drpc[x];
       if (v != 0.f) atomicAdd(a.dt_rpc + x, v);
     }
@@ -670,7 +671,11 @@ TileGeom tile_geom(int H, int n_rpc, long long N, long long E, long long B) {
   auto fit = [&](double b) { return (long long)((b - fixed) / per_node); };
   long long T = fit(budget2);
   const double avg = B > 0 ? (double)N / (double)B : 0.0;
-  if ((avg > 0 && (double)T < avg) || T < 64) T = fit(budget1);   // wide rows / big graphs: one CTA per SM
+  const bool uniform = B > 0 && N % B == 0;                 // equally sized graphs (hint; the tile list does not rely on it)
+  // two CTAs per SM when the graphs fit such a tile (exactly, if they are uniform; comfortably -- average <= 60 % of the
+  // tile -- if their sizes vary: larger ones would be cut); else whole-SM tiles that pack one or two graphs
+  const bool two = T >= 64 && (avg == 0.0 || (uniform ? avg <= (double)T : avg <= 0.6 * (double)T));
+  if (!two) T = fit(budget1);
   if (T > N) T = N;
   if (T > 65535) T = 65535;
   if (T < 1) T = 1;
@@ -681,31 +686,37 @@ TileGeom tile_geom(int H, int n_rpc, long long N, long long E, long long B) {
 
 // ---- graph-aligned tile list: greedy packing of WHOLE graphs (never cut while a graph fits a tile) up to T nodes /
 // ecap edges; a graph that alone exceeds a tile is cut into T-node pieces (those tiles run the global-gather variant).
-// One CTA: graph boundaries by binary search in the sorted `batch` vector (gptr), then a serial packing pass over the
-// B graphs out of shared memory (B <= a few thousand; ~10 cycles per graph).  batch == nullptr: fixed T-node tiles.
-__global__ void __launch_bounds__(1024) k_build_tiles(const int64_t* __restrict__ batch, int N, int B,
-                                                      const int* __restrict__ rowptr, int T, int ecap,
-                                                      int* __restrict__ gptr, int* __restrict__ tile_ptr,
-                                                      int* __restrict__ ntiles, int max_tiles) {
-  extern __shared__ int sg[];   // gptr copy [B+1] | edge offset of every graph start [B+1]   (when it fits)
+// Two kernels: (1) graph boundaries from the sorted `batch` vector, fully parallel (a node that starts a graph writes
+// its index; depends only on the batch vector, so the engine issues it beside the input prologue); (2) one CTA: the
+// boundaries and the edge offsets of the graph starts go to shared memory in parallel, then a serial packing pass over
+// the B graphs (~10 cycles per graph).  batch == nullptr: fixed T-node tiles.
+__global__ void k_tile_bounds(const int64_t* __restrict__ batch, int N, int B, int* __restrict__ gptr) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n == 0) gptr[B] = N;
+  if (n >= N) return;
+  const int64_t g = batch[n];
+  if (g < 0 || g >= B) return;
+  if (n == 0 || batch[n - 1] != g) gptr[g] = n;     // gptr was filled with -1: graphs without nodes stay -1
+}
+__global__ void __launch_bounds__(1024) k_build_tiles(int has_batch, int N, int B, const int* __restrict__ rowptr, int T,
+                                                      int ecap, const int* __restrict__ gptr,
+                                                      int* __restrict__ tile_ptr, int* __restrict__ ntiles,
+                                                      int max_tiles) {
+  extern __shared__ int sg[];   // gptr copy [B+1] | edge offset of every graph start [B+1]
   const int tid = threadIdx.x;
-  if (!batch || B <= 0) {
+  if (!has_batch || B <= 0) {
     const int nt = (N + T - 1) / T;
     for (int t = tid; t <= nt && t <= max_tiles; t += blockDim.x) tile_ptr[t] = min(t * T, N);
     if (tid == 0) *ntiles = min(nt, max_tiles);
     return;
   }
-  for (int g = tid; g <= B; g += blockDim.x) {
-    int lo = 0, hi = N;               // first node whose graph id >= g
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (batch[mid] < g) lo = mid + 1;
-      else hi = mid;
-    }
-    gptr[g] = lo;
-    sg[g] = lo;
-    sg[B + 1 + g] = rowptr[lo];
-  }
+  for (int g = tid; g <= B; g += blockDim.x) sg[g] = gptr[g];
+  __syncthreads();
+  if (tid == 0)                                     // graphs without nodes start where the next graph starts
+    for (int g = B - 1; g >= 0; --g)
+      if (sg[g] < 0) sg[g] = sg[g + 1];
+  __syncthreads();
+  for (int g = tid; g <= B; g += blockDim.x) sg[B + 1 + g] = rowptr[sg[g]];
   __syncthreads();
   if (tid != 0) return;
   int nt = 0, cur = sg[0], cur_e = sg[B + 1];
@@ -717,7 +728,7 @@ __global__ void __launch_bounds__(1024) k_build_tiles(const int64_t* __restrict_
     const int a0 = sg[g], a1 = sg[g + 1];
     const int e0 = sg[B + 1 + g], e1 = sg[B + 1 + g + 1];
     const int n = a1 - a0, m = e1 - e0;
-    if (n == 0) continue;
+    if (n <= 0) continue;
     if (n > T || m > ecap) {            // does not fit a tile on its own: cut it (cross-tile neighbours -> global variant)
       close_at(a0);
       for (int x = a0; x < a1; x += T) close_at(min(x + T, a1));
@@ -742,22 +753,35 @@ int set_smem(K kernel, size_t bytes) {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-// grid + tile fields of a launch: with a tile list, persistent CTAs (as many as fit the SMs) draw tiles by ticket
-int plan_launch(TileArgs& a, const PertTiles* tl, const TileGeom& g, size_t bytes, long long N) {
+// grid + tile fields of a launch: with a tile list, persistent CTAs (as many as fit the SMs) draw tiles by ticket.
+// Returns the CTAs per SM the shared-memory footprint allows (2 -> 512-thread CTAs, 1 -> 1024-thread CTAs).
+int plan_launch(TileArgs& a, const PertTiles* tl, const TileGeom& g, size_t bytes, long long N, int& grid) {
   a.tile_nodes = g.T;
   a.edge_cap = g.ecap;
   a.tile_ptr = nullptr;
   a.ntiles = nullptr;
   a.ticket = nullptr;
-  if (!tl) return pert_cdiv(N, g.T);
+  const int per_sm = bytes + STATIC_SMEM + 1024 <= 233472 / 2 ? 2 : 1;
+  if (!tl) {
+    grid = pert_cdiv(N, g.T);
+    return per_sm;
+  }
   a.tile_ptr = tl->tile_ptr;
   a.ntiles = tl->ntiles;
   a.ticket = pert_ticket_slot();
   if (!a.ticket) return -1;
-  const int per_sm = bytes + STATIC_SMEM + 1024 <= 233472 / 2 ? 2 : 1;
-  int grid = PERT_NUM_SMS * per_sm;
+  grid = PERT_NUM_SMS * per_sm;
   if (grid > tl->max_tiles) grid = tl->max_tiles;
-  return grid < 1 ? 1 : grid;
+  if (grid < 1) grid = 1;
+  return per_sm;
+}
+
+template <typename K>
+int launch_k(K kernel, int grid, int threads, size_t bytes, const TileArgs& a, cudaStream_t st) {
+  int rc = set_smem(kernel, bytes);
+  if (rc) return rc;
+  kernel<<<grid, threads, bytes, st>>>(a);
+  return PERT_OK;
 }
 
 template <int LPR>
@@ -767,17 +791,14 @@ int launch_fwd(const TileArgs& a0, long long N, long long E, long long B, bool h
   const TileGeom g = tl ? TileGeom{tl->T, tl->ecap} : tile_geom(H, a0.n_rpc, N, E, B);
   const size_t bytes = smem_bytes(g.T, H, 0, g.ecap, 3);   // src, packed ids, logit staging
   TileArgs a = a0;
-  const int grid = plan_launch(a, tl, g, bytes, N);
-  if (grid < 0) return (int)cudaGetLastError();
-  int rc;
-  if (has_e) {
-    if ((rc = set_smem(k_tile_fwd<LPR, true>, bytes))) return rc;
-    k_tile_fwd<LPR, true><<<grid, TILE_THREADS, bytes, st>>>(a);
-  } else {
-    if ((rc = set_smem(k_tile_fwd<LPR, false>, bytes))) return rc;
-    k_tile_fwd<LPR, false><<<grid, TILE_THREADS, bytes, st>>>(a);
-  }
-  return PERT_OK;
+  int grid = 0;
+  const int per_sm = plan_launch(a, tl, g, bytes, N, grid);
+  if (per_sm < 0) return (int)cudaGetLastError();
+  if (per_sm == 2)
+    return has_e ? launch_k(k_tile_fwd<LPR, true, 512>, grid, 512, bytes, a, st)
+                 : launch_k(k_tile_fwd<LPR, false, 512>, grid, 512, bytes, a, st);
+  return has_e ? launch_k(k_tile_fwd<LPR, true, 1024>, grid, 1024, bytes, a, st)
+               : launch_k(k_tile_fwd<LPR, false, 1024>, grid, 1024, bytes, a, st);
 }
 template <int LPR>
 int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, const PertTiles* tl,
@@ -787,24 +808,25 @@ int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool h
   const size_t bd = smem_bytes(g.T, H, 0, g.ecap, 4);                      // src, ids, alpha, dalpha staging
   const size_t bs = smem_bytes(g.T, H, has_e ? a0.n_rpc : 0, g.ecap, 4);   // dst, ids, alpha, ds
   TileArgs ad = a0, as = a0;
-  const int gd = plan_launch(ad, tl, g, bd, N), gs = plan_launch(as, tl, g, bs, N);
-  if (gd < 0 || gs < 0) return (int)cudaGetLastError();
-  int rc;
+  int gd = 0, gs = 0;
+  const int pd = plan_launch(ad, tl, g, bd, N, gd), ps = plan_launch(as, tl, g, bs, N, gs);
+  if (pd < 0 || ps < 0) return (int)cudaGetLastError();
   // per-target rpc sums (see RPC_FAST) live in caller scratch; without it the general atomics path runs
-  float* ws = (has_e && a0.n_rpc <= RPC_FAST && LPR >= RPC_FAST && TILE_THREADS % H == 0) ? a0.rpc_ws : nullptr;
+  float* ws = (has_e && a0.n_rpc <= RPC_FAST && LPR >= RPC_FAST && 512 % H == 0) ? a0.rpc_ws : nullptr;
   ad.rpc_ws = as.rpc_ws = ws;
-  if (has_e) {
-    if ((rc = set_smem(k_tile_bwd_dst<LPR, true>, bd))) return rc;
-    if ((rc = set_smem(k_tile_bwd_src<LPR, true>, bs))) return rc;
-    k_tile_bwd_dst<LPR, true><<<gd, TILE_THREADS, bd, st>>>(ad);
-    k_tile_bwd_src<LPR, true><<<gs, TILE_THREADS, bs, st>>>(as);
-  } else {
-    if ((rc = set_smem(k_tile_bwd_dst<LPR, false>, bd))) return rc;
-    if ((rc = set_smem(k_tile_bwd_src<LPR, false>, bs))) return rc;
-    k_tile_bwd_dst<LPR, false><<<gd, TILE_THREADS, bd, st>>>(ad);
-    k_tile_bwd_src<LPR, false><<<gs, TILE_THREADS, bs, st>>>(as);
-  }
-  return PERT_OK;
+  int rc;
+  if (pd == 2)
+    rc = has_e ? launch_k(k_tile_bwd_dst<LPR, true, 512>, gd, 512, bd, ad, st)
+               : launch_k(k_tile_bwd_dst<LPR, false, 512>, gd, 512, bd, ad, st);
+  else
+    rc = has_e ? launch_k(k_tile_bwd_dst<LPR, true, 1024>, gd, 1024, bd, ad, st)
+               : launch_k(k_tile_bwd_dst<LPR, false, 1024>, gd, 1024, bd, ad, st);
+  if (rc) return rc;
+  if (ps == 2)
+    return has_e ? launch_k(k_tile_bwd_src<LPR, true, 512>, gs, 512, bs, as, st)
+                 : launch_k(k_tile_bwd_src<LPR, false, 512>, gs, 512, bs, as, st);
+  return has_e ? launch_k(k_tile_bwd_src<LPR, true, 1024>, gs, 1024, bs, as, st)
+               : launch_k(k_tile_bwd_src<LPR, false, 1024>, gs, 1024, bs, as, st);
 }
 
 }  // namespace
@@ -870,21 +892,31 @@ int pert_tile_list_view(long long N, long long E, long long B, int H, int n_rpc,
   out->tile_ptr = tiles_mem + 1 + (B + 1);
   return PERT_OK;
 }
-int pert_tile_list_build(const int64_t* batch, long long N, long long E, long long B, const int* rowptr, int H,
-                         int n_rpc, int* tiles_mem, PertTiles* out, cudaStream_t st) {
+// step 1 (depends on the batch vector only): graph boundaries into the scratch
+int pert_tile_list_bounds(const int64_t* batch, long long N, long long B, int* tiles_mem, cudaStream_t st) {
+  if (!tiles_mem || N <= 0) return PERT_ERR_BADARG;
+  if (!batch || B <= 0) return PERT_OK;
+  int* gptr = tiles_mem + 1;
+  cudaError_t e = cudaMemsetAsync(gptr, 0xff, (size_t)(B + 1) * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  k_tile_bounds<<<pert_cdiv(N, 256), 256, 0, st>>>(batch, (int)N, (int)B, gptr);
+  return PERT_OK;
+}
+// step 2 (needs rowptr): packing.  `has_batch` = step 1 ran for this batch.
+int pert_tile_list_build(int has_batch, long long N, long long E, long long B, const int* rowptr, int H, int n_rpc,
+                         int* tiles_mem, PertTiles* out, cudaStream_t st) {
   if (!rowptr) return PERT_ERR_BADARG;
   int rc = pert_tile_list_view(N, E, B, H, n_rpc, tiles_mem, out);
   if (rc) return rc;
   int* ntiles = tiles_mem;
   int* gptr = tiles_mem + 1;
   int* tile_ptr = gptr + (B + 1);
-  const size_t sm = batch && B > 0 ? (size_t)2 * (B + 1) * sizeof(int) : 0;
-  if (sm > 200 * 1024) return PERT_ERR_UNSUPPORTED;
+  const size_t sm = has_batch && B > 0 ? (size_t)2 * (B + 1) * sizeof(int) : 0;
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;
   }
-  k_build_tiles<<<1, 1024, sm, st>>>(batch, (int)N, (int)B, rowptr, out->T, out->ecap, gptr, tile_ptr, ntiles,
+  k_build_tiles<<<1, 1024, sm, st>>>(has_batch, (int)N, (int)B, rowptr, out->T, out->ecap, gptr, tile_ptr, ntiles,
                                      out->max_tiles);
   return PERT_OK;
 }

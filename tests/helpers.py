@@ -84,33 +84,94 @@ def is_structural_zero_grad(name, n_convs=None):
 
 
 def assert_grads_close(named_c, named_o, rtol, n_convs=None):
+    """Checks EVERY gradient (no early exit: the parity log and the failure message list all offenders)."""
     po = dict(named_o)
     scale = max(float(g.grad.abs().max()) for g in po.values() if g.grad is not None)
+    failures = []
     for n, p in named_c:
         ref = po[n].grad
         if ref is None:
             continue
         assert p.grad is not None, n
-        if is_structural_zero_grad(n, n_convs):
-            assert float(p.grad.abs().max()) <= 1e-5 * scale, f"grad {n} should be ~0"
-            assert float(ref.abs().max()) <= 1e-5 * scale
-        elif ".lin_key." in n or ".lin_query." in n or n.startswith(("lin_key.", "lin_query.")):
-            # Gradients of the ATTENTION-LOGIT path (lin_query / lin_key weights and the query bias).  ds_t = alpha_t (dalpha_t - sum alpha dalpha) cancels inside every
-            # target's neighbourhood (softmax shift invariance: sum_t ds_t = 0, hence sum_j dk_j = 0), and
-            # dW_{q,k} = sum_nodes d{q,k} x^T sums 10^4..10^5 such terms: at cfg3-5, conv 0, the result is as small as a
-            # few terms (conditioning kappa = sum|terms| / |result| ~ 10^2..10^4) and 500x below the step's largest
-            # gradient.  Every tcgen05 kind::tf32 accumulation truncates (round toward zero), which costs ~1e-5 of
-            # sum|terms| per GEMM (profiles/tn_accuracy_probe.py: 1e-5 vs 8e-7 for an fp32 FMA GEMM) in the weight
-            # gradient itself and ~1e-6 in the upstream data gradients that feed ds; kappa turns that into up to 1.5e-2
-            # OF THESE TWO TENSORS while it stays < 1e-5 of the step's gradient scale.
-            # Bar: the standard 1e-4 element-wise check (met at cfg1/cfg2 and for every layer >= 1); where kappa defeats
-            # it, the absolute error must stay below 1e-5 of the largest gradient of the step and 2e-2 of the tensor.
-            a, b = p.grad.detach().double().cpu(), ref.detach().double().cpu()
-            e, en = elem_err(a, b), rel_err(a, b)
-            _log(f"grad {n} (logit path)", a, b, e, en)
-            if e > rtol:
-                abs_err = float((a - b).abs().max())
+        try:
+            _check_one_grad(n, p.grad, ref, po, rtol, scale, n_convs)
+        except AssertionError as e:
+            failures.append(str(e))
+    assert not failures, "\n".join(failures)
+
+
+def _check_one_grad(n, grad, ref, po, rtol, scale, n_convs):
+    if is_structural_zero_grad(n, n_convs):
+        assert float(grad.abs().max()) <= 1e-5 * scale, f"grad {n} should be ~0"
+        assert float(ref.abs().max()) <= 1e-5 * scale
+    elif ".lin_key." in n or ".lin_query." in n or n.startswith(("lin_key.", "lin_query.")):
+        # Gradients of the ATTENTION-LOGIT path (lin_query / lin_key weights and the query bias).  ds_t
+        # = alpha_t (dalpha_t - sum alpha dalpha) cancels inside every target's neighbourhood (softmax shift invariance:
+        # sum_t ds_t = 0, hence sum_j dk_j = 0), and dW_{q,k} = sum_nodes d{q,k} x^T sums 10^4..10^5 such terms: at
+        # cfg3-5, conv 0, the result is as small as a few terms (conditioning kappa = sum|terms| / |result| ~ 10^2..10^4)
+        # and 500x below the step's largest gradient.  Every tcgen05 kind::tf32 accumulation truncates (round toward
+        # zero), which costs ~1e-5 of sum|terms| per GEMM (profiles/tn_accuracy_probe.py: 1e-5 vs 8e-7 for an fp32 FMA
+        # GEMM) in the weight gradient itself and ~1e-6 in the upstream data gradients that feed ds; kappa turns that
+        # into up to 1.5e-2 OF THESE TENSORS while it stays < 1e-5 of the step's gradient scale (DESIGN.md section 6).
+        # Bar: the standard 1e-4 element-wise check (met at cfg1/cfg2 and for every layer >= 1); where kappa defeats it,
+        # the absolute error must stay below 1e-5 of the largest gradient of the step and 2e-2 of the tensor.
+        a, b = grad.detach().double().cpu(), ref.detach().double().cpu()
+        e, en = elem_err(a, b), rel_err(a, b)
+        _log(f"grad {n} (logit path)", a, b, e, en)
+        if e > rtol:
+            abs_err = float((a - b).abs().max())
+            assert abs_err <= 1e-5 * scale and en <= 2e-2, \
+                f"grad {n}: elem {e:.3e} norm {en:.3e}, abs {abs_err:.3e} (step gradient scale {scale:.3e})"
+    else:
+        assert_close(grad, ref, rtol=rtol, what=f"grad {n}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full-size comparisons: at 10^5 nodes the fp32 CPU reference path is itself only reproducible up to its own rounding --
+# a ReLU of the global head or of a BatchNorm output whose argument is within 1e-7 of zero lands on the other side in
+# fp32 than in exact arithmetic, which moves whole gradient tensors by O(1/B) ~ 1e-3 (measured at the cfg4 shard: the fp32
+# oracle is 3.4e-3 away from the fp64 oracle on global_linear1.weight, and so is every fp32 implementation that takes the
+# other branch).  So the oracle is run in fp32 (the reference path) AND in fp64 (the exact value of the same function),
+# and a tensor passes when the CUDA result is within the bar of EITHER, or at least as close to the fp64 value as the fp32
+# reference path is (factor 2).
+def assert_close_ref(a, b32, b64, rtol=RTOL, what=""):
+    e64, e32 = elem_err(a, b64), elem_err(a, b32)
+    ref_noise = elem_err(b32, b64)
+    if _LOG:
+        with open(_LOG, "a") as f:
+            f.write(json.dumps({"what": what, "shape": list(b64.shape), "elem": min(e64, e32), "norm": rel_err(a, b64),
+                                "elem_vs_f64": e64, "elem_vs_f32": e32, "f32_oracle_vs_f64": ref_noise,
+                                "max_ref": float(b64.detach().abs().max()) if b64.numel() else 0.0}) + "\n")
+    ok = min(e64, e32) <= rtol or e64 <= 2.0 * ref_noise
+    assert ok, (f"{what}: element-wise rel err {e64:.3e} vs fp64 oracle, {e32:.3e} vs fp32 oracle "
+                f"(fp32 oracle itself is {ref_noise:.3e} from fp64) > {rtol:.1e}")
+    return ok
+
+
+def assert_grads_close_ref(named_c, named_o32, named_o64, rtol, n_convs=None):
+    """assert_grads_close against the fp32 reference path with the fp64 value as arbiter (see assert_close_ref)."""
+    p32, p64 = dict(named_o32), dict(named_o64)
+    scale = max(float(g.grad.abs().max()) for g in p64.values() if g.grad is not None)
+    failures = []
+    for n, p in named_c:
+        r32, r64 = p32[n].grad, p64[n].grad
+        if r64 is None:
+            continue
+        assert p.grad is not None, n
+        try:
+            if is_structural_zero_grad(n, n_convs):
+                assert float(p.grad.abs().max()) <= 1e-5 * scale, f"grad {n} should be ~0"
+                continue
+            try:
+                assert_close_ref(p.grad, r32, r64, rtol=rtol, what=f"grad {n}")
+            except AssertionError:
+                if not (".lin_key." in n or ".lin_query." in n):
+                    raise
+                # logit-path tensors, cancellation-limited under the truncating tensor-core accumulate (_check_one_grad)
+                a, b = p.grad.detach().double().cpu(), r64.detach().double().cpu()
+                abs_err, en = float((a - b).abs().max()), rel_err(a, b)
                 assert abs_err <= 1e-5 * scale and en <= 2e-2, \
-                    f"grad {n}: elem {e:.3e} norm {en:.3e}, abs {abs_err:.3e} (step gradient scale {scale:.3e})"
-        else:
-            assert_close(p.grad, ref, rtol=rtol, what=f"grad {n}")
+                    f"grad {n}: norm {en:.3e}, abs {abs_err:.3e} (step gradient scale {scale:.3e})"
+        except AssertionError as e:
+            failures.append(str(e))
+    assert not failures, "\n".join(failures)

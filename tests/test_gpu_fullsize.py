@@ -132,26 +132,38 @@ def test_gemm_tn_fused_colsum(H):
 
 # ------------------------------------------------------------------ whole model at the real batch sizes
 def _full_parity(cfg, ng, tag):
+    import copy
+
+    from tests.helpers import assert_close_ref, assert_grads_close_ref
+
     oracle, model = make_models(cfg)
+    oracle64 = copy.deepcopy(oracle).double()          # exact value of the same function: arbiter for fp32 noise
     b = make_batch(cfg, ng)
     oracle.train()
+    oracle64.train()
     model.train()
     go, lo = oracle(*forward_args(b))
+    a64 = [t.double() if t.is_floating_point() else t for t in forward_args(b)]
+    go64, lo64 = oracle64(*a64)
     bc = b.to("cuda")
     gc, lc = model(*forward_args(bc))
-    assert_close(gc, go, what=f"{tag} global_predict")
-    assert_close(lc, lo, what=f"{tag} local_predict")
+    assert_close_ref(gc, go, go64, what=f"{tag} global_predict")
+    assert_close_ref(lc, lo, lo64, what=f"{tag} local_predict")
     loss_o = model_oracle.torch_quantile_loss(b.y.float(), go.flatten(), 0.5) + 1e-3 * lo.square().mean()
+    loss_64 = model_oracle.torch_quantile_loss(b.y.double(), go64.flatten(), 0.5) + 1e-3 * lo64.square().mean()
     loss_c = model_oracle.torch_quantile_loss(bc.y.float(), gc.flatten(), 0.5) + 1e-3 * lc.square().mean()
     loss_o.backward()
+    loss_64.backward()
     loss_c.backward()
-    assert_close(loss_c, loss_o, what=f"{tag} loss")
-    assert_grads_close(model.named_parameters(), oracle.named_parameters(), RTOL, n_convs=len(model.convs))
+    assert_close_ref(loss_c, loss_o, loss_64, what=f"{tag} loss")
+    assert_grads_close_ref(model.named_parameters(), oracle.named_parameters(), oracle64.named_parameters(), RTOL,
+                           n_convs=len(model.convs))
+    b64 = dict(oracle64.named_buffers())
     for n, bbuf in model.named_buffers():
-        assert_close(bbuf.float(), dict(oracle.named_buffers())[n].float(), what=f"{tag} {n}")
-    # predicted-latency MAE / MAPE of the batch (BASELINE north_star: "MAE matching the reference within 1e-4")
-    mae_o = float((go.flatten() - b.y).abs().mean())
-    mae_c = float((gc.flatten() - bc.y).abs().mean())
+        assert_close_ref(bbuf.float(), dict(oracle.named_buffers())[n].float(), b64[n].double(), what=f"{tag} {n}")
+    # predicted-latency MAE of the batch (BASELINE north_star: "MAE matching the reference within 1e-4")
+    mae_o = float((go.detach().flatten() - b.y).abs().mean())
+    mae_c = float((gc.detach().flatten() - bc.y).abs().mean())
     assert abs(mae_c - mae_o) <= 1e-4 * abs(mae_o), (mae_c, mae_o)
 
 
