@@ -134,16 +134,33 @@ __device__ __forceinline__ bool next_tile(const TileArgs& a, bool first, int& n0
     nt = min(a.tile_nodes, a.N - n0);
     return nt > 0;
   }
-  __syncthreads();                       // every reader of the previous tile's shared memory (and of s_tile) is done
-  if (threadIdx.x == 0) {
-    const unsigned int total = (unsigned int)*a.ntiles;
-    const unsigned int c = atomicAdd(a.ticket, 1u);
-    if (c >= total && c == total + gridDim.x - 1) *a.ticket = 0;
-    s_tile = c < total ? (int)c : -1;
+  const int total = *a.ntiles;
+  int t;
+  if (first) {
+    t = blockIdx.x;                      // the first tile of a CTA needs no ticket: tickets hand out tiles >= gridDim.x
+  } else {
+    __syncthreads();                     // every reader of the previous tile's shared memory (and of s_tile) is done
+    if (threadIdx.x == 0) {
+      // draw c -> tile gridDim.x + c.  Every CTA ends with exactly one failing draw, so the launch makes
+      // max(0, total - gridDim.x) + gridDim.x draws; the last one resets the counter for the next launch.
+      const unsigned int c = atomicAdd(a.ticket, 1u);
+      const unsigned int extra = total > (int)gridDim.x ? (unsigned int)(total - (int)gridDim.x) : 0u;
+      if (c == extra + gridDim.x - 1) *a.ticket = 0;
+      s_tile = (int)gridDim.x + (int)c;
+    }
+    __syncthreads();
+    t = s_tile;
   }
-  __syncthreads();
-  const int t = s_tile;
-  if (t < 0) return false;
+  if (t >= total) {
+    if (first) {                         // no first tile: still owes its one failing draw
+      if (threadIdx.x == 0) {
+        const unsigned int c = atomicAdd(a.ticket, 1u);
+        const unsigned int extra = total > (int)gridDim.x ? (unsigned int)(total - (int)gridDim.x) : 0u;
+        if (c == extra + gridDim.x - 1) *a.ticket = 0;
+      }
+    }
+    return false;
+  }
   n0 = a.tile_ptr[t];
   nt = a.tile_ptr[t + 1] - n0;
   return true;
@@ -720,9 +737,13 @@ __global__ void __launch_bounds__(1024) k_build_tiles(int has_batch, int N, int 
   __syncthreads();
   if (tid != 0) return;
   int nt = 0, cur = sg[0], cur_e = sg[B + 1];
+  int last = cur;                       // last boundary written (kept in a register: tile_ptr is write-only here)
   tile_ptr[0] = cur;
   auto close_at = [&](int node) {
-    if (node > tile_ptr[nt] && nt < max_tiles) tile_ptr[++nt] = node;
+    if (node > last && nt < max_tiles) {
+      tile_ptr[++nt] = node;
+      last = node;
+    }
   };
   for (int g = 0; g < B; ++g) {
     const int a0 = sg[g], a1 = sg[g + 1];
@@ -743,7 +764,7 @@ __global__ void __launch_bounds__(1024) k_build_tiles(int has_batch, int N, int 
     }
   }
   close_at(sg[B]);
-  if (tile_ptr[nt] < N) close_at(N);           // nodes after the last graph boundary (defensive)
+  if (last < N) close_at(N);                   // nodes after the last graph boundary (defensive)
   *ntiles = nt;
 }
 

@@ -1,4 +1,5 @@
-"""Short driver for ncu captures: 3 train steps of the BASELINE cfg (default cfg2) through the public API."""
+"""A few eager train steps of the benchmark workload for ncu launch lists / --set full captures:
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python profiles/prof_step.py [cfg] [steps]"""
 import os
 import sys
 
@@ -8,16 +9,16 @@ import torch
 from pert_gnn_kdd23_b200.data import Batch
 from pert_gnn_kdd23_b200.model import SAGEDeterministic
 from pert_gnn_kdd23_b200.synthetic import make_data_list, model_args
-from pert_gnn_kdd23_b200.train import FlatParams, FusedAdam, fused_train_step as train_step
+from pert_gnn_kdd23_b200.train import FlatParams, FusedAdam, fused_train_step
 
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+ng = int(sys.argv[3]) if len(sys.argv) > 3 else None
 torch.manual_seed(0)
 model = SAGEDeterministic(*model_args(cfg)).cuda()
-fp = FlatParams(model)
-opt = FusedAdam(fp)
-b = Batch.from_data_list(make_data_list(cfg)).to("cuda")
+opt = FusedAdam(FlatParams(model), lr=3e-4)
+b = Batch.from_data_list(make_data_list(cfg, num_graphs=ng)).to("cuda")
 for _ in range(steps):
-    loss = train_step(model, opt, b)
+    fused_train_step(model, opt, b, 0.5)
 torch.cuda.synchronize()
-print("loss", float(loss))
+print("done")

@@ -136,15 +136,32 @@ def _full_parity(cfg, ng, tag):
 
     from tests.helpers import assert_close_ref, assert_grads_close_ref
 
-    oracle, model = make_models(cfg)
-    oracle64 = copy.deepcopy(oracle).double()          # exact value of the same function: arbiter for fp32 noise
     b = make_batch(cfg, ng)
-    oracle.train()
-    oracle64.train()
-    model.train()
-    go, lo = oracle(*forward_args(b))
     a64 = [t.double() if t.is_floating_point() else t for t in forward_args(b)]
-    go64, lo64 = oracle64(*a64)
+    # The comparison is made where the model is differentiable to fp32 resolution.  With 10^5 ReLU arguments in the global
+    # head (B x H), a draw of the weights regularly leaves one of them within 1e-7 of zero (seed 0 at the cfg4 shard:
+    # 9.0e-8); which side an fp32 implementation lands on then depends on its summation order, and the two legitimate
+    # outcomes differ by that graph's whole contribution -- O(1/B) ~ 3e-3 of global_linear1.weight and of everything
+    # upstream (measured: the fp32 oracle on two different hosts, and the CUDA path, split over the two branches).
+    # The weights are re-drawn (seed 0, 1, ...) until no head pre-activation is within 2e-6 of zero in fp64.
+    for seed in range(16):
+        oracle, model = make_models(cfg, seed=seed)
+        oracle64 = copy.deepcopy(oracle).double()      # exact value of the same function: arbiter for fp32 noise
+        oracle.train()
+        oracle64.train()
+        model.train()
+        seen = {}
+        hook = oracle64.global_linear1.register_forward_hook(lambda m, i, o: seen.__setitem__("a", o.detach()))
+        go64, lo64 = oracle64(*a64)
+        hook.remove()
+        margin = float(seen["a"].abs().min())
+        if margin >= 2e-6:
+            break
+        del model
+        torch.cuda.empty_cache()
+    else:
+        pytest.skip("no weight draw without a knife-edge ReLU in 16 tries")
+    go, lo = oracle(*forward_args(b))
     bc = b.to("cuda")
     gc, lc = model(*forward_args(bc))
     assert_close_ref(gc, go, go64, what=f"{tag} global_predict")
