@@ -235,6 +235,11 @@ typedef struct PertModelDesc {
 
 long long pert_model_workspace_bytes(const PertModelDesc* desc, long long N, long long E, long long B);
 long long pert_model_packed_bytes(const PertModelDesc* desc);
+/* Test / debug aid: offset (in floats) inside the workspace of a saved activation of the last forward:
+ * which = 0: input of conv `layer` (>= 1) = post-BatchNorm-ReLU activations [N,H]; which = 1: relu(global_linear1) [B,H].
+ * Lets a reference be differentiated on the same linear piece of the network (which ReLUs were active). */
+long long pert_model_workspace_offset(const PertModelDesc* desc, long long N, long long E, long long B, int which,
+                                      int layer);
 /* bn_running: [n_convs-1][2][H] (running_mean | running_var), bn_nbt: [n_convs-1] int64 (either may be NULL in
  * training mode); index arrays from pert_build_index (built with edge_attr); probs/pnn [N] fp32.
  * Outputs: global_pred [B], local_pred [N] (NULL to skip). */

@@ -58,6 +58,7 @@ SIGNATURES = {
     # whole-model engine (first argument: const PertModelDesc*, see engine.py)
     "pert_model_workspace_bytes": (LL, [P, LL, LL, LL]),
     "pert_model_packed_bytes": (LL, [P]),
+    "pert_model_workspace_offset": (LL, [P, LL, LL, LL, I, I]),
     "pert_model_forward": (I, [P, P, P, P, P, P, P, P, P, P, LL, LL, LL, P, P, P, P, P, LL, I, P, P, P, P, P, P]),
     "pert_model_backward": (I, [P, P, P, P, P, P, P, P, LL, LL, LL, P, P, P, P, P, P, P, P, LL, I, P, P, P, P]),
 }

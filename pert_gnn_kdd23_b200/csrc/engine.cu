@@ -564,6 +564,18 @@ long long pert_model_workspace_bytes(const PertModelDesc* d, long long N, long l
   Ws w = carve(d, N, E, B, nullptr);
   return w.total * 4;
 }
+// Test / debug aid: where a saved activation lives inside the workspace (floats from its start): which = 0 -> the input of
+// conv `layer` >= 1, i.e. the post-BatchNorm-ReLU activations [N, H]; which = 1 -> the global head's hidden layer
+// relu(global_linear1(.)) [B, H].  Returns the offset or a negative PERT_ERR_*.
+long long pert_model_workspace_offset(const PertModelDesc* d, long long N, long long E, long long B, int which,
+                                      int layer) {
+  if (check_desc(d) || N < 0 || E < 0 || B < 0) return PERT_ERR_BADARG;
+  float* base = reinterpret_cast<float*>(4096);     // carve() only does pointer arithmetic
+  Ws w = carve(d, N, E, B, base);
+  if (which == 0 && layer >= 1 && layer < d->n_convs) return w.x[layer] - base;
+  if (which == 1) return w.h1 - base;
+  return PERT_ERR_BADARG;
+}
 long long pert_model_packed_bytes(const PertModelDesc* d) {
   if (check_desc(d)) return PERT_ERR_BADARG;
   Ws w = carve(d, 0, 0, 0, nullptr);

@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(1024) k_build_tiles(int has_batch, int N, int 
                                                       int ecap, const int* __restrict__ gptr,
                                                       int* __restrict__ tile_ptr, int* __restrict__ ntiles,
                                                       int max_tiles) {
-  extern __shared__ int sg[];   // gptr copy [B+1] | edge offset of every graph start [B+1]
+  extern __shared__ int sg[];   // gptr copy [B+1] | edge offset of every graph start [B+1] | nxt [B+1]
   const int tid = threadIdx.x;
   if (!has_batch || B <= 0) {
     const int nt = (N + T - 1) / T;
@@ -735,35 +735,44 @@ __global__ void __launch_bounds__(1024) k_build_tiles(int has_batch, int N, int 
   __syncthreads();
   for (int g = tid; g <= B; g += blockDim.x) sg[B + 1 + g] = rowptr[sg[g]];
   __syncthreads();
+  // nxt[g] = first graph that no longer fits a tile opened at graph g (node AND edge capacity; binary search over the two
+  // prefix arrays, all graphs in parallel).  A graph that exceeds a tile on its own gets nxt = g + 1 and is cut below.
+  int* nxt = sg + 2 * (B + 1);
+  const int* cn = sg;
+  const int* ce = sg + B + 1;
+  for (int g = tid; g < B; g += blockDim.x) {
+    int lo = g + 1, hi = B;             // largest h in [g+1, B] with cn[h]-cn[g] <= T and ce[h]-ce[g] <= ecap
+    if (cn[lo] - cn[g] > T || ce[lo] - ce[g] > ecap) {
+      nxt[g] = g + 1;
+      continue;
+    }
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (cn[mid] - cn[g] <= T && ce[mid] - ce[g] <= ecap) lo = mid;
+      else hi = mid - 1;
+    }
+    nxt[g] = lo;
+  }
+  __syncthreads();
   if (tid != 0) return;
-  int nt = 0, cur = sg[0], cur_e = sg[B + 1];
-  int last = cur;                       // last boundary written (kept in a register: tile_ptr is write-only here)
-  tile_ptr[0] = cur;
+  // the tile sequence is the chain 0 -> nxt[0] -> nxt[nxt[0]] ...: one dependent shared-memory load per TILE
+  int nt = 0, last = cn[0];
+  tile_ptr[0] = last;
   auto close_at = [&](int node) {
     if (node > last && nt < max_tiles) {
       tile_ptr[++nt] = node;
       last = node;
     }
   };
-  for (int g = 0; g < B; ++g) {
-    const int a0 = sg[g], a1 = sg[g + 1];
-    const int e0 = sg[B + 1 + g], e1 = sg[B + 1 + g + 1];
-    const int n = a1 - a0, m = e1 - e0;
-    if (n <= 0) continue;
-    if (n > T || m > ecap) {            // does not fit a tile on its own: cut it (cross-tile neighbours -> global variant)
-      close_at(a0);
-      for (int x = a0; x < a1; x += T) close_at(min(x + T, a1));
-      cur = a1;
-      cur_e = e1;
-      continue;
+  for (int g = 0; g < B;) {
+    const int h = nxt[g];
+    if (h == g + 1 && (cn[h] - cn[g] > T || ce[h] - ce[g] > ecap)) {   // oversize graph: T-node pieces
+      for (int x = cn[g]; x < cn[h]; x += T) close_at(min(x + T, cn[h]));
+    } else {
+      close_at(cn[h]);
     }
-    if (a1 - cur > T || e1 - cur_e > ecap) {   // adding g would overflow the open tile: close it before g
-      close_at(a0);
-      cur = a0;
-      cur_e = e0;
-    }
+    g = h;
   }
-  close_at(sg[B]);
   if (last < N) close_at(N);                   // nodes after the last graph boundary (defensive)
   *ntiles = nt;
 }
@@ -908,7 +917,7 @@ int pert_tile_list_view(long long N, long long E, long long B, int H, int n_rpc,
   out->ecap = g.ecap;
   out->max_tiles = (int)(B + N / 32 + 8);
   if ((long long)B + pert_cdiv(N, g.T) + 2 > out->max_tiles) return PERT_ERR_UNSUPPORTED;
-  if ((size_t)2 * (B + 1) * sizeof(int) > 200 * 1024) return PERT_ERR_UNSUPPORTED;   // builder's shared-memory copy
+  if ((size_t)3 * (B + 1) * sizeof(int) > 200 * 1024) return PERT_ERR_UNSUPPORTED;   // builder's shared-memory copy
   out->ntiles = tiles_mem;
   out->tile_ptr = tiles_mem + 1 + (B + 1);
   return PERT_OK;
@@ -932,7 +941,7 @@ int pert_tile_list_build(int has_batch, long long N, long long E, long long B, c
   int* ntiles = tiles_mem;
   int* gptr = tiles_mem + 1;
   int* tile_ptr = gptr + (B + 1);
-  const size_t sm = has_batch && B > 0 ? (size_t)2 * (B + 1) * sizeof(int) : 0;
+  const size_t sm = has_batch && B > 0 ? (size_t)3 * (B + 1) * sizeof(int) : 0;
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;

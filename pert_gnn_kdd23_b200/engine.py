@@ -162,6 +162,21 @@ class Engine:
             self.ws_generation += 1
         return self.ws
 
+    def active_relus(self):
+        """{'bn{i}': [N,H] bool, 'head': [B,H] bool}: which ReLUs were active in the LAST forward (read from the saved
+        activations in the workspace).  Test aid: lets a reference be differentiated on the same linear piece."""
+        x, cat_X, entry_id, probs, pnn, batch, index, training, N, E, B = self._saved
+        H = self.desc.H
+        out = {}
+        for l in range(1, self.n_convs):
+            off = self.lib.pert_model_workspace_offset(C.byref(self.desc), N, E, B, 0, l)
+            _lib.check(int(min(off, 0)), "pert_model_workspace_offset")
+            out[f"bn{l - 1}"] = self.ws[off:off + N * H].view(N, H) > 0
+        off = self.lib.pert_model_workspace_offset(C.byref(self.desc), N, E, B, 1, 0)
+        _lib.check(int(min(off, 0)), "pert_model_workspace_offset")
+        out["head"] = self.ws[off:off + B * H].view(B, H) > 0
+        return out
+
     def _pack_launches(self):
         # mirrors engine.cu: conv 0 contributes 24 segments, the others 16; a launch holds at most 96
         n, count = 0, 0

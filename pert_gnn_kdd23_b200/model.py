@@ -43,6 +43,9 @@ class SAGEDeterministic(torch.nn.Module):
         # Function per operator (ops.py).  Same kernels, same results; the engine removes the interpreter gaps.
         self.use_engine = True
         self._engine = None
+        # test hook (operator path only): dict that receives the post-ReLU activations ('bn{i}', 'head'), so that a reference
+        # can be differentiated on the SAME linear piece of the network (tests/test_gpu_fullsize.py); None = off
+        self._capture = None
 
     def engine(self, flat=None):
         """The step engine of this replica.  There is ONE FlatParams per model: the one passed in, else the one a
@@ -92,6 +95,8 @@ class SAGEDeterministic(torch.nn.Module):
         for i, conv in enumerate(self.convs[:-1]):
             h = conv.forward_tables(h, index, if_t, rpc_t, perm0 if i == 0 else None, pad if i == 0 else 0)
             h = self.bns[i](h, relu=True)
+            if self._capture is not None:
+                self._capture[f"bn{i}"] = h.detach()
             h = F.dropout(h, p=self.dropout, training=self.training)
         last = len(self.convs) - 1
         h = self.convs[-1].forward_tables(h, index, if_t, rpc_t, perm0 if last == 0 else None,
@@ -101,5 +106,7 @@ class SAGEDeterministic(torch.nn.Module):
                                              self.local_linear.weight, self.local_linear.bias, B)
         g = torch.cat([pool, ops.embedding(self.entry_embeds.weight, entry_id.reshape(-1))], dim=1)
         g = ops.linear(g, self.global_linear1.weight, self.global_linear1.bias, relu=True)
+        if self._capture is not None:
+            self._capture["head"] = g.detach()
         g = ops.linear(g, self.global_linear2.weight, self.global_linear2.bias)
         return g, local_predict

@@ -132,54 +132,61 @@ def test_gemm_tn_fused_colsum(H):
 
 # ------------------------------------------------------------------ whole model at the real batch sizes
 def _full_parity(cfg, ng, tag):
+    """Outputs, loss, every gradient and the BatchNorm statistics of the FULL batch against the oracle.
+
+    Derivatives are compared ON THE SAME LINEAR PIECE of the network.  A batch of 10^5 nodes puts ~10^7 arguments through
+    the BatchNorm ReLUs; a few dozen of them lie within the 1e-6 by which two fp32 implementations of the conv stack differ,
+    and each such unit that lands on the other side of zero adds or removes one node's term from weight-gradient sums whose
+    result is ~sqrt(N) terms large -- 1e-3 of conv 0/1 gradients at cfg3-5 (measured: identical for the tcgen05, the exact
+    fp32 SIMT GEMMs and both families of conv kernels, while BatchNorm itself agrees with torch to 1e-7:
+    profiles/bn_probe.py), although every forward value agrees to 1e-6.  That is a property of fp32 evaluation of a
+    piecewise-linear network, not of a kernel.  So the step ENGINE (what bench.py times) runs forward, the set of active ReLUs
+    is read back from its saved activations (Engine.active_relus), and the oracle (fp32 = the reference path, fp64 =
+    arbiter) is evaluated and differentiated with exactly those ReLUs active.  The free-running oracle (its own ReLUs) is
+    checked on the forward values as well."""
     import copy
 
     from tests.helpers import assert_close_ref, assert_grads_close_ref
 
     b = make_batch(cfg, ng)
-    a64 = [t.double() if t.is_floating_point() else t for t in forward_args(b)]
-    # The comparison is made where the model is differentiable to fp32 resolution.  With 10^5 ReLU arguments in the global
-    # head (B x H), a draw of the weights regularly leaves one of them within 1e-7 of zero (seed 0 at the cfg4 shard:
-    # 9.0e-8); which side an fp32 implementation lands on then depends on its summation order, and the two legitimate
-    # outcomes differ by that graph's whole contribution -- O(1/B) ~ 3e-3 of global_linear1.weight and of everything
-    # upstream (measured: the fp32 oracle on two different hosts, and the CUDA path, split over the two branches).
-    # The weights are re-drawn (seed 0, 1, ...) until no head pre-activation is within 2e-6 of zero in fp64.
-    for seed in range(16):
-        oracle, model = make_models(cfg, seed=seed)
-        oracle64 = copy.deepcopy(oracle).double()      # exact value of the same function: arbiter for fp32 noise
-        oracle.train()
-        oracle64.train()
-        model.train()
-        seen = {}
-        hook = oracle64.global_linear1.register_forward_hook(lambda m, i, o: seen.__setitem__("a", o.detach()))
-        go64, lo64 = oracle64(*a64)
-        hook.remove()
-        margin = float(seen["a"].abs().min())
-        if margin >= 2e-6:
-            break
-        del model
-        torch.cuda.empty_cache()
-    else:
-        pytest.skip("no weight draw without a knife-edge ReLU in 16 tries")
-    go, lo = oracle(*forward_args(b))
+    a32 = forward_args(b)
+    a64 = [t.double() if t.is_floating_point() else t for t in a32]
+    oracle, model = make_models(cfg)
+    oracle64 = copy.deepcopy(oracle).double()
+    oracle_free = copy.deepcopy(oracle)
+    oracle.train()
+    oracle64.train()
+    oracle_free.train()
+    model.train()
     bc = b.to("cuda")
-    gc, lc = model(*forward_args(bc))
-    assert_close_ref(gc, go, go64, what=f"{tag} global_predict")
-    assert_close_ref(lc, lo, lo64, what=f"{tag} local_predict")
-    loss_o = model_oracle.torch_quantile_loss(b.y.float(), go.flatten(), 0.5) + 1e-3 * lo.square().mean()
-    loss_64 = model_oracle.torch_quantile_loss(b.y.double(), go64.flatten(), 0.5) + 1e-3 * lo64.square().mean()
-    loss_c = model_oracle.torch_quantile_loss(bc.y.float(), gc.flatten(), 0.5) + 1e-3 * lc.square().mean()
+
+    def loss_of(g, l, y):
+        return model_oracle.torch_quantile_loss(y, g.flatten(), 0.5) + 1e-3 * l.square().mean()
+
+    gc, lc = model(*forward_args(bc))                      # engine path (model.use_engine is True)
+    masks = {k: v.cpu() for k, v in model._engine.active_relus().items()}
+    loss_c = loss_of(gc, lc, bc.y.float())
+    loss_c.backward()
+    go, lo = oracle(*a32, relu_masks=masks)
+    go64, lo64 = oracle64(*a64, relu_masks=masks)
+    loss_o, loss_64 = loss_of(go, lo, b.y.float()), loss_of(go64, lo64, b.y.double())
     loss_o.backward()
     loss_64.backward()
-    loss_c.backward()
+    assert_close_ref(gc, go, go64, what=f"{tag} global_predict")
+    assert_close_ref(lc, lo, lo64, what=f"{tag} local_predict")
     assert_close_ref(loss_c, loss_o, loss_64, what=f"{tag} loss")
     assert_grads_close_ref(model.named_parameters(), oracle.named_parameters(), oracle64.named_parameters(), RTOL,
                            n_convs=len(model.convs))
     b64 = dict(oracle64.named_buffers())
     for n, bbuf in model.named_buffers():
         assert_close_ref(bbuf.float(), dict(oracle.named_buffers())[n].float(), b64[n].double(), what=f"{tag} {n}")
+    # the free-running reference (its own ReLUs) gives the same forward values, and (almost) the same set of active ReLUs
+    with torch.no_grad():
+        gfree, lfree = oracle_free(*a32)
+    assert_close(gc, gfree, what=f"{tag} global_predict (reference with its own ReLUs)")
+    assert_close(lc, lfree, what=f"{tag} local_predict (reference with its own ReLUs)")
     # predicted-latency MAE of the batch (BASELINE north_star: "MAE matching the reference within 1e-4")
-    mae_o = float((go.detach().flatten() - b.y).abs().mean())
+    mae_o = float((gfree.flatten() - b.y).abs().mean())
     mae_c = float((gc.detach().flatten() - bc.y).abs().mean())
     assert abs(mae_c - mae_o) <= 1e-4 * abs(mae_o), (mae_c, mae_o)
 
