@@ -60,6 +60,7 @@ struct PertTiles {            // graph-aligned tile list of one batch for one ro
 };
 unsigned int* pert_ticket_slot();   // next slot of the self-resetting ticket ring (csrc/gemm_tc.cu)
 long long pert_tile_list_ints(long long N, long long B);
+bool pert_tile_fixed_ok(long long N, long long E, long long B, int H, int n_rpc);
 int pert_tile_list_view(long long N, long long E, long long B, int H, int n_rpc, int* tiles_mem, PertTiles* out);
 int pert_tile_list_bounds(const int64_t* batch, long long N, long long B, int* tiles_mem, cudaStream_t st);
 int pert_tile_list_build(int has_batch, long long N, long long E, long long B, const int* rowptr, int H, int n_rpc,

@@ -633,7 +633,7 @@ int pert_model_forward(const PertModelDesc* d, const float* params, float* bn_ru
                            status, s2));
   TRY(pert_copy_cols(x, d->F, w.x[0], d->k0, H, N, s2));
   // graph boundaries of the batch for the tile list (needs only the batch vector): beside the prologue as well
-  const bool want_tiles = tiles_enabled() && E > 0 && N > 0;
+  const bool want_tiles = tiles_enabled() && E > 0 && N > 0 && !pert_tile_fixed_ok(N, E, B, H, d->n_rpc);
   if (want_tiles) TRY(pert_tile_list_bounds(batch, N, B, w.tiles, s2));
   if (forked) TRY(aux_join(ax, st));
   // 3. conv stack
@@ -755,7 +755,7 @@ int pert_model_backward(const PertModelDesc* d, const float* params, float* grad
   AuxStream* ax = aux_stream();
   bool forked = false;
   PertTiles tiles{};            // the list forward built for this batch (same geometry: a pure function of the sizes)
-  const bool have_tiles = tiles_enabled() && E > 0 &&
+  const bool have_tiles = tiles_enabled() && E > 0 && !pert_tile_fixed_ok(N, E, B, H, d->n_rpc) &&
                           pert_tile_list_view(N, E, B, H, d->n_rpc, w.tiles, &tiles) == PERT_OK;
   for (int l = L - 1; l >= 0; --l) {
     const int K = k_of(d, l);
