@@ -284,27 +284,25 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) 
     const bool all_in = (__syncthreads_or(bad) == 0) && (S.ptr[nt] - e_lo <= a.edge_cap);
     mbar_wait(S.bar, phase);
 
-    // node slots are handed out in descending-degree order (S.ord); q / skip rows are requested one node ahead
+    // node slots are handed out in descending-degree order (S.ord); the q row is requested one node ahead, the skip row
+    // at the start of its own node (it is consumed after the edge loop, which hides its latency: 4 registers fewer
+    // than prefetching it a node ahead as well)
     int slot = g0 + grp;
     int loc = slot < nt ? ldsu16(sa.ord + slot * 2) : 0;
-    float4 q_n = f4zero(), s_n = f4zero();
-    if (slot < nt) {
-      q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
-      if (a.s) s_n = ldg4(a.s + (size_t)(n0 + loc) * H + lig * 4);
-    }
+    float4 q_n = f4zero();
+    if (slot < nt) q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
     auto run = [&](auto fast_c) {
       constexpr bool FAST = decltype(fast_c)::value;
       for (; slot - grp < nt; slot += GPC) {   // warp-uniform: the warp's first group still has a node
         const bool valid = slot < nt;
         const int i = n0 + loc;
         const float4 q = f4scale(qscale, q_n);
-        const float4 skip = s_n;
+        const float4 skip = (valid && a.s) ? ldg4(a.s + (size_t)i * H + lig * 4) : f4zero();
         const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
         const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
         if (slot + GPC < nt) {
           loc = ldsu16(sa.ord + (slot + GPC) * 2);
           q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
-          if (a.s) s_n = ldg4(a.s + (size_t)(n0 + loc) * H + lig * 4);
         }
         const int deg = p1 - p0;
         const int degmax = __reduce_max_sync(0xffffffffu, deg);
