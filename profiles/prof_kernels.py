@@ -24,6 +24,7 @@ alpha, dsp = torch.empty(E, device="cuda"), torch.empty(E, device="cuda")
 out, g = torch.empty(N, H, device="cuda"), torch.randn(N, H, device="cuda")
 dpl = torch.empty(4, N, H, device="cuda")
 dt_if, dt_rpc = torch.zeros_like(t_if), torch.zeros_like(t_rpc)
+rpc_ws = torch.empty(16 * N, device="cuda")
 msg = torch.randn(E, H, device="cuda")
 for _ in range(reps):
     _lib.call("pert_segment_reduce_fwd", p(msg), p(gi.rowptr), None, p(out), N, H, 1, st)
@@ -31,6 +32,6 @@ for _ in range(reps):
               p(gi.csr_if), p(gi.csr_rpc), p(t_if), p(t_rpc), p(out), H, p(alpha), 8, N, E, b.num_graphs, H, st)
     _lib.call("pert_tconv_bwd", p(g), H, p(planes[0]), p(planes[1]), p(planes[2]), H, p(gi.rowptr), p(gi.csr_src),
               p(gi.csr_if), p(gi.csr_rpc), p(gi.colptr), p(gi.csc_pos), p(gi.csc_dst), p(t_if), p(t_rpc), p(alpha),
-              p(dpl[0]), p(dpl[1]), p(dpl[2]), H, p(dsp), p(dt_if), p(dt_rpc), 8, N, E, b.num_graphs, H, st)
+              p(dpl[0]), p(dpl[1]), p(dpl[2]), H, p(dsp), p(rpc_ws), p(dt_if), p(dt_rpc), 8, N, E, b.num_graphs, H, st)
 torch.cuda.synchronize()
 print("ok")
