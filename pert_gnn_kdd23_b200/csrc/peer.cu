@@ -94,9 +94,17 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(PeerArgs a) {
   // ---- 3. reduce in rank order + Adam
   const long long off = (a.step & 1ull) * a.n_al;
   for (long long i = t0; i < n4; i += stride) {
-    float4 s = f4zero();
-    for (int r = 0; r < a.world; ++r) s = f4add(s, __ldcv(reinterpret_cast<const float4*>(a.xbuf[r] + off) + i));
+    // all peers' loads are issued before the first add (one NVLink round trip per element instead of `world`; r2 at 8
+    // GPUs: this phase took 22 us with the loads chained through the running sum); the sum keeps the rank order
+    float4 pv_r[PEER_MAX];
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; ++r)
+      pv_r[r] = r < a.world ? __ldcv(reinterpret_cast<const float4*>(a.xbuf[r] + off) + i) : f4zero();
     const float4 pv = ld4(a.p + i * 4), mv = ld4(a.m + i * 4), vv = ld4(a.v + i * 4);
+    float4 s = f4zero();
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; ++r)
+      if (r < a.world) s = f4add(s, pv_r[r]);
     float gs[4] = {s.x, s.y, s.z, s.w}, pp[4] = {pv.x, pv.y, pv.z, pv.w}, mm[4] = {mv.x, mv.y, mv.z, mv.w},
           vs[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
