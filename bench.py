@@ -466,10 +466,6 @@ def run_b200(args, rank, world, local_rank):
     assert torch.cuda.is_available(), "bench.py (CUDA arm) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if os.environ.get("PERT_CACHE_CONFIG"):          # experiment: device-wide shared-memory / L1 preference (A/B only)
-        rt = PertProbe._cudart()
-        rt.cudaDeviceSetCacheConfig.argtypes = [__import__("ctypes").c_int]
-        print("cudaDeviceSetCacheConfig ->", rt.cudaDeviceSetCacheConfig(int(os.environ["PERT_CACHE_CONFIG"])), file=sys.stderr)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = args.cfg

@@ -16,6 +16,7 @@
 // Tile size (nodes) is chosen by the host so that two CTAs of 512 threads fit one SM; when the batch holds equally
 // sized graphs the tile is a whole number of graphs (no cut edges).
 #include "common.cuh"
+#include <stdlib.h>
 #include <type_traits>
 
 namespace {
@@ -251,9 +252,14 @@ __device__ __forceinline__ SAddr saddr_of(const Smem& S) {
 // contribute zeros), so shuffles use the full mask and no per-group branch divergence bookkeeping is generated.
 
 // ============================================================== forward
-template <int LPR, bool HAS_E, int NT>
-__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) {
-  constexpr int H = 4 * LPR;
+// VPL = float4 vectors per lane: a node row of H = 4 * LPR * VPL floats is owned by LPR lanes, lane `lig` holding the
+// float4 pieces lig, lig + LPR, ... (each piece index is contiguous across the group's lanes: conflict-free shared-memory
+// rows, coalesced global rows).  VPL = 1: one warp walks 32 / LPR nodes; VPL = 2 halves the lanes per node, so a warp
+// walks twice as many nodes per instruction stream (fewer instructions per edge: the per-edge bookkeeping, the shuffle
+// tree and the per-node prologue / epilogue are shared by twice the data) at twice the registers per thread.
+template <int LPR, int VPL, bool HAS_E, int NT>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) k_tile_fwd(TileArgs a) {
+  constexpr int H = 4 * LPR * VPL;
   constexpr int GPW = 32 / LPR;
   constexpr int GPC = NT / LPR;  // lane groups per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -262,9 +268,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) 
   const int tid = threadIdx.x;
   const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
   const float qscale = a.inv_sqrt_c * 1.4426950408889634f;   // logits kept in log2 units: exp(x) = 2^(x*log2 e)
-  const uint32_t lane4 = lig * 16;
   const int g0 = (tid >> 5) * GPW;          // first group slot of this warp
-  float4 bsum = f4zero(), bsq = f4zero();   // this lane's 4 columns over its nodes (fused BatchNorm statistics)
+  float4 bsum[VPL], bsq[VPL];               // this lane's columns over its nodes (fused BatchNorm statistics)
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) bsum[u] = bsq[u] = f4zero();
+  auto ldrow = [&](const float* base, size_t row, float4 (&v)[VPL]) {
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) v[u] = ldg4(base + row * H + (lig + u * LPR) * 4);
+  };
   tile_barrier_init(S, tid);
   uint32_t phase = 0;
   int n0, nt;
@@ -285,32 +296,42 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) 
     mbar_wait(S.bar, phase);
 
     // node slots are handed out in descending-degree order (S.ord); the q row is requested one node ahead, the skip row
-    // at the start of its own node (it is consumed after the edge loop, which hides its latency: 4 registers fewer
-    // than prefetching it a node ahead as well)
+    // at the start of its own node (it is consumed after the edge loop, which hides its latency)
     int slot = g0 + grp;
     int loc = slot < nt ? ldsu16(sa.ord + slot * 2) : 0;
-    float4 q_n = f4zero();
-    if (slot < nt) q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
+    float4 q_n[VPL];
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) q_n[u] = f4zero();
+    if (slot < nt) ldrow(a.q, (size_t)(n0 + loc), q_n);
     auto run = [&](auto fast_c) {
       constexpr bool FAST = decltype(fast_c)::value;
       for (; slot - grp < nt; slot += GPC) {   // warp-uniform: the warp's first group still has a node
         const bool valid = slot < nt;
         const int i = n0 + loc;
-        const float4 q = f4scale(qscale, q_n);
-        const float4 skip = (valid && a.s) ? ldg4(a.s + (size_t)i * H + lig * 4) : f4zero();
+        float4 q[VPL], skip[VPL];
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          q[u] = f4scale(qscale, q_n[u]);
+          skip[u] = f4zero();
+        }
+        if (valid && a.s) ldrow(a.s, (size_t)i, skip);
         const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
         const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
         if (slot + GPC < nt) {
           loc = ldsu16(sa.ord + (slot + GPC) * 2);
-          q_n = ldg4(a.q + (size_t)(n0 + loc) * H + lig * 4);
+          ldrow(a.q, (size_t)(n0 + loc), q_n);
         }
         const int deg = p1 - p0;
         const int degmax = __reduce_max_sync(0xffffffffu, deg);
-        float4 acc = f4zero();
+        float4 acc[VPL];
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) acc[u] = f4zero();
         float m = -INFINITY, Z = 0.f;
         // software pipeline over edges: ids + table rows of edge t+1 are requested before edge t is consumed
         int j = n0, id = 0;
-        float4 eif = f4zero(), erp = f4zero();
+        float4 eif[VPL], erp[VPL];
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) eif[u] = erp[u] = f4zero();
         auto fetch = [&](int p, bool on) {
           j = n0;
           id = 0;
@@ -325,8 +346,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) 
             }
           }
           if (HAS_E) {
-            eif = ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4);
-            erp = ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4);
+            ldrow(a.t_if, (size_t)ID_IF(id), eif);
+            ldrow(a.t_rpc, (size_t)ID_RPC(id), erp);
           }
         };
         fetch(p0, 0 < deg);
@@ -334,22 +355,32 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) 
           const bool on = t < deg;
           const int p = p0 + t;
           const int cj = j;
-          const float4 e = f4add(eif, erp);
+          float4 e[VPL];
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) e[u] = f4add(eif[u], erp[u]);
           fetch(p + 1, t + 1 < deg);
-          float4 kk, vv;
+          float4 kk[VPL], vv[VPL];
           const unsigned sl = (unsigned)(cj - n0);
           if (FAST || sl < (unsigned)nt) {
-            kk = lds4s(sa.ta + sl * (H * 4) + lane4);
-            vv = lds4s(sa.tb + sl * (H * 4) + lane4);
+#pragma unroll
+            for (int u = 0; u < VPL; ++u) {
+              kk[u] = lds4s(sa.ta + sl * (H * 4) + (lig + u * LPR) * 16);
+              vv[u] = lds4s(sa.tb + sl * (H * 4) + (lig + u * LPR) * 16);
+            }
           } else {
-            kk = ldg4(a.k + (size_t)cj * H + lig * 4);
-            vv = ldg4(a.v + (size_t)cj * H + lig * 4);
+            ldrow(a.k, (size_t)cj, kk);
+            ldrow(a.v, (size_t)cj, vv);
           }
-          if (HAS_E) {
-            kk = f4add(kk, e);
-            vv = f4add(vv, e);
+          float part = 0.f;
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) {
+            if (HAS_E) {
+              kk[u] = f4add(kk[u], e[u]);
+              vv[u] = f4add(vv[u], e[u]);
+            }
+            part += f4dot(q[u], kk[u]);
           }
-          const float s = gsum_full<LPR>(f4dot(q, kk));
+          const float s = gsum_full<LPR>(part);
           if (on && lig == 0) {
             const int le = p - e_lo;
             if (FAST || le < ne_s) stsf(sa.f0 + le * 4, s);
@@ -359,19 +390,25 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) 
           const float sc = on ? ex2(m - mn) : 1.f;
           const float pz = on ? ex2(s - mn) : 0.f;
           Z = fmaf(Z, sc, pz);
-          acc.x = fmaf(pz, vv.x, acc.x * sc);
-          acc.y = fmaf(pz, vv.y, acc.y * sc);
-          acc.z = fmaf(pz, vv.z, acc.z * sc);
-          acc.w = fmaf(pz, vv.w, acc.w * sc);
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) {
+            acc[u].x = fmaf(pz, vv[u].x, acc[u].x * sc);
+            acc[u].y = fmaf(pz, vv[u].y, acc[u].y * sc);
+            acc[u].z = fmaf(pz, vv[u].z, acc[u].z * sc);
+            acc[u].w = fmaf(pz, vv[u].w, acc[u].w * sc);
+          }
           m = mn;
         }
         const float invZ = 1.0f / (Z + 1e-16f);
         if (valid) {
-          const float4 o = f4add(f4scale(invZ, acc), skip);
-          st4(a.out + (size_t)i * H + lig * 4, o);
-          bsum = f4add(bsum, o);
-          bsq.x = fmaf(o.x, o.x, bsq.x); bsq.y = fmaf(o.y, o.y, bsq.y);
-          bsq.z = fmaf(o.z, o.z, bsq.z); bsq.w = fmaf(o.w, o.w, bsq.w);
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) {
+            const float4 o = f4add(f4scale(invZ, acc[u]), skip[u]);
+            st4(a.out + (size_t)i * H + (lig + u * LPR) * 4, o);
+            bsum[u] = f4add(bsum[u], o);
+            bsq[u].x = fmaf(o.x, o.x, bsq[u].x); bsq[u].y = fmaf(o.y, o.y, bsq[u].y);
+            bsq[u].z = fmaf(o.z, o.z, bsq[u].z); bsq[u].w = fmaf(o.w, o.w, bsq[u].w);
+          }
         }
         __syncwarp();
         for (int p = p0 + lig; p < p1; p += LPR) {
@@ -392,13 +429,16 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_fwd(TileArgs a) 
     double* sc = reinterpret_cast<double*>(S.ta);
     for (int x = tid; x < 2 * H; x += NT) sc[x] = 0.0;
     __syncthreads();
-    float vals[8] = {bsum.x, bsum.y, bsum.z, bsum.w, bsq.x, bsq.y, bsq.z, bsq.w};
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      float v = vals[kk];
+    for (int u = 0; u < VPL; ++u) {
+      float vals[8] = {bsum[u].x, bsum[u].y, bsum[u].z, bsum[u].w, bsq[u].x, bsq[u].y, bsq[u].z, bsq[u].w};
 #pragma unroll
-      for (int off = LPR; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);   // the warp's groups
-      if (grp == 0) atomicAdd(&sc[(kk < 4 ? 0 : H) + lig * 4 + (kk & 3)], (double)v);
+      for (int kk = 0; kk < 8; ++kk) {
+        float v = vals[kk];
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);   // the warp's groups
+        if (grp == 0) atomicAdd(&sc[(kk < 4 ? 0 : H) + (lig + u * LPR) * 4 + (kk & 3)], (double)v);
+      }
     }
     __syncthreads();
     for (int x = tid; x < 2 * H; x += NT)
@@ -813,21 +853,35 @@ int launch_k(K kernel, int grid, int threads, size_t bytes, const TileArgs& a, c
   return PERT_OK;
 }
 
-template <int LPR>
+// forward launch for row width H: the VPL = 2 variant (LPR = H / 8 lanes per node, 256-thread CTAs with up to 128
+// registers, still two CTAs per SM) when two CTAs fit an SM, else VPL = 1 with 1024-thread CTAs.  PERT_TCONV_VPL=1 forces
+// the one-vector-per-lane kernels (A/B).
+static int fwd_vpl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PERT_TCONV_VPL");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+template <int H>
 int launch_fwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, const PertTiles* tl,
                cudaStream_t st) {
-  constexpr int H = 4 * LPR;
   const TileGeom g = tl ? TileGeom{tl->T, tl->ecap} : tile_geom(H, a0.n_rpc, N, E, B);
   const size_t bytes = smem_bytes(g.T, H, 0, g.ecap, 3);   // src, packed ids, logit staging
   TileArgs a = a0;
   int grid = 0;
   const int per_sm = plan_launch(a, tl, g, bytes, N, grid);
   if (per_sm < 0) return (int)cudaGetLastError();
-  if (per_sm == 2)
-    return has_e ? launch_k(k_tile_fwd<LPR, true, 512>, grid, 512, bytes, a, st)
-                 : launch_k(k_tile_fwd<LPR, false, 512>, grid, 512, bytes, a, st);
-  return has_e ? launch_k(k_tile_fwd<LPR, true, 1024>, grid, 1024, bytes, a, st)
-               : launch_k(k_tile_fwd<LPR, false, 1024>, grid, 1024, bytes, a, st);
+  if (per_sm == 2) {
+    if (fwd_vpl() == 2 && H >= 32)
+      return has_e ? launch_k(k_tile_fwd<H / 8, 2, true, 256>, grid, 256, bytes, a, st)
+                   : launch_k(k_tile_fwd<H / 8, 2, false, 256>, grid, 256, bytes, a, st);
+    return has_e ? launch_k(k_tile_fwd<H / 4, 1, true, 512>, grid, 512, bytes, a, st)
+                 : launch_k(k_tile_fwd<H / 4, 1, false, 512>, grid, 512, bytes, a, st);
+  }
+  return has_e ? launch_k(k_tile_fwd<H / 4, 1, true, 1024>, grid, 1024, bytes, a, st)
+               : launch_k(k_tile_fwd<H / 4, 1, false, 1024>, grid, 1024, bytes, a, st);
 }
 template <int LPR>
 int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, const PertTiles* tl,
@@ -874,9 +928,9 @@ int pert_tile_fwd(const float* q, const float* k, const float* v, const float* s
   a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc; a.out = out; a.alpha = alpha; a.bn_acc = bn_acc;
   a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
   switch (H) {
-    case 32: return launch_fwd<8>(a, N, E, B, t_if != nullptr, tiles, st);
-    case 64: return launch_fwd<16>(a, N, E, B, t_if != nullptr, tiles, st);
-    case 128: return launch_fwd<32>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 32: return launch_fwd<32>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 64: return launch_fwd<64>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 128: return launch_fwd<128>(a, N, E, B, t_if != nullptr, tiles, st);
     default: return PERT_ERR_UNSUPPORTED;
   }
 }
