@@ -447,9 +447,9 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) k_tile_fwd(TileArgs a)
 }
 
 // ============================================================== backward, target pass (dq, ds)
-template <int LPR, bool HAS_E, int NT>
-__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs a) {
-  constexpr int H = 4 * LPR;
+template <int LPR, int VPL, bool HAS_E, int NT>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) k_tile_bwd_dst(TileArgs a) {
+  constexpr int H = 4 * LPR * VPL;
   constexpr int GPW = 32 / LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int GPC = NT / LPR;
@@ -457,8 +457,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs
   const SAddr sa = saddr_of(S);
   const int tid = threadIdx.x;
   const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
-  const uint32_t lane4 = lig * 16;
   const int g0 = (tid >> 5) * GPW;
+  auto ldrow = [&](const float* base, size_t row, float4 (&v)[VPL]) {
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) v[u] = ldg4(base + row * H + (lig + u * LPR) * 4);
+  };
   tile_barrier_init(S, tid);
   uint32_t phase = 0;
   int n0, nt;
@@ -481,24 +484,28 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs
 
     int slot = g0 + grp;
     int loc = slot < nt ? ldsu16(sa.ord + slot * 2) : 0;
-    float4 g_n = f4zero();
-    if (slot < nt) g_n = ldg4(a.g + (size_t)(n0 + loc) * H + lig * 4);
+    float4 g_n[VPL];
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) g_n[u] = f4zero();
+    if (slot < nt) ldrow(a.g, (size_t)(n0 + loc), g_n);
     auto run = [&](auto fast_c) {
       constexpr bool FAST = decltype(fast_c)::value;
       for (; slot - grp < nt; slot += GPC) {
         const bool valid = slot < nt;
         const int i = n0 + loc;
-        const float4 g = g_n;
+        float4 g[VPL];
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) g[u] = g_n[u];
         const int p0 = valid ? ldsi(sa.ptr + loc * 4) : 0;
         const int p1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
         if (slot + GPC < nt) {
           loc = ldsu16(sa.ord + (slot + GPC) * 2);
-          g_n = ldg4(a.g + (size_t)(n0 + loc) * H + lig * 4);
+          ldrow(a.g, (size_t)(n0 + loc), g_n);
         }
         const int deg = p1 - p0;
         const int degmax = __reduce_max_sync(0xffffffffu, deg);
         // one edge record: source row offsets + e = T_if[a] + T_rpc[b]
-        auto edge = [&](int p, bool on, int& j, float& al, float4& e, int& rid) {
+        auto edge = [&](int p, bool on, int& j, float& al, float4 (&e)[VPL], int& rid) {
           j = n0;
           al = 0.f;
           int id = 0;
@@ -514,9 +521,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs
               if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
             }
           }
-          e = f4zero();
-          if (HAS_E)
-            e = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + lig * 4), ldg4(a.t_rpc + ID_RPC(id) * H + lig * 4));
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) {
+            e[u] = f4zero();
+            if (HAS_E)
+              e[u] = f4add(ldg4(a.t_if + (size_t)ID_IF(id) * H + (lig + u * LPR) * 4),
+                           ldg4(a.t_rpc + ID_RPC(id) * H + (lig + u * LPR) * 4));
+          }
           rid = ID_RPC(id);
         };
         // ONE pass over the in-edges.  With d_t = <g_i, v_j + e_t> (shifted by the first edge's value c, which cancels
@@ -526,32 +537,43 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs
         // so k_j, v_j and the table rows of an edge are fetched once (the two-pass form fetched the edge record and
         // its table rows twice); ds_t is written by a scalar post-pass with the lanes spread over the node's edges.
         float dot = 0.f, c_shift = 0.f;
-        float4 P = f4zero(), Q = f4zero();
+        float4 P[VPL], Q[VPL];
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) P[u] = Q[u] = f4zero();
         float sumA = 0.f, sumW = 0.f;          // lane b: sums of alpha / w over this node's in-edges of rpc type b
         for (int t = 0; t < degmax; ++t) {
           const bool on = t < deg;
           const int p = p0 + t;
           int j, rid;
           float al;
-          float4 e;
+          float4 e[VPL];
           edge(p, on, j, al, e, rid);
-          float4 kk, vv;
+          float4 kk[VPL], vv[VPL];
           const unsigned sl = (unsigned)(j - n0);
           if (FAST || sl < (unsigned)nt) {
-            kk = lds4s(sa.ta + sl * (H * 4) + lane4);
-            vv = lds4s(sa.tb + sl * (H * 4) + lane4);
+#pragma unroll
+            for (int u = 0; u < VPL; ++u) {
+              kk[u] = lds4s(sa.ta + sl * (H * 4) + (lig + u * LPR) * 16);
+              vv[u] = lds4s(sa.tb + sl * (H * 4) + (lig + u * LPR) * 16);
+            }
           } else {
-            kk = ldg4(a.k + (size_t)j * H + lig * 4);
-            vv = ldg4(a.v + (size_t)j * H + lig * 4);
+            ldrow(a.k, (size_t)j, kk);
+            ldrow(a.v, (size_t)j, vv);
           }
-          const float da = gsum_full<LPR>(f4dot(g, f4add(vv, e)));
+          float part = 0.f;
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) part += f4dot(g[u], f4add(vv[u], e[u]));
+          const float da = gsum_full<LPR>(part);
           if (t == 0) c_shift = da;
           const float dc = da - c_shift;
           const float w = al * dc;             // alpha is 0 on finished groups
           dot += w;
-          const float4 ke = f4add(kk, e);
-          P = f4fma(w, ke, P);
-          Q = f4fma(al, ke, Q);
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) {
+            const float4 ke = f4add(kk[u], e[u]);
+            P[u] = f4fma(w, ke, P[u]);
+            Q[u] = f4fma(al, ke, Q[u]);
+          }
           if (HAS_E && on && lig == rid) { sumA += al; sumW += w; }
           if (on && lig == 0) {
             const int le = p - e_lo;
@@ -559,9 +581,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs
             else a.dsp[p] = dc;
           }
         }
-        float4 dq;
-        dq.x = (P.x - dot * Q.x) * a.inv_sqrt_c; dq.y = (P.y - dot * Q.y) * a.inv_sqrt_c;
-        dq.z = (P.z - dot * Q.z) * a.inv_sqrt_c; dq.w = (P.w - dot * Q.w) * a.inv_sqrt_c;
         const float sumS = (sumW - dot * sumA) * a.inv_sqrt_c;
         __syncwarp();
         for (int p = p0 + lig; p < p1; p += LPR) {
@@ -570,7 +589,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs
           const float al = (FAST || le < ne_s) ? ldsf(sa.f0 + le * 4) : __ldg(a.alpha + p);
           a.dsp[p] = al * (dc - dot) * a.inv_sqrt_c;
         }
-        if (valid) st4(a.out + (size_t)i * H + lig * 4, dq);
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) {
+            float4 dq;
+            dq.x = (P[u].x - dot * Q[u].x) * a.inv_sqrt_c; dq.y = (P[u].y - dot * Q[u].y) * a.inv_sqrt_c;
+            dq.z = (P[u].z - dot * Q[u].z) * a.inv_sqrt_c; dq.w = (P[u].w - dot * Q[u].w) * a.inv_sqrt_c;
+            st4(a.out + (size_t)i * H + (lig + u * LPR) * 4, dq);
+          }
+        }
         if (HAS_E && a.rpc_ws && valid && lig < RPC_FAST) {
           a.rpc_ws[(size_t)i * 2 * RPC_FAST + lig] = sumA;
           a.rpc_ws[(size_t)i * 2 * RPC_FAST + RPC_FAST + lig] = sumS;
@@ -583,9 +610,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_dst(TileArgs
 }
 
 // ============================================================== backward, source pass (dk, dv, table grads)
-template <int LPR, bool HAS_E, int NT>
-__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_src(TileArgs a) {
-  constexpr int H = 4 * LPR;
+template <int LPR, int VPL, bool HAS_E, int NT>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) k_tile_bwd_src(TileArgs a) {
+  constexpr int H = 4 * LPR * VPL;
   constexpr int GPW = 32 / LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int GPC = NT / LPR;
@@ -593,7 +620,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_src(TileArgs
   const SAddr sa = saddr_of(S);
   const int tid = threadIdx.x;
   const int lane = tid & 31, lig = lane % LPR, grp = lane / LPR;
-  const uint32_t lane4 = lig * 16;
   const int g0 = (tid >> 5) * GPW;
   float* s_drpc = S.rpc;   // privatised gradient of the rpc-type table (few hot rows), flushed once per CTA
   if (HAS_E)
@@ -631,7 +657,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_src(TileArgs
       const int c1 = valid ? ldsi(sa.ptr + loc * 4 + 4) : 0;
       const int deg = c1 - c0;
       const int degmax = __reduce_max_sync(0xffffffffu, deg);
-      float4 dk = f4zero(), dv = f4zero();
+      float4 dk[VPL], dv[VPL];
+#pragma unroll
+      for (int u = 0; u < VPL; ++u) dk[u] = dv[u] = f4zero();
       for (int t = 0; t < degmax; ++t) {
         const bool on = t < deg;
         const int c = c0 + t;
@@ -648,32 +676,38 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_tile_bwd_src(TileArgs
             if (HAS_E) id = PACK_ID(__ldg(a.csr_if + p), __ldg(a.csr_rpc + p));
           }
         }
-        float4 gi, qi;
         const unsigned sl = (unsigned)(i - n0);
-        if (FAST || sl < (unsigned)nt) {
-          gi = lds4s(sa.ta + sl * (H * 4) + lane4);
-          qi = lds4s(sa.tb + sl * (H * 4) + lane4);
-        } else {
-          gi = ldg4(a.g + (size_t)i * H + lig * 4);
-          qi = ldg4(a.q + (size_t)i * H + lig * 4);
-        }
-        dk = f4fma(ds, qi, dk);
-        dv = f4fma(al, gi, dv);
-        if (HAS_E && on) {
-          const float4 de = f4fma(ds, qi, f4scale(al, gi));
-          red4(a.dt_if + (size_t)ID_IF(id) * H + lig * 4, de);
-          if (!a.rpc_ws) {                 // general path (n_rpc > RPC_FAST): privatised table, per-edge atomics
-            float* prp = s_drpc + ID_RPC(id) * H + lig * 4;
-            atomicAdd(prp + 0, de.x);
-            atomicAdd(prp + 1, de.y);
-            atomicAdd(prp + 2, de.z);
-            atomicAdd(prp + 3, de.w);
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          float4 gi, qi;
+          if (FAST || sl < (unsigned)nt) {
+            gi = lds4s(sa.ta + sl * (H * 4) + (lig + u * LPR) * 16);
+            qi = lds4s(sa.tb + sl * (H * 4) + (lig + u * LPR) * 16);
+          } else {
+            gi = ldg4(a.g + (size_t)i * H + (lig + u * LPR) * 4);
+            qi = ldg4(a.q + (size_t)i * H + (lig + u * LPR) * 4);
+          }
+          dk[u] = f4fma(ds, qi, dk[u]);
+          dv[u] = f4fma(al, gi, dv[u]);
+          if (HAS_E && on) {
+            const float4 de = f4fma(ds, qi, f4scale(al, gi));
+            red4(a.dt_if + (size_t)ID_IF(id) * H + (lig + u * LPR) * 4, de);
+            if (!a.rpc_ws) {                 // general path (n_rpc > RPC_FAST): privatised table, per-edge atomics
+              float* prp = s_drpc + ID_RPC(id) * H + (lig + u * LPR) * 4;
+              atomicAdd(prp + 0, de.x);
+              atomicAdd(prp + 1, de.y);
+              atomicAdd(prp + 2, de.z);
+              atomicAdd(prp + 3, de.w);
+            }
           }
         }
       }
       if (valid) {
-        st4(a.dk + (size_t)jn * H + lig * 4, dk);
-        st4(a.dv + (size_t)jn * H + lig * 4, dv);
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          st4(a.dk + (size_t)jn * H + (lig + u * LPR) * 4, dk[u]);
+          st4(a.dv + (size_t)jn * H + (lig + u * LPR) * 4, dv[u]);
+        }
       }
     }
   };
@@ -883,10 +917,9 @@ int launch_fwd(const TileArgs& a0, long long N, long long E, long long B, bool h
   return has_e ? launch_k(k_tile_fwd<H / 4, 1, true, 1024>, grid, 1024, bytes, a, st)
                : launch_k(k_tile_fwd<H / 4, 1, false, 1024>, grid, 1024, bytes, a, st);
 }
-template <int LPR>
+template <int H>
 int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool has_e, const PertTiles* tl,
                cudaStream_t st) {
-  constexpr int H = 4 * LPR;
   const TileGeom g = tl ? TileGeom{tl->T, tl->ecap} : tile_geom(H, a0.n_rpc, N, E, B);
   const size_t bd = smem_bytes(g.T, H, 0, g.ecap, 4);                      // src, ids, alpha, dalpha staging
   const size_t bs = smem_bytes(g.T, H, has_e ? a0.n_rpc : 0, g.ecap, 4);   // dst, ids, alpha, ds
@@ -894,22 +927,34 @@ int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool h
   int gd = 0, gs = 0;
   const int pd = plan_launch(ad, tl, g, bd, N, gd), ps = plan_launch(as, tl, g, bs, N, gs);
   if (pd < 0 || ps < 0) return (int)cudaGetLastError();
+  // VPL = 2 (H / 8 lanes per node, 256-thread CTAs) whenever two CTAs share an SM and the rpc sums still have a lane per
+  // type (LPR >= RPC_FAST), i.e. H >= 64; else one vector per lane
+  const bool vpl2 = fwd_vpl() == 2 && pd == 2 && ps == 2 && H / 8 >= RPC_FAST;
+  constexpr int L1 = H / 4, L2 = H / 8 > 0 ? H / 8 : 1;
   // per-target rpc sums (see RPC_FAST) live in caller scratch; without it the general atomics path runs
-  float* ws = (has_e && a0.n_rpc <= RPC_FAST && LPR >= RPC_FAST && 512 % H == 0) ? a0.rpc_ws : nullptr;
+  const int lpr = vpl2 ? L2 : L1, nthr = vpl2 ? 256 : (ps == 2 ? 512 : 1024);
+  float* ws = (has_e && a0.n_rpc <= RPC_FAST && lpr >= RPC_FAST && nthr % H == 0) ? a0.rpc_ws : nullptr;
   ad.rpc_ws = as.rpc_ws = ws;
   int rc;
+  if (vpl2) {
+    rc = has_e ? launch_k(k_tile_bwd_dst<L2, 2, true, 256>, gd, 256, bd, ad, st)
+               : launch_k(k_tile_bwd_dst<L2, 2, false, 256>, gd, 256, bd, ad, st);
+    if (rc) return rc;
+    return has_e ? launch_k(k_tile_bwd_src<L2, 2, true, 256>, gs, 256, bs, as, st)
+                 : launch_k(k_tile_bwd_src<L2, 2, false, 256>, gs, 256, bs, as, st);
+  }
   if (pd == 2)
-    rc = has_e ? launch_k(k_tile_bwd_dst<LPR, true, 512>, gd, 512, bd, ad, st)
-               : launch_k(k_tile_bwd_dst<LPR, false, 512>, gd, 512, bd, ad, st);
+    rc = has_e ? launch_k(k_tile_bwd_dst<L1, 1, true, 512>, gd, 512, bd, ad, st)
+               : launch_k(k_tile_bwd_dst<L1, 1, false, 512>, gd, 512, bd, ad, st);
   else
-    rc = has_e ? launch_k(k_tile_bwd_dst<LPR, true, 1024>, gd, 1024, bd, ad, st)
-               : launch_k(k_tile_bwd_dst<LPR, false, 1024>, gd, 1024, bd, ad, st);
+    rc = has_e ? launch_k(k_tile_bwd_dst<L1, 1, true, 1024>, gd, 1024, bd, ad, st)
+               : launch_k(k_tile_bwd_dst<L1, 1, false, 1024>, gd, 1024, bd, ad, st);
   if (rc) return rc;
   if (ps == 2)
-    return has_e ? launch_k(k_tile_bwd_src<LPR, true, 512>, gs, 512, bs, as, st)
-                 : launch_k(k_tile_bwd_src<LPR, false, 512>, gs, 512, bs, as, st);
-  return has_e ? launch_k(k_tile_bwd_src<LPR, true, 1024>, gs, 1024, bs, as, st)
-               : launch_k(k_tile_bwd_src<LPR, false, 1024>, gs, 1024, bs, as, st);
+    return has_e ? launch_k(k_tile_bwd_src<L1, 1, true, 512>, gs, 512, bs, as, st)
+                 : launch_k(k_tile_bwd_src<L1, 1, false, 512>, gs, 512, bs, as, st);
+  return has_e ? launch_k(k_tile_bwd_src<L1, 1, true, 1024>, gs, 1024, bs, as, st)
+               : launch_k(k_tile_bwd_src<L1, 1, false, 1024>, gs, 1024, bs, as, st);
 }
 
 }  // namespace
@@ -951,9 +996,9 @@ int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, con
   a.dt_if = dt_if; a.dt_rpc = dt_rpc; a.rpc_ws = rpc_ws;
   a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
   switch (H) {
-    case 32: return launch_bwd<8>(a, N, E, B, t_if != nullptr, tiles, st);
-    case 64: return launch_bwd<16>(a, N, E, B, t_if != nullptr, tiles, st);
-    case 128: return launch_bwd<32>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 32: return launch_bwd<32>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 64: return launch_bwd<64>(a, N, E, B, t_if != nullptr, tiles, st);
+    case 128: return launch_bwd<128>(a, N, E, B, t_if != nullptr, tiles, st);
     default: return PERT_ERR_UNSUPPORTED;
   }
 }
