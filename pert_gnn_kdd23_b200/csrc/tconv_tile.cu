@@ -929,7 +929,15 @@ int launch_bwd(const TileArgs& a0, long long N, long long E, long long B, bool h
   if (pd < 0 || ps < 0) return (int)cudaGetLastError();
   // VPL = 2 (H / 8 lanes per node, 256-thread CTAs) whenever two CTAs share an SM and the rpc sums still have a lane per
   // type (LPR >= RPC_FAST), i.e. H >= 64; else one vector per lane
-  const bool vpl2 = fwd_vpl() == 2 && pd == 2 && ps == 2 && H / 8 >= RPC_FAST;
+  // (measured r2: the two-vector variant HURTS the backward pair -- cfg2 61.3 vs 59.3 us, cfg3 148 vs 129 -- whose REDG
+  // and shared-memory atomics want the resident warps more than fewer instructions; forward gains 12 %.  So the
+  // backward default stays one vector per lane; PERT_TCONV_VPL_BWD=2 selects the other for A/B.)
+  static int bwd_v = -1;
+  if (bwd_v < 0) {
+    const char* e = getenv("PERT_TCONV_VPL_BWD");
+    bwd_v = (e && e[0] == '2') ? 2 : 1;
+  }
+  const bool vpl2 = bwd_v == 2 && pd == 2 && ps == 2 && H / 8 >= RPC_FAST;
   constexpr int L1 = H / 4, L2 = H / 8 > 0 ? H / 8 : 1;
   // per-target rpc sums (see RPC_FAST) live in caller scratch; without it the general atomics path runs
   const int lpr = vpl2 ? L2 : L1, nthr = vpl2 ? 256 : (ps == 2 ? 512 : 1024);
