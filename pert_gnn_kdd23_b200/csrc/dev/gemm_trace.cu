@@ -50,23 +50,29 @@ int main() {
   float ms;
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    int rc = pert_gemm_nt_tc(X, H, 0, 0, W, H, bias, P, H, H, N * H, N, 4 * H, H, 0, 0);
+    int rc = 0;
+    for (int k = 0; k < 10; ++k) rc |= pert_gemm_nt_tc(X, H, 0, 0, W, H, bias, P, H, H, N * H, N, 4 * H, H, 0, 0);   // train of 10: launch gaps amortised
     cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    ms /= 10.f;
     if (rc) printf("nt fwd rc %d\n", rc);
   }
   dump("NT forward [N,64]x[256,64]^T -> planes", 6, 8, 4, ms);
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
     // data gradient: dX[N,64] = dP[N,256 blocked] . Wt[64,256]^T   (B rows = output features, K = 256)
-    int rc = pert_gemm_nt_tc(P, H, H, N * H, W, 4 * H, nullptr, dX, H, 0, 0, N, H, 4 * H, 0, 0);
+    int rc = 0;
+    for (int k = 0; k < 10; ++k) rc |= pert_gemm_nt_tc(P, H, H, N * H, W, 4 * H, nullptr, dX, H, 0, 0, N, H, 4 * H, 0, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    ms /= 10.f;
     if (rc) printf("nt dgrad rc %d\n", rc);
   }
   dump("NT dgrad planes x [64,256]^T -> [N,64]", 6, 14, 4, ms);
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    int rc = pert_gemm_tn_tc(P, H, H, N * H, X, H, 0, 0, dW, H, cs, N, 4 * H, H, 0);
+    int rc = 0;
+    for (int k = 0; k < 10; ++k) rc |= pert_gemm_tn_tc(P, H, H, N * H, X, H, 0, 0, dW, H, cs, N, 4 * H, H, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    ms /= 10.f;
     if (rc) printf("tn rc %d\n", rc);
   }
   dump("TN wgrad planes^T x X -> [256,64]", 4, 12, 3, ms);
