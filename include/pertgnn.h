@@ -44,7 +44,8 @@ extern "C" {
 #define PERT_ERR_RANGE (-3)
 #define PERT_ERR_PEER_TIMEOUT (-4)
 
-/* ABI version (major*1000 + minor).  2000: pert_tconv_bwd takes rpc_ws; node_depth / eval-metric entry points. */
+/* ABI version (major*1000 + minor).  2000: pert_tconv_bwd takes rpc_ws; node_depth / eval-metric entry points.
+ * 2001: pert_pert_graph_count / pert_pert_graph_build. */
 int pert_version(void);
 
 /* ---- index construction (integer, bit-exact) ---------------------------------------------------
@@ -322,6 +323,27 @@ typedef struct PertBatchOut {
  * reference raises KeyError there). */
 int pert_store_assemble(const PertStore* store, const int64_t* trace_ids, long long B, long long N, long long E,
                         int* offsets, const PertBatchOut* out, int* status, void* stream);
+
+/* ---- PERT-graph construction ---------------------------------------------------------------
+ * Replaces misc.py:221-319 (GraphConstruct.get_pert_edge_index) for T traces at once.  Input: the cleaned span rows
+ * (what misc.py:87-105 drop_wrong_edges leaves) of all traces concatenated, row_ptr[T+1]; per row um, dm, interface,
+ * rpctype, t_start (= timestamp), t_end (= endTimestamp), all int64 [R]; root_ms[T] (misc.py:138-142).
+ * Output per trace: nodes = 2*rows + distinct microservices, edges = 4*rows (edge slots of trace t start at
+ * 4*row_ptr[t]); ms_id[N] = sorted_span_id; edge_index[2,4R] with trace-local node ids (global_ids = 0, the
+ * per-pattern tensors the reference stores) or batch-global ids (global_ids = 1); edge_attr[4R,4] =
+ * [interface, rpctype, call, same_ms]; root_nid[T] = GLOBAL id of stage 0 of the root microservice (-1 + PERT_ERR_RANGE
+ * in status if the root is absent; the reference raises KeyError).  Node numbering is the canonical order documented
+ * in csrc/pertgraph.cu (the reference's is pandas / set iteration order); edge order is the reference's.
+ * Two passes so the caller can size the outputs: _count writes node_cnt[T]; the caller scans it into node_ptr[T+1].
+ * max_rows >= the longest trace (<= PERT_PERT_GRAPH_MAX_ROWS); a longer trace sets PERT_ERR_RANGE. */
+#define PERT_PERT_GRAPH_MAX_ROWS 2048
+int pert_pert_graph_count(const int64_t* row_ptr, long long T, const int64_t* um, const int64_t* dm, int max_rows,
+                          int64_t* node_cnt, int* status, void* stream);
+int pert_pert_graph_build(const int64_t* row_ptr, long long T, long long R, const int64_t* um, const int64_t* dm,
+                          const int64_t* interface, const int64_t* rpctype, const int64_t* t_start,
+                          const int64_t* t_end, const int64_t* root_ms, const int64_t* node_ptr, int max_rows,
+                          int global_ids, int64_t* ms_id, int64_t* edge_index, int64_t* edge_attr, int64_t* root_nid,
+                          int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,9 @@ SIGNATURES = {
     "pert_allreduce_adam": (I, [P, P, P, P, LL, F, F, F, F, F, LL, F, P, I, I, P, P, P]),
     # device-side batch assembly from the pattern store (first / 7th argument: struct pointers, see store.py)
     "pert_store_assemble": (I, [P, P, LL, LL, LL, P, P, P, P]),
+    # PERT-graph construction (pertgraph.py)
+    "pert_pert_graph_count": (I, [P, LL, P, P, I, P, P, P]),
+    "pert_pert_graph_build": (I, [P, LL, LL, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
     # whole-model engine (first argument: const PertModelDesc*, see engine.py)
     "pert_model_workspace_bytes": (LL, [P, LL, LL, LL]),
     "pert_model_packed_bytes": (LL, [P]),

@@ -248,3 +248,46 @@ def make_trace_artifacts(seed=7, n_ms=48, n_patterns=14, n_entries=6, n_traces=7
     values = rng.random((len(index), N_FEAT - 1)).astype(np.float64)     # read back from CSV as float64
     return {"runtime2graph": runtime2graph, "entry2runtimes": entry2runtimes, "tr2data": tr2data,
             "resource_index": index, "resource_values": values, "n_ms": n_ms, "n_if": n_if, "n_rpc": n_rpc}
+
+
+def make_span_tables(seed=11, n_traces=24, n_ms=40, calls=(1, 30), n_if=32, n_rpc=6, anomalies=True):
+    """Raw per-trace span tables with the columns the reference's preprocessing hands to GraphConstruct
+    (preprocess.py:296-318: timestamp, rpcid, um, rpctype, dm, interface, rt, endTimestamp = timestamp + |rt|, :263),
+    all int64.  -> list of dicts.  The first generated call (root -> entry service) has the strictly largest |rt| and
+    the smallest timestamp, which is how misc.py:138-142 identifies the root.  Timestamps are coarse on purpose
+    (many ties, zero-length calls) and, with ``anomalies``, the rows include what misc.py:87-105 drop_wrong_edges
+    removes: self loops, repeated rpcids, calls back to the root, repeated (um, dm) pairs and reversed pairs."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_traces):
+        m = int(rng.integers(calls[0], calls[1] + 1))
+        root, entry = (int(v) for v in rng.choice(n_ms, size=2, replace=False))
+        t0 = int(rng.integers(1000, 5000))
+        rows = [[t0, root, entry, 200 + int(rng.integers(0, 50))]]     # timestamp, um, dm, rt
+        called = [entry]
+        for _k in range(m - 1):
+            um = called[int(rng.integers(0, len(called)))] if rng.random() < 0.8 else int(rng.integers(0, n_ms))
+            dm = int(rng.integers(0, n_ms))
+            if anomalies and rng.random() < 0.06:
+                dm = um                                              # self loop
+            elif anomalies and rng.random() < 0.06:
+                dm = root                                            # call back to the root
+            elif anomalies and rng.random() < 0.08 and len(rows) > 1:
+                o = rows[int(rng.integers(1, len(rows)))]
+                um, dm = (o[1], o[2]) if rng.random() < 0.5 else (o[2], o[1])   # repeated / reversed pair
+            rt = int(rng.integers(0, 6)) * (1 if rng.random() < 0.5 else -1)
+            rows.append([t0 + int(rng.integers(0, 8)), um, dm, rt])
+            called.append(dm)
+        rows = np.array(rows, dtype=np.int64)
+        rows = rows[rng.permutation(len(rows))]
+        n = len(rows)
+        rpcid = np.arange(n, dtype=np.int64)
+        if anomalies and n > 3:
+            for _d in range(int(rng.integers(0, 3))):
+                a, b = rng.integers(0, n, size=2)
+                rpcid[a] = rpcid[b]                                  # repeated rpcid
+        out.append({"timestamp": rows[:, 0].copy(), "um": rows[:, 1].copy(), "dm": rows[:, 2].copy(),
+                    "rt": rows[:, 3].copy(), "rpcid": rpcid, "interface": rng.integers(0, n_if, n).astype(np.int64),
+                    "rpctype": rng.integers(0, n_rpc, n).astype(np.int64),
+                    "endTimestamp": rows[:, 0] + np.abs(rows[:, 3])})
+    return out

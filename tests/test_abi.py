@@ -32,7 +32,7 @@ def test_version_and_host_side_validation():
     from pert_gnn_kdd23_b200 import _lib
 
     L = _lib.lib()
-    assert L.pert_version() >= 2000
+    assert L.pert_version() >= 2001
     assert L.pert_index_workspace_bytes(10, 20) > 0
     assert L.pert_index_workspace_bytes(-1, 0) == -1
     assert L.pert_tconv_supported_width(64) == 1 and L.pert_tconv_supported_width(65) == 0
@@ -45,6 +45,8 @@ def test_version_and_host_side_validation():
                                  None, None) == -1
     assert L.pert_node_depth(None, 3, None, None, None) == -1 and L.pert_level_order(None, 3, None, None, None) == -1
     assert L.pert_eval_metrics(None, None, 0.5, 4, None, None) == -1
+    assert L.pert_pert_graph_count(None, 1, None, None, 8, None, None, None) == -1
+    assert L.pert_pert_graph_build(*([None, 1, 4] + [None] * 8 + [8, 0] + [None] * 6)) == -1
     assert L.pert_peer_exchange_bytes(1000) >= 2 * 1000 * 4 and L.pert_peer_exchange_bytes(-1) == 0
     assert L.pert_peer_open(None, None) == -1 and L.pert_peer_close(None) == 0 and L.pert_peer_free(None) == 0
 
