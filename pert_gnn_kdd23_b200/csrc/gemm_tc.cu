@@ -666,6 +666,7 @@ struct TnTmaArgs {
   float* colsum;
   int R, Mc, Nc, NcP, nchunks, NS, pw, a_contig, b_contig;
   unsigned int* ctr;   // this launch's ticket counters (see g_ticket_ring)
+  int nacc;            // TMEM accumulators the chunks rotate over (1..4)
 };
 struct TnTmaBars {
   uint64_t ring_full[RING_MAX], ring_empty[RING_MAX], op_full[2], op_empty[2], done;
@@ -676,6 +677,7 @@ struct TnTmaBars {
 // RCT: reduction rows per chunk (64; 32 when the 64-row operand + ring stages do not fit next to each other: Nc > 96)
 template <int GMAX, int RCT>
 __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
+  constexpr int TN_A_COL = TMEM_COLS - 4 * RCT;            // two A stages (hi | lo, RCT columns each) at the top of TMEM
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) TnTmaBars bars;
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
       for (int i = 0; i < RCT; ++i) csum += av[i];
       mbar_wait(&bars.op_empty[stage], ph ^ 1);
       fence_after();
-      const uint32_t t_hi = tmem + lane_off + A_COL + stage * 128;
+      const uint32_t t_hi = tmem + lane_off + TN_A_COL + stage * (2 * RCT);
 #pragma unroll
       for (int grp = 0; grp < RCT / 16; ++grp) {
         uint32_t hi[16], lo[16];
@@ -816,10 +818,18 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
     if (nproc > 0) {
       mbar_wait(&bars.done, 0);
       fence_after();
+      const int nused = nproc < g.nacc ? nproc : g.nacc;   // accumulators that received at least one chunk
       for (int c0 = 0; c0 < NcP; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_off + D_COL + c0, r);
         tmem_wait_ld();
+        for (int a = 1; a < nused; ++a) {                  // partial sums are combined with round-to-nearest adds
+          uint32_t r2[16];
+          tmem_ld16(tmem + lane_off + D_COL + a * NcP + c0, r2);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        }
         if (mok) {
           float* dst = g.C + (size_t)mcol * g.ldc + c0;
 #pragma unroll
@@ -891,15 +901,19 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_gemm_tn_tma(TnTmaArgs g) {
         if (bars.op_meta[stage] < 0) break;
         const uint32_t bhi0 = smem_u32(smem + (size_t)stage * 2 * op_bytes);
         const uint32_t blo0 = bhi0 + (uint32_t)op_bytes;
-        const uint32_t t_hi = tmem + A_COL + stage * 128;
+        const uint32_t t_hi = tmem + TN_A_COL + stage * (2 * RCT);
+        // Chunks rotate over nacc accumulators: the tensor core truncates every accumulation (round toward zero), a
+        // one-sided error that grows with the number of steps times the ulp of the running sum; nacc shorter, smaller
+        // partial sums divide it by nacc (the epilogue adds them with round-to-nearest).
+        const uint32_t d = tmem + D_COL + (uint32_t)(n % g.nacc) * NcP;
 #pragma unroll
         for (int s = 0; s < RCT / 8; ++s) {
           const uint32_t koff = (uint32_t)s * 2 * LBO;
           const uint64_t bhi = make_desc(bhi0 + koff, LBO, SBO);
           const uint64_t blo = make_desc(blo0 + koff, LBO, SBO);
-          mma_ts(tmem + D_COL, t_hi + s * 8, bhi, idesc, (n | s) ? 1u : 0u);
-          mma_ts(tmem + D_COL, t_hi + RCT + s * 8, bhi, idesc, 1u);
-          mma_ts(tmem + D_COL, t_hi + s * 8, blo, idesc, 1u);
+          mma_ts(d, t_hi + s * 8, bhi, idesc, (n >= g.nacc || s) ? 1u : 0u);
+          mma_ts(d, t_hi + RCT + s * 8, bhi, idesc, 1u);
+          mma_ts(d, t_hi + s * 8, blo, idesc, 1u);
         }
         mma_commit(&bars.op_empty[stage]);
         ++n;
@@ -1303,6 +1317,14 @@ static bool tma_enabled() {
   }
   return on == 1;
 }
+static bool tn_single_acc() {   // PERT_GEMM_TN_ACC=1: one weight-gradient accumulator (accuracy A/B)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PERT_GEMM_TN_ACC");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
 static bool tc_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -1471,8 +1493,11 @@ int pert_gemm_tn_tc(const float* A, int lda, int a_cb, long long a_cbs, const fl
       int gx = PERT_NUM_SMS / mblk;
       if (gx < 1) gx = 1;
       if (gx > nchunks) gx = nchunks;
+      int nacc = (TMEM_COLS - 4 * rc) / NcP;               // accumulators that fit below the A stages
+      nacc = nacc > 4 ? 4 : (nacc < 1 ? 1 : nacc);
+      if (tn_single_acc()) nacc = 1;
       TnTmaArgs g{A,        lda, a_cb, a_cbs, B,   ldb,     C,  ldc, a_colsum,
-                  (int)R,   Mc,  Nc,   NcP,   nchunks, NS, pw, lda == pw ? 1 : 0, ldb == Nc ? 1 : 0, ticket_slot()};
+                  (int)R,   Mc,  Nc,   NcP,   nchunks, NS, pw, lda == pw ? 1 : 0, ldb == Nc ? 1 : 0, ticket_slot(), nacc};
       if (!g.ctr) return (int)cudaGetLastError();
       const size_t smem = op + ring * NS;
       const int ngrp = (NcP + 31) / 32;

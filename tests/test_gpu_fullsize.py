@@ -204,10 +204,12 @@ def test_model_cfg4_shard():
 
 
 def test_model_cfg5_full():
-    # 5 layers x 256,000 nodes x 128: outputs / loss / BN statistics at 1e-4; gradients at 3e-4 -- the truncating
-    # tensor-core accumulators compound over ten GEMM layers of backward: measured <= 1.9e-4
-    # (convs.1.lin_skip.weight) where the exact-fp32 reference path itself is 5e-6 from fp64
-    _full_parity(5, None, "cfg5[256x1000]", grad_rtol=3e-4)
+    # 5 layers x 256,000 nodes x 128: outputs / loss / BN statistics at 1e-4; gradients at 2e-4 -- the truncating
+    # tensor-core accumulators compound over ten GEMM layers of backward: measured <= 8.4e-5
+    # (convs.3.lin_edge.weight; 1.9e-4 before the weight-gradient kernel rotated its chunks over several TMEM
+    # accumulators) where the exact-fp32 reference path itself is 1.3e-5 from fp64 -- the bar leaves the run-to-run
+    # spread of the float atomics (x1.5) above the measured value
+    _full_parity(5, None, "cfg5[256x1000]", grad_rtol=2e-4)
 
 
 def test_model_cfg2_jittered_sizes():
