@@ -85,25 +85,39 @@ class PertGraphs:
 
 def build_pert_graphs(tables, roots, device="cuda"):
     """``tables``: per trace a dict of the CLEANED span rows (COLUMNS, int64 array-likes); ``roots``: root
-    microservice per trace.  One H2D copy of the concatenated rows, two kernel launches for the graphs, the level
-    index for ``node_depth``; the only synchronisation is reading the node total to size the outputs."""
-    dev = torch.device(device)
-    if dev.type != "cuda":
-        raise _lib.PertGnnError("build_pert_graphs needs a CUDA device (no CPU fallback)")
+    microservice per trace.  Concatenates on the host and calls ``build_pert_graphs_flat``."""
     T = len(tables)
     rows = np.array([len(t["um"]) for t in tables], dtype=np.int64)
     row_ptr = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
     R = int(row_ptr[-1])
     if T == 0 or R == 0:
         raise ValueError("no span rows")
-    max_rows = int(rows.max())
-    if max_rows > MAX_ROWS:
-        raise _lib.PertGnnError(f"a trace has {max_rows} rows; the kernel handles at most {MAX_ROWS}")
     host = np.empty((len(COLUMNS), R), dtype=np.int64)
     for c, name in enumerate(COLUMNS):
         host[c] = np.concatenate([np.asarray(t[name], dtype=np.int64).reshape(-1) for t in tables])
+    return build_pert_graphs_flat(host, row_ptr, roots, device)
+
+
+def build_pert_graphs_flat(columns, row_ptr, roots, device="cuda"):
+    """``columns``: int64 [6, R] (rows of COLUMNS, all traces concatenated -- a span table grouped by trace id, host
+    array or CUDA tensor); ``row_ptr``: int64 [T+1] host array; ``roots``: [T].  One H2D copy of the rows, two kernel
+    launches for the graphs, the level index for ``node_depth``; the only synchronisation is reading the node total
+    to size the outputs."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.PertGnnError("build_pert_graphs needs a CUDA device (no CPU fallback)")
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    T, R = len(row_ptr) - 1, int(row_ptr[-1])
+    rows = np.diff(row_ptr)
+    if T <= 0 or R <= 0:
+        raise ValueError("no span rows")
+    max_rows = int(rows.max())
+    if max_rows > MAX_ROWS:
+        raise _lib.PertGnnError(f"a trace has {max_rows} rows; the kernel handles at most {MAX_ROWS}")
     with torch.cuda.device(dev):
-        cols = torch.from_numpy(host).to(dev)
+        cols = columns if torch.is_tensor(columns) else torch.from_numpy(np.ascontiguousarray(columns, dtype=np.int64))
+        cols = cols.to(dev).contiguous()
+        assert cols.dtype == torch.int64 and tuple(cols.shape) == (len(COLUMNS), R)
         rp = torch.from_numpy(row_ptr).to(dev)
         rm = torch.as_tensor(np.asarray(roots, dtype=np.int64)).to(dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)

