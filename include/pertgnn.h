@@ -45,7 +45,7 @@ extern "C" {
 #define PERT_ERR_PEER_TIMEOUT (-4)
 
 /* ABI version (major*1000 + minor).  2000: pert_tconv_bwd takes rpc_ws; node_depth / eval-metric entry points.
- * 2001: pert_pert_graph_count / pert_pert_graph_build. */
+ * 2001: pert_pert_graph_count / pert_pert_graph_build.  2002: pert_allreduce_adam timing[5], reduce-scatter form. */
 int pert_version(void);
 
 /* ---- index construction (integer, bit-exact) ---------------------------------------------------
@@ -185,8 +185,13 @@ int pert_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
                    float eps, float weight_decay, long long step, float grad_scale, void* stream);
 
 /* ---- gradient all-reduce fused with Adam over NVLink peer memory (csrc/peer.cu) ---------------------------
- * Data-parallel form of pert_adam_step: every rank publishes its flat gradient in an IPC-shared exchange buffer,
- * waits for the peers' flags and applies Adam to the rank-ordered sum -- one kernel per step, no NCCL on the step
+ * Data-parallel form of pert_adam_step, one kernel per step and no NCCL on the step path: every rank publishes its
+ * flat gradient in an IPC-shared exchange buffer and signals the peers; rank r then sums slice r of all gradients in
+ * rank order (1/world of each peer's buffer over NVLink), applies Adam to that slice (m, v are only maintained for the
+ * owned slice, ZeRO-1 style) and stores the new parameters into every peer's buffer; a second flag round collects the
+ * other slices (replicas bit-identical by construction).  That form runs for world > 4; up to 4 ranks every rank pulls
+ * whole gradients and runs the full Adam with ONE flag round (cheaper while the volume is small; measured both ways at
+ * 2 and 8 GPUs).  PERT_PEER_MODE=ag|rs (environment, same on all ranks) forces one form.
  * path.  Setup: pert_peer_alloc on every rank, exchange the 64-byte handles out of band (torch.distributed
  * all_gather), pert_peer_open the peers'.  `xbufs` is a HOST array of `world` device pointers (index = rank).
  * `step` = 1, 2, ... must equal the number of calls so far on every rank (the arrival counter is monotonic).
@@ -199,9 +204,10 @@ int pert_peer_free(void* ptr);
 int pert_allreduce_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, long long step, float grad_scale, void* const* xbufs, int rank,
                         int world, int* status, long long* timing, void* stream);
-/* timing (optional device int64[4]): CTA 0 adds the nanoseconds (%globaltimer) it spent in (0) publishing the gradient
+/* timing (optional device int64[5]): CTA 0 adds the nanoseconds (%globaltimer) it spent in (0) publishing the gradient
  * + grid arrival, (1) waiting for the peers' flags -- the slowest rank's skew plus the flag round trip --, (2) the
- * rank-ordered reduce + Adam, and (3) += 1 per call: the per-phase evidence behind the scaling curve (bench.py `peer`). */
+ * rank-ordered reduce + Adam of its slice + parameter push + second arrival, (3) waiting for the peers' slices and
+ * copying them, and (4) += 1 per call: the per-phase evidence behind the scaling curve (bench.py `peer`). */
 
 /* ---- whole-model step engine --------------------------------------------------------------------------
  * SAGEDeterministic.forward (model.py:76-114) and its backward as one call each: the same kernels as above,

@@ -93,8 +93,9 @@ class FusedAdam:
 
 class PeerAdam(FusedAdam):
     """FusedAdam whose step also averages the gradient over the data-parallel ranks: ONE kernel per step
-    (csrc/peer.cu) that publishes the flat gradient in a CUDA-IPC exchange buffer, waits for the peers' flags over
-    NVLink and applies Adam to the rank-ordered sum -- no NCCL call on the step path.  ``DataParallel`` skips its own
+    (csrc/peer.cu) that publishes the flat gradient in a CUDA-IPC exchange buffer, reduces + updates ITS 1/world slice
+    of the parameters from the peers' buffers over NVLink and pushes the result to every rank (m, v are maintained
+    for the owned slice only) -- no NCCL call on the step path.  ``DataParallel`` skips its own
     all-reduce when the optimiser is a PeerAdam.  Needs one process per GPU on one node (``torch.distributed``
     initialised, used once to exchange the 64-byte IPC handles); with a single rank it degenerates to FusedAdam."""
 
@@ -110,7 +111,7 @@ class PeerAdam(FusedAdam):
         self._own = None
         self._peers = []
         self.status = torch.zeros(1, dtype=torch.int32, device=flat.flat.device)
-        self.timing = torch.zeros(4, dtype=torch.int64, device=flat.flat.device)   # ns in publish / wait / reduce, calls
+        self.timing = torch.zeros(5, dtype=torch.int64, device=flat.flat.device)   # ns publish/wait/reduce/gather, calls
         if self.world == 1:
             return
         if self.world > 8:
@@ -171,13 +172,15 @@ class PeerAdam(FusedAdam):
         ops.LAUNCHES["n"] += 1
 
     def phase_times_us(self, reset=True):
-        """Mean microseconds CTA 0 of the fused kernel spent publishing, waiting for the peers, and reducing + Adam
-        (synchronising read; the wait phase is the slowest rank's skew plus the flag round trip over NVLink)."""
+        """Mean microseconds CTA 0 of the fused kernel spent publishing, waiting for the peers' gradients, reducing +
+        Adam on its slice + pushing the parameters, and gathering the peers' slices (synchronising read; the wait phase
+        is the slowest rank's skew plus the flag round trip over NVLink)."""
         t = self.timing.cpu().tolist()
         if reset:
             self.timing.zero_()
-        n = max(t[3], 1)
-        return {"publish_us": t[0] / n / 1e3, "wait_us": t[1] / n / 1e3, "reduce_adam_us": t[2] / n / 1e3, "calls": t[3]}
+        n = max(t[4], 1)
+        return {"publish_us": t[0] / n / 1e3, "wait_us": t[1] / n / 1e3, "reduce_adam_us": t[2] / n / 1e3,
+                "gather_us": t[3] / n / 1e3, "calls": t[4]}
 
     def check(self):
         """Synchronising check of the device status word (a peer that never arrived sets PERT_ERR_PEER_TIMEOUT)."""

@@ -430,10 +430,13 @@ def test_peer_adam_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(here, "dist_peer_adam.py")],
-                       capture_output=True, text=True, timeout=300)
-    assert "PEER_ADAM_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    for k, mode in enumerate(("ag", "rs")):     # both forms of the fused kernel (csrc/peer.cu; auto picks by world size)
+        env = dict(os.environ, PERT_PEER_MODE=mode)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29541 + k),
+                            os.path.join(here, "dist_peer_adam.py")],
+                           capture_output=True, text=True, timeout=300, env=env)
+        assert "PEER_ADAM_OK" in r.stdout, (mode, r.stdout[-2000:], r.stderr[-2000:])
 
 
 def test_model_cfg1_eval():
