@@ -45,7 +45,8 @@ extern "C" {
 #define PERT_ERR_PEER_TIMEOUT (-4)
 
 /* ABI version (major*1000 + minor).  2000: pert_tconv_bwd takes rpc_ws; node_depth / eval-metric entry points.
- * 2001: pert_pert_graph_count / pert_pert_graph_build.  2002: pert_allreduce_adam timing[5], reduce-scatter form. */
+ * 2001: pert_pert_graph_count / pert_pert_graph_build.  2002: pert_allreduce_adam timing[5], reduce-scatter form.
+ * 2003: pert_span_graph_count / pert_span_graph_build. */
 int pert_version(void);
 
 /* ---- index construction (integer, bit-exact) ---------------------------------------------------
@@ -350,6 +351,16 @@ int pert_pert_graph_build(const int64_t* row_ptr, long long T, long long R, cons
                           const int64_t* t_end, const int64_t* root_ms, const int64_t* node_ptr, int max_rows,
                           int global_ids, int64_t* ms_id, int64_t* edge_index, int64_t* edge_attr, int64_t* root_nid,
                           int* status, void* stream);
+/* Span graph of T traces (misc.py:190-219 get_span_edge_index; `--graph_type span` is pert_gnn.py's default): nodes =
+ * the trace's sorted unique microservice ids (ms_id[N], N from pert_span_graph_count), edge_index[2,R] = positions of
+ * um / dm in that list (one edge per row, table order; edge slots of trace t start at row_ptr[t]), edge_attr[R,2] =
+ * [interface, rpctype], root_nid[T] as above.  Bit-identical to the reference's tensors. */
+int pert_span_graph_count(const int64_t* row_ptr, long long T, const int64_t* um, const int64_t* dm, int max_rows,
+                          int64_t* node_cnt, int* status, void* stream);
+int pert_span_graph_build(const int64_t* row_ptr, long long T, long long R, const int64_t* um, const int64_t* dm,
+                          const int64_t* interface, const int64_t* rpctype, const int64_t* root_ms,
+                          const int64_t* node_ptr, int max_rows, int global_ids, int64_t* ms_id, int64_t* edge_index,
+                          int64_t* edge_attr, int64_t* root_nid, int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@ For every table of synthetic.make_span_tables(SEED) it builds the DataFrame prep
 from /root/reference/misc.py itself:
   GraphConstruct.__init__  -> get_root_spanID (:138-142) and drop_wrong_edges (:87-105)
   get_pert_edge_index      -> edge_index, edge_attr, node_depth, sorted_span_id          (:221-370)
+  get_span_edge_index      -> edge_index, node_depth, edge_attr, sorted_unique_ms        (:190-219)
 Stored per trace t: the surviving row indices (`t{t}_keep`), the root (`t{t}_root`) and the four outputs.  The raw
 tables are regenerated from the seed by the tests (synthetic.make_span_tables is deterministic).
 Usage:  python oracle/gen_golden_pert.py
@@ -23,7 +24,8 @@ from pert_gnn_kdd23_b200.synthetic import make_span_tables  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "ref_pert.npz")
 SEED, N_TRACES = 11, 24
-COLS = ("timestamp", "rpcid", "um", "rpctype", "dm", "interface", "rt", "endTimestamp")
+COLS = ("timestamp", "rpcid", "um", "interface", "dm", "rpctype", "rt", "endTimestamp")   # interface before rpctype:
+# misc.py:178 takes .loc[:, ["interface", "rpctype"]].values of a single-dtype frame (a negative-stride view otherwise)
 
 
 def load_reference_misc():
@@ -53,6 +55,12 @@ def main():
         out[f"t{t}_edge_attr"] = ea.numpy()
         out[f"t{t}_node_depth"] = nd.numpy()
         out[f"t{t}_ms_id"] = np.asarray(span, dtype=np.int64)
+        gs = misc.GraphConstruct(df, resource_df, np.arange(n_ms))
+        sei, _sx, snd, sea, _sdur, sms = gs.get_span_edge_index()
+        out[f"t{t}_span_edge_index"] = sei.numpy()
+        out[f"t{t}_span_edge_attr"] = sea.numpy()
+        out[f"t{t}_span_node_depth"] = snd.numpy()
+        out[f"t{t}_span_ms_id"] = np.asarray(sms, dtype=np.int64)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(tables), "traces")
 

@@ -4,6 +4,7 @@ pert_gnn_kdd23_b200/ imports this file.
 Restates, in plain Python loops (small cases only):
   get_root_ms        <- /root/reference/misc.py:138-142  (GraphConstruct.get_root_spanID)
   drop_wrong_edges   <- misc.py:87-105
+  span_graph         <- misc.py:190-219 (get_span_edge_index)
   pert_graph         <- misc.py:221-319 (get_pert_edge_index: stage chains, call / return edges in time order)
                         + :113-136,159-175 (min DFS depth -> the long-cast node_depth tensor)
   canonical_form     -- relabelling-invariant description of a PERT graph, used to compare with the reference's own
@@ -91,6 +92,20 @@ def pert_graph(um, dm, interface, rpctype, t_start, t_end, root):
     root_nid = stages[int(root)][0]                                     # :308
     depth = node_depth_tensor(dfs_min_depth(ei, n, root_nid))           # :159-175 + long cast :368
     return np.array(ms_id, dtype=np.int64), ei, ea, depth, root_nid
+
+
+def span_graph(um, dm, interface, rpctype, root):
+    """misc.py:190-219 get_span_edge_index (+ depth :113-175): torch.unique(sorted=True, return_inverse=True) over the
+    [2, r] um/dm matrix.  -> ms_id [n], edge_index [2,r], edge_attr [r,2], node_depth [n,1], root_nid.  Fully
+    specified by the reference, so this is compared bit for bit."""
+    both = np.stack([np.asarray(um, dtype=np.int64), np.asarray(dm, dtype=np.int64)])
+    ms_id, inv = np.unique(both.reshape(-1), return_inverse=True)
+    ei = inv.reshape(2, -1).astype(np.int64)
+    root_nid = int(np.searchsorted(ms_id, root))
+    assert ms_id[root_nid] == root
+    ea = np.stack([np.asarray(interface, dtype=np.int64), np.asarray(rpctype, dtype=np.int64)], axis=1)
+    depth = node_depth_tensor(dfs_min_depth(ei, len(ms_id), root_nid))
+    return ms_id.astype(np.int64), ei, ea, depth, root_nid
 
 
 def canonical_form(ms_id, edge_index, edge_attr, node_depth):

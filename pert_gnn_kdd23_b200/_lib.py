@@ -58,6 +58,8 @@ SIGNATURES = {
     # PERT-graph construction (pertgraph.py)
     "pert_pert_graph_count": (I, [P, LL, P, P, I, P, P, P]),
     "pert_pert_graph_build": (I, [P, LL, LL, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
+    "pert_span_graph_count": (I, [P, LL, P, P, I, P, P, P]),
+    "pert_span_graph_build": (I, [P, LL, LL, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
     # whole-model engine (first argument: const PertModelDesc*, see engine.py)
     "pert_model_workspace_bytes": (LL, [P, LL, LL, LL]),
     "pert_model_packed_bytes": (LL, [P]),

@@ -1,4 +1,8 @@
-// PERT-graph construction on the GPU.
+// PERT-graph and span-graph construction on the GPU.
+//
+// Span graph (misc.py:190-219, the `--graph_type span` default of pert_gnn.py:32): nodes = sorted unique microservice
+// ids (torch.unique(sorted=True, return_inverse=True)), one edge per span row in table order, edge_attr =
+// [interface, rpctype]; fully specified, so the device result equals the reference's tensors bit for bit.
 //
 // The reference builds one PERT graph per runtime pattern on the host with pandas row loops
 // (misc.py:221-319, GraphConstruct.get_pert_edge_index):
@@ -33,7 +37,7 @@ struct PgArgs {
   int64_t* edge_attr;       // [4R, 4]
   int64_t* root_nid;        // [T] global node id
   long long R;              // total rows (edge_index row stride = 4R)
-  int max_rows, global_ids;
+  int max_rows, global_ids, span;
   int* status;
 };
 
@@ -43,8 +47,10 @@ __host__ __device__ inline size_t pg_smem_bytes(int mr) {
 }
 
 #pragma nv_diag_suppress 128   // the count instantiation returns before the build half
-template <bool BUILD>
+// MODE 0: node counts (PERT: 2 rows + distinct ids; span: distinct ids)   1: PERT graph   2: span graph
+template <int MODE>
 __global__ void __launch_bounds__(256) k_pert_graph(PgArgs a) {
+  constexpr bool BUILD = MODE != 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int t = blockIdx.x;
   const long long r0 = a.row_ptr[t];
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(256) k_pert_graph(PgArgs a) {
   __syncthreads();
   const int D = D_s;
   if (!BUILD) {
-    if (threadIdx.x == 0) a.node_cnt[t] = 2LL * r + D;
+    if (threadIdx.x == 0) a.node_cnt[t] = a.span ? (long long)D : 2LL * r + D;
     return;
   }
   for (int i = threadIdx.x; i < m2; i += blockDim.x) {
@@ -112,6 +118,34 @@ __global__ void __launch_bounds__(256) k_pert_graph(PgArgs a) {
     }
   }
   __syncthreads();
+  if (MODE == 2) {
+    // span graph (misc.py:190-219): nodes = sorted unique ids (torch.unique), one edge per row in table order
+    const long long n0 = a.node_ptr[t];
+    const long long goff = a.global_ids ? n0 : 0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) a.ms_id[n0 + d] = u[d];
+    for (int i = threadIdx.x; i < r; i += blockDim.x) {
+      const long long e = r0 + i;
+      a.edge_index[e] = goff + ui[i];
+      a.edge_index[a.R + e] = goff + di[i];
+      reinterpret_cast<longlong2*>(a.edge_attr)[e] = make_longlong2(a.itf[r0 + i], a.rpc[r0 + i]);
+    }
+    if (threadIdx.x == 0) {
+      const int64_t rm = a.root_ms[t];
+      int lo = 0, hi = D - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (u[mid] < rm) lo = mid + 1;
+        else hi = mid;
+      }
+      if (D > 0 && u[lo] == rm) {
+        a.root_nid[t] = n0 + lo;
+      } else {
+        a.root_nid[t] = -1;
+        if (a.status) atomicExch(a.status, PERT_ERR_RANGE);
+      }
+    }
+    return;
+  }
   // block placement: callers by (count desc, id asc), then leaves by id asc.  u is ascending, so id order = index order.
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const int c = cnt[d];
@@ -190,11 +224,11 @@ __global__ void __launch_bounds__(256) k_pert_graph(PgArgs a) {
   }
 }
 
-int pg_launch(bool build, const PgArgs& a, long long T, cudaStream_t st) {
+int pg_launch(int mode, const PgArgs& a, long long T, cudaStream_t st) {
   if (T <= 0) return 0;
   if (a.max_rows <= 0 || a.max_rows > PERT_PERT_GRAPH_MAX_ROWS) return PERT_ERR_UNSUPPORTED;
   const size_t smem = pg_smem_bytes(a.max_rows);
-  auto fn = build ? k_pert_graph<true> : k_pert_graph<false>;
+  auto fn = mode == 0 ? k_pert_graph<0> : (mode == 1 ? k_pert_graph<1> : k_pert_graph<2>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -204,10 +238,8 @@ int pg_launch(bool build, const PgArgs& a, long long T, cudaStream_t st) {
   return 0;
 }
 
-}  // namespace
-
-extern "C" int pert_pert_graph_count(const int64_t* row_ptr, long long T, const int64_t* um, const int64_t* dm,
-                                     int max_rows, int64_t* node_cnt, int* status, void* stream) {
+int pg_count(int span, const int64_t* row_ptr, long long T, const int64_t* um, const int64_t* dm, int max_rows,
+             int64_t* node_cnt, int* status, void* stream) {
   if (!row_ptr || !um || !dm || !node_cnt || T < 0) return PERT_ERR_BADARG;
   PgArgs a{};
   a.row_ptr = row_ptr;
@@ -215,8 +247,20 @@ extern "C" int pert_pert_graph_count(const int64_t* row_ptr, long long T, const 
   a.dm = dm;
   a.node_cnt = node_cnt;
   a.max_rows = max_rows;
+  a.span = span;
   a.status = status;
-  return pg_launch(false, a, T, (cudaStream_t)stream);
+  return pg_launch(0, a, T, (cudaStream_t)stream);
+}
+
+}  // namespace
+
+extern "C" int pert_pert_graph_count(const int64_t* row_ptr, long long T, const int64_t* um, const int64_t* dm,
+                                     int max_rows, int64_t* node_cnt, int* status, void* stream) {
+  return pg_count(0, row_ptr, T, um, dm, max_rows, node_cnt, status, stream);
+}
+extern "C" int pert_span_graph_count(const int64_t* row_ptr, long long T, const int64_t* um, const int64_t* dm,
+                                     int max_rows, int64_t* node_cnt, int* status, void* stream) {
+  return pg_count(1, row_ptr, T, um, dm, max_rows, node_cnt, status, stream);
 }
 
 extern "C" int pert_pert_graph_build(const int64_t* row_ptr, long long T, long long R, const int64_t* um,
@@ -246,5 +290,33 @@ extern "C" int pert_pert_graph_build(const int64_t* row_ptr, long long T, long l
   a.max_rows = max_rows;
   a.global_ids = global_ids;
   a.status = status;
-  return pg_launch(true, a, T, (cudaStream_t)stream);
+  return pg_launch(1, a, T, (cudaStream_t)stream);
+}
+
+extern "C" int pert_span_graph_build(const int64_t* row_ptr, long long T, long long R, const int64_t* um,
+                                     const int64_t* dm, const int64_t* interface, const int64_t* rpctype,
+                                     const int64_t* root_ms, const int64_t* node_ptr, int max_rows, int global_ids,
+                                     int64_t* ms_id, int64_t* edge_index, int64_t* edge_attr, int64_t* root_nid,
+                                     int* status, void* stream) {
+  if (!row_ptr || !um || !dm || !interface || !rpctype || !root_ms || !node_ptr || !ms_id || !edge_index ||
+      !edge_attr || !root_nid || T < 0 || R < 0)
+    return PERT_ERR_BADARG;
+  PgArgs a{};
+  a.row_ptr = row_ptr;
+  a.um = um;
+  a.dm = dm;
+  a.itf = interface;
+  a.rpc = rpctype;
+  a.root_ms = root_ms;
+  a.node_ptr = node_ptr;
+  a.ms_id = ms_id;
+  a.edge_index = edge_index;
+  a.edge_attr = edge_attr;
+  a.root_nid = root_nid;
+  a.R = R;
+  a.max_rows = max_rows;
+  a.global_ids = global_ids;
+  a.span = 1;
+  a.status = status;
+  return pg_launch(2, a, T, (cudaStream_t)stream);
 }

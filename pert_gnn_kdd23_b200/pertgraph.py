@@ -3,6 +3,7 @@ the reference stores in ``runtime2pertgraph_map`` (preprocess.py:350-371), built
 
 Reference: /root/reference/misc.py ``GraphConstruct``
   ``get_root_ms`` / ``drop_wrong_edges``  (misc.py:138-142 / :87-105)  row filters; host numpy, as in the reference
+  ``build_span_graphs``                   (misc.py:190-219 + :113-175) CUDA: sorted unique ids + one edge per row
   ``build_pert_graphs``                   (misc.py:221-319 + :113-175) CUDA: csrc/pertgraph.cu builds the stage chains
       and the call / return edges of every trace (one CTA each); the level index (csrc/index.cu pert_min_depth /
       pert_node_depth) gives ``node_depth``.
@@ -83,7 +84,14 @@ class PertGraphs:
                 "node_depth": self.node_depth[n0:n1]}
 
 
-def build_pert_graphs(tables, roots, device="cuda"):
+def build_span_graphs(tables, roots, device="cuda"):
+    """Span graphs (misc.py:190-219; ``--graph_type span``): like ``build_pert_graphs``; ``pattern(t)`` is the dict
+    preprocess.py:333-340 stores (edge_attr has the two columns [interface, rpctype]).  Bit-identical to the
+    reference's tensors."""
+    return build_pert_graphs(tables, roots, device, kind="span")
+
+
+def build_pert_graphs(tables, roots, device="cuda", kind="pert"):
     """``tables``: per trace a dict of the CLEANED span rows (COLUMNS, int64 array-likes); ``roots``: root
     microservice per trace.  Concatenates on the host and calls ``build_pert_graphs_flat``."""
     T = len(tables)
@@ -95,14 +103,16 @@ def build_pert_graphs(tables, roots, device="cuda"):
     host = np.empty((len(COLUMNS), R), dtype=np.int64)
     for c, name in enumerate(COLUMNS):
         host[c] = np.concatenate([np.asarray(t[name], dtype=np.int64).reshape(-1) for t in tables])
-    return build_pert_graphs_flat(host, row_ptr, roots, device)
+    return build_pert_graphs_flat(host, row_ptr, roots, device, kind)
 
 
-def build_pert_graphs_flat(columns, row_ptr, roots, device="cuda"):
+def build_pert_graphs_flat(columns, row_ptr, roots, device="cuda", kind="pert"):
     """``columns``: int64 [6, R] (rows of COLUMNS, all traces concatenated -- a span table grouped by trace id, host
     array or CUDA tensor); ``row_ptr``: int64 [T+1] host array; ``roots``: [T].  One H2D copy of the rows, two kernel
     launches for the graphs, the level index for ``node_depth``; the only synchronisation is reading the node total
-    to size the outputs."""
+    to size the outputs.  ``kind``: "pert" (misc.py:221-319) or "span" (misc.py:190-219)."""
+    assert kind in ("pert", "span")
+    span = kind == "span"
     dev = torch.device(device)
     if dev.type != "cuda":
         raise _lib.PertGnnError("build_pert_graphs needs a CUDA device (no CPU fallback)")
@@ -123,24 +133,30 @@ def build_pert_graphs_flat(columns, row_ptr, roots, device="cuda"):
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         cnt = torch.empty(T, dtype=torch.int64, device=dev)
         st = _lib.stream()
-        _lib.call("pert_pert_graph_count", _lib.ptr(rp), T, _lib.ptr(cols[0]), _lib.ptr(cols[1]), max_rows,
-                  _lib.ptr(cnt), _lib.ptr(status), st)
+        _lib.call("pert_span_graph_count" if span else "pert_pert_graph_count", _lib.ptr(rp), T, _lib.ptr(cols[0]),
+                  _lib.ptr(cols[1]), max_rows, _lib.ptr(cnt), _lib.ptr(status), st)
         node_ptr = torch.zeros(T + 1, dtype=torch.int64, device=dev)
         torch.cumsum(cnt, 0, out=node_ptr[1:])
         node_ptr_h = node_ptr.cpu().numpy()                       # sizes the outputs (the one sync)
-        N, E = int(node_ptr_h[-1]), 4 * R
+        epr = 1 if span else 4                                    # edges per span row
+        N, E = int(node_ptr_h[-1]), epr * R
         ms_id = torch.empty(N, dtype=torch.int64, device=dev)
         ei = torch.empty(2, E, dtype=torch.int64, device=dev)
-        ea = torch.empty(E, 4, dtype=torch.int64, device=dev)
+        ea = torch.empty(E, 2 if span else 4, dtype=torch.int64, device=dev)
         root_nid = torch.empty(T, dtype=torch.int64, device=dev)
-        _lib.call("pert_pert_graph_build", _lib.ptr(rp), T, R, *(_lib.ptr(cols[c]) for c in range(6)), _lib.ptr(rm),
-                  _lib.ptr(node_ptr), max_rows, 1, _lib.ptr(ms_id), _lib.ptr(ei), _lib.ptr(ea), _lib.ptr(root_nid),
-                  _lib.ptr(status), st)
+        if span:
+            _lib.call("pert_span_graph_build", _lib.ptr(rp), T, R, *(_lib.ptr(cols[c]) for c in range(4)),
+                      _lib.ptr(rm), _lib.ptr(node_ptr), max_rows, 1, _lib.ptr(ms_id), _lib.ptr(ei), _lib.ptr(ea),
+                      _lib.ptr(root_nid), _lib.ptr(status), st)
+        else:
+            _lib.call("pert_pert_graph_build", _lib.ptr(rp), T, R, *(_lib.ptr(cols[c]) for c in range(6)),
+                      _lib.ptr(rm), _lib.ptr(node_ptr), max_rows, 1, _lib.ptr(ms_id), _lib.ptr(ei), _lib.ptr(ea),
+                      _lib.ptr(root_nid), _lib.ptr(status), st)
         # level index over the whole batch of graphs (global ids), then back to trace-local ids
         gi = _index.build_index(ei, N)
         gptr = node_ptr.to(torch.int32)
         depth = _index.min_depth(gptr, gi, root_nid.clamp_min(0).to(torch.int32))
         node_depth = _index.node_depth(gptr, depth)
-        off = torch.repeat_interleave(node_ptr[:-1], torch.from_numpy(4 * rows).to(dev), output_size=E)
+        off = torch.repeat_interleave(node_ptr[:-1], torch.from_numpy(epr * rows).to(dev), output_size=E)
         ei -= off
-    return PertGraphs(node_ptr_h, 4 * row_ptr, ms_id, ei, ea, node_depth, root_nid, status)
+    return PertGraphs(node_ptr_h, epr * row_ptr, ms_id, ei, ea, node_depth, root_nid, status)

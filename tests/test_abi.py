@@ -32,7 +32,7 @@ def test_version_and_host_side_validation():
     from pert_gnn_kdd23_b200 import _lib
 
     L = _lib.lib()
-    assert L.pert_version() >= 2002
+    assert L.pert_version() >= 2003
     assert L.pert_index_workspace_bytes(10, 20) > 0
     assert L.pert_index_workspace_bytes(-1, 0) == -1
     assert L.pert_tconv_supported_width(64) == 1 and L.pert_tconv_supported_width(65) == 0

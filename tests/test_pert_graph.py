@@ -1,7 +1,8 @@
 """PERT-graph construction against the REFERENCE'S OWN GraphConstruct.
 
 tests/golden/ref_pert.npz holds what /root/reference/misc.py returned on synthetic.make_span_tables(11)
-(oracle/gen_golden_pert.py): surviving rows, root, edge_index, edge_attr, node_depth, sorted_span_id per trace.
+(oracle/gen_golden_pert.py): surviving rows, root, and per trace the PERT graph (edge_index, edge_attr, node_depth,
+sorted_span_id) and the span graph (`--graph_type span`: edge_index, edge_attr, node_depth, sorted_unique_ms).
 CPU tests pin the oracle restatement and the host row filters to it; the gpu tests compare the CUDA builder
 bit for bit with the oracle (same canonical node numbering) and, up to relabelling, with the reference outputs."""
 import os
@@ -47,6 +48,17 @@ def test_oracle_matches_reference_graphconstruct():
         assert O.canonical_form(ms, ei, ea, nd) == ref, t
         assert nd.dtype == g[f"t{t}_node_depth"].dtype and nd.shape == g[f"t{t}_node_depth"].shape
     assert anomalies > 20          # the row filters are really exercised
+
+
+def test_span_oracle_matches_reference_bit_for_bit():
+    """misc.py:190-219 is fully specified (torch.unique sorted): the oracle equals the reference's tensors exactly."""
+    g, tabs = _gold()
+    for t, tab in enumerate(tabs):
+        c = _cleaned(tab, g[f"t{t}_keep"])
+        ms, ei, ea, nd, _ = O.span_graph(c["um"], c["dm"], c["interface"], c["rpctype"], int(g[f"t{t}_root"]))
+        for k, v in (("ms_id", ms), ("edge_index", ei), ("edge_attr", ea), ("node_depth", nd)):
+            w = g[f"t{t}_span_{k}"]
+            assert v.dtype == w.dtype and np.array_equal(v, w), (t, k)
 
 
 def test_host_row_filters_match_reference():
@@ -111,6 +123,41 @@ def test_cuda_pert_graphs_match_reference_and_oracle():
         p = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in pg.pattern(t).items()}
         ref = O.canonical_form(g[f"t{t}_ms_id"], g[f"t{t}_edge_index"], g[f"t{t}_edge_attr"], g[f"t{t}_node_depth"])
         assert O.canonical_form(p["ms_id"], p["edge_index"], p["edge_attr"], p["node_depth"]) == ref, t
+
+
+@pytest.mark.gpu
+def test_cuda_span_graphs_equal_reference_tensors():
+    """`--graph_type span` (pert_gnn.py:32 default): the CUDA builder reproduces the reference's own tensors exactly."""
+    from pert_gnn_kdd23_b200 import pertgraph
+
+    g, tabs = _gold()
+    cleaned = [_cleaned(tab, g[f"t{t}_keep"]) for t, tab in enumerate(tabs)]
+    roots = [int(g[f"t{t}_root"]) for t in range(len(tabs))]
+    sg = pertgraph.build_span_graphs(cleaned, roots, "cuda").check()
+    for t in range(len(tabs)):
+        p = sg.pattern(t)
+        assert p["num_nodes"] == int(g[f"t{t}_span_edge_index"].max()) + 1      # preprocess.py:332
+        for k in ("ms_id", "edge_index", "edge_attr", "node_depth"):
+            got, want = p[k].cpu().numpy(), g[f"t{t}_span_{k}"]
+            if k == "ms_id":
+                got = got.reshape(-1)
+            assert got.dtype == want.dtype and np.array_equal(got, want), (t, k)
+    # ragged, long traces against the oracle
+    tables, rts = [], []
+    for seed, calls, nms in ((31, (1, 3), 10), (32, (300, 800), 300)):
+        for tab in make_span_tables(seed, 5, n_ms=nms, calls=calls):
+            root = pertgraph.get_root_ms(tab)
+            keep = pertgraph.drop_wrong_edges(tab, root)
+            if len(keep):
+                tables.append(_cleaned(tab, keep))
+                rts.append(root)
+    sg = pertgraph.build_span_graphs(tables, rts, "cuda").check()
+    for t, (c, root) in enumerate(zip(tables, rts)):
+        ms, ei, ea, nd, rn = O.span_graph(c["um"], c["dm"], c["interface"], c["rpctype"], root)
+        p = sg.pattern(t)
+        assert np.array_equal(p["ms_id"].cpu().numpy().reshape(-1), ms) and np.array_equal(p["edge_index"].cpu().numpy(), ei)
+        assert np.array_equal(p["edge_attr"].cpu().numpy(), ea) and np.array_equal(p["node_depth"].cpu().numpy(), nd)
+        assert int(sg.root_nid[t]) - int(sg.node_ptr[t]) == rn
 
 
 @pytest.mark.gpu
