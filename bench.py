@@ -26,6 +26,8 @@ Arms and JSON keys beyond the base contract:
   cpu_baseline  the oracle (torch restatement of the reference's PyG 2.4.0 ops) on this box's host cores, thread
                 count chosen by a calibration sweep
   clocks        NVML SM clock / throttle reasons sampled inside the timed region
+  pert_pipeline (N = 1) span rows -> PERT graphs on the GPU -> resident pattern store -> device-side batch assembly ->
+                train step: graph-build rate, DAGs/s from trace ids, DAGs/s of the step on PERT-shaped batches
 """
 import argparse
 import json
@@ -619,6 +621,12 @@ def run_b200(args, rank, world, local_rank):
     # ---- BASELINE.json configs[3] (4096 graphs over 8 GPUs = 512 graphs / GPU, 128-dim, 3 layers) beside the headline
     cfg4 = run_cfg4_block(args, rank, world, dev, barrier, make_optimizer) if (args.cfg == 2 and not args.no_cfg4) else None
     cfg2j = run_jitter_block(args, rank, world, dev, barrier, make_optimizer) if (args.cfg == 2 and not args.no_cfg4) else None
+    pert_pipe = None
+    if args.cfg == 2 and not args.no_cfg4 and world == 1:
+        try:
+            pert_pipe = run_pert_pipeline_block(args, dev, barrier)
+        except Exception as e:  # noqa: BLE001 -- a supplementary block must not take the headline line down
+            pert_pipe = {"error": repr(e)[:300]}
 
     if hasattr(opt, "check"):
         opt.check()
@@ -693,7 +701,7 @@ def run_b200(args, rank, world, local_rank):
                             "launch list mirrored from csrc/engine.cu + index build + loss + Adam) x steps of one block; "
                             "cross-check: profiles/r2_launches_step.csv (ncu launch list of the same command)",
         "wall_s": t_wall, "clocks": clocks, "final_loss": float(loss), "parity_first_step": parity,
-        "peer": peer_phases, "cfg4": cfg4, "cfg2_jittered": cfg2j,
+        "peer": peer_phases, "cfg4": cfg4, "cfg2_jittered": cfg2j, "pert_pipeline": pert_pipe,
     }
     print(json.dumps(line), flush=True)
 
@@ -760,6 +768,71 @@ def run_jitter_block(args, rank, world, dev, barrier, make_optimizer):
     return run_extra_block(args, rank, world, dev, barrier, make_optimizer, 2, 256, 0.2,
                            "cfg2j: 256 DAGs x 200 +- 20 % nodes (3 edges per node) per GPU, 64-dim, num_layers=3, "
                            "fwd+bwd+Adam, resident batches, graph replay")
+
+
+def run_pert_pipeline_block(args, dev, barrier):
+    """SURVEY rows N2 + N1 + N4 in front of the train step, all on the GPU: span rows -> PERT graphs
+    (pertgraph.build_pert_graphs) -> resident pattern store -> batches of 256 traces assembled on the device
+    (store.StoreLoader: sample assembly incl. the (timestamp, ms) feature join + collation) -> fused train step.
+    `from_trace_ids`: every step assembles its batch from 256 trace ids (2 KB of H2D) and trains on it;
+    `resident_graph_replay`: the train step alone on assembled PERT-shaped batches (comparable with `value`)."""
+    from pert_gnn_kdd23_b200.model import SAGEDeterministic
+    from pert_gnn_kdd23_b200.store import PatternStore, StoreLoader
+    from pert_gnn_kdd23_b200.synthetic import make_pert_artifacts, model_args
+    from pert_gnn_kdd23_b200.train import FlatParams, FusedAdam, GraphedTrainStep, fused_train_step
+
+    art, info = make_pert_artifacts(seed=3, n_patterns=256, n_entries=64, n_traces=4096, device=dev)
+    art2, info2 = make_pert_artifacts(seed=3, n_patterns=256, n_entries=64, n_traces=4096, device=dev)   # warm timing
+    store = PatternStore.from_artifacts(art, dev)
+    B = 256
+    ids = list(range(len(store)))
+    torch.manual_seed(0)
+    model = SAGEDeterministic(*model_args(2)).to(dev)
+    opt = FusedAdam(FlatParams(model), lr=1e-3)
+    loader = StoreLoader(store, ids, batch_size=B)
+    nb = len(loader)
+
+    def epoch_block(k):                         # k steps, each: assemble 256 traces on the device + train
+        done = 0
+        while done < k:
+            for batch in loader:
+                fused_train_step(model, opt, batch, 0.5)
+                done += 1
+                if done == k:
+                    break
+
+    epoch_block(5)
+    barrier()
+    K = max(5, min(args.steps, 20))
+    secs, blocks = timed_blocks(epoch_block, K, barrier, 1, dev, min_region_s=0.3, max_blocks=40)
+    store.check()
+    res = [store.assemble(ids[i * B:(i + 1) * B]) for i in range(3)]
+    gstep = GraphedTrainStep(model, opt, 0.5, None)
+    st = {"i": 0}
+
+    def block(k):
+        for _ in range(k):
+            gstep(res[st["i"] % 3])
+            st["i"] += 1
+
+    block(7)
+    barrier()
+    secs2, blocks2 = timed_blocks(block, K, barrier, 1, dev, min_region_s=0.3, max_blocks=40)
+    Nn, Ee = int(res[0].x.size(0)), int(res[0].edge_index.size(1))
+    return {"workload": f"PERT-exact synthetic: {B} traces per step, one PERT graph each (60-72 calls: nodes = 2 calls + "
+                        "distinct ms, edges = 4 calls), 64-dim, num_layers=3, fwd+bwd+Adam",
+            "graph_build": {"patterns": info2["patterns"], "span_rows": info2["span_rows"], "pert_nodes": info2["nodes"],
+                            "pert_edges": info2["edges"], "ms": 1e3 * info2["build_s"],
+                            "patterns_per_s": info2["patterns"] / info2["build_s"],
+                            "what": "host span rows -> H2D -> count + build kernels -> level index -> node_depth"},
+            "from_trace_ids": {"value": B * K / secs, "unit": "DAGs/s", "ms_per_step": 1e3 * secs / K,
+                               "h2d_bytes_per_step": 8 * B, "blocks": len(blocks),
+                               "what": "device-side sample assembly + collation from the resident store, then the eager "
+                                       "fused train step"},
+            "resident_graph_replay": {"value": B * K / secs2, "unit": "DAGs/s", "ms_per_step": 1e3 * secs2 / K,
+                                      "blocks": len(blocks2), "replays": gstep.replays,
+                                      "capture_error": gstep.capture_error},
+            "nodes_per_batch": Nn, "edges_per_batch": Ee, "store_resident_bytes": store.resident_bytes}
 
 
 def main():

@@ -31,16 +31,33 @@ __global__ void k_embedding_fwd(const float* __restrict__ table, int n_rows, con
 }
 
 // dtable[ids[n*id_stride], :] += dy[n, 0:H]      (REDG.128; nn.Embedding dense backward)
+// One thread owns one float4 column of EB_RUN consecutive rows and merges equal ids before the atomic: the stage nodes
+// of a microservice are consecutive in a PERT graph (misc.py:238-250: 2c+1 nodes per caller share cat_X), so real
+// batches send runs of rows to the same table row.
+constexpr int EB_RUN = 8;
 __global__ void k_embedding_bwd(const float* __restrict__ dy, int ld_dy, const int64_t* __restrict__ ids,
                                 int id_stride, float* __restrict__ dtable, int n_rows, long long N, int H) {
   const int vec_per_row = H >> 2;
-  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= N * vec_per_row) return;
-  long long n = id / vec_per_row;
-  int c = (int)(id % vec_per_row) * 4;
-  int64_t r = ids[n * id_stride];
-  if (r < 0 || r >= n_rows) return;
-  red4(dtable + (size_t)r * H + c, ldg4(dy + (size_t)n * ld_dy + c));
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long chunks = (N + EB_RUN - 1) / EB_RUN;
+  if (id >= chunks * vec_per_row) return;
+  const long long n0 = (id / vec_per_row) * EB_RUN;
+  const int c = (int)(id % vec_per_row) * 4;
+  int64_t cur = -1;
+  float4 acc = f4zero();
+#pragma unroll
+  for (int k = 0; k < EB_RUN; ++k) {
+    const long long n = n0 + k;
+    if (n >= N) break;
+    const int64_t r = ids[n * id_stride];
+    if (r != cur) {
+      if (cur >= 0 && cur < n_rows) red4(dtable + (size_t)cur * H + c, acc);
+      cur = r;
+      acc = f4zero();
+    }
+    acc = f4add(acc, ldg4(dy + (size_t)n * ld_dy + c));
+  }
+  if (cur >= 0 && cur < n_rows) red4(dtable + (size_t)cur * H + c, acc);
 }
 
 // out[n, col0 : col0+F] = x[n, 0:F]; out[n, col0+F : ld_out) = 0
@@ -528,7 +545,7 @@ int pert_embedding_bwd(const float* dy, int ld_dy, const int64_t* ids, int id_st
                        long long N, int H, void* stream) {
   if (N < 0 || H <= 0 || H % 4 || ld_dy % 4 || !dy || !dtable || !al16(dy) || !al16(dtable)) return PERT_ERR_BADARG;
   if (N == 0) return PERT_OK;
-  long long total = N * (H / 4);
+  long long total = ((N + EB_RUN - 1) / EB_RUN) * (H / 4);
   k_embedding_bwd<<<pert_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, ld_dy, ids, id_stride, dtable,
                                                                          n_rows, N, H);
   PERT_LAUNCH_CHECK();

@@ -74,6 +74,7 @@ struct TileArgs {
   double* bn_acc;   // fwd: optional [2][H] column sums / sums of squares of `out` (BatchNorm statistics), +=
   float* rpc_ws;    // [N][2][RPC_FAST] per-target sums over in-edges of (alpha, ds) by rpc type, or null (see bwd_src)
   int N, tile_nodes, edge_cap;
+  int hot_if;          // interface id whose table-gradient row is accumulated per CTA instead of per edge (source pass)
   float inv_sqrt_c;
   // graph-aligned tile list (csrc: k_build_tiles): tile t = nodes [tile_ptr[t], tile_ptr[t+1]); null = fixed tiles of
   // tile_nodes nodes, one per CTA.  CTAs draw tiles from `ticket` (self-resetting counter) until it exceeds *ntiles.
@@ -623,6 +624,14 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) k_tile_bwd_src(TileArg
   float* s_drpc = S.rpc;   // privatised gradient of the rpc-type table (few hot rows), flushed once per CTA
   if (HAS_E)
     for (int x = tid; x < a.n_rpc * H; x += NT) s_drpc[x] = 0.f;
+  // Interface id `hot_if` (0: what the reference writes on every chain and return edge of a PERT graph, misc.py:247,289,
+  // i.e. 3 of 4 edges of real data) would serialise tens of thousands of REDG.128 on ONE 4H-byte row per layer (measured:
+  // a PERT-shaped batch ran 2x slower than a random one with twice the edges).  Its contributions stay in registers
+  // and leave once per CTA (through the first row of tile A, which is dead after the tile loop: the geometry of cfg2
+  // fits its 200-node graphs into a two-CTA tile with less than 256 bytes to spare).
+  float4 hot[VPL];
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) hot[u] = f4zero();
   tile_barrier_init(S, tid);
   uint32_t phase = 0;
   int n0, nt;
@@ -659,6 +668,7 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) k_tile_bwd_src(TileArg
       float4 dk[VPL], dv[VPL];
 #pragma unroll
       for (int u = 0; u < VPL; ++u) dk[u] = dv[u] = f4zero();
+#pragma unroll 2
       for (int t = 0; t < degmax; ++t) {
         const bool on = t < deg;
         const int c = c0 + t;
@@ -690,7 +700,8 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) k_tile_bwd_src(TileArg
           dv[u] = f4fma(al, gi, dv[u]);
           if (HAS_E && on) {
             const float4 de = f4fma(ds, qi, f4scale(al, gi));
-            red4(a.dt_if + (size_t)ID_IF(id) * H + (lig + u * LPR) * 4, de);
+            if (ID_IF(id) == a.hot_if) hot[u] = f4add(hot[u], de);
+            else red4(a.dt_if + (size_t)ID_IF(id) * H + (lig + u * LPR) * 4, de);
             if (!a.rpc_ws) {                 // general path (n_rpc > RPC_FAST): privatised table, per-edge atomics
               float* prp = s_drpc + ID_RPC(id) * H + (lig + u * LPR) * 4;
               atomicAdd(prp + 0, de.x);
@@ -735,10 +746,26 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) k_tile_bwd_src(TileArg
   }
   }   // tile loop
   if (HAS_E) {
+    __syncthreads();                       // every warp is done with the staged tiles
+    float* s_hot = S.ta;
+    for (int x = tid; x < H; x += NT) s_hot[x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) {
+      float* hp = s_hot + (lig + u * LPR) * 4;
+      if (hot[u].x != 0.f) atomicAdd(hp + 0, hot[u].x);
+      if (hot[u].y != 0.f) atomicAdd(hp + 1, hot[u].y);
+      if (hot[u].z != 0.f) atomicAdd(hp + 2, hot[u].z);
+      if (hot[u].w != 0.f) atomicAdd(hp + 3, hot[u].w);
+    }
     __syncthreads();
     for (int x = tid; x < a.n_rpc * H; x += NT) {
       const float v = s_drpc[x];
       if (v != 0.f) atomicAdd(a.dt_rpc + x, v);
+    }
+    for (int x = tid; x < H; x += NT) {
+      const float v = s_hot[x];
+      if (v != 0.f) atomicAdd(a.dt_if + (size_t)a.hot_if * H + x, v);
     }
   }
 }
@@ -1000,7 +1027,7 @@ int pert_tile_bwd(const float* g_, int ld_g, const float* q, const float* k, con
   a.colptr = colptr; a.csc_pos = csc_pos; a.csc_dst = csc_dst;
   a.t_if = t_if; a.t_rpc = t_rpc; a.n_rpc = n_rpc;
   a.out = dq; a.dk = dk; a.dv = dv; a.alpha = const_cast<float*>(alpha); a.dsp = dsp;
-  a.dt_if = dt_if; a.dt_rpc = dt_rpc; a.rpc_ws = rpc_ws;
+  a.dt_if = dt_if; a.dt_rpc = dt_rpc; a.rpc_ws = rpc_ws; a.hot_if = 0;
   a.N = (int)N; a.inv_sqrt_c = 1.0f / sqrtf((float)H);
   switch (H) {
     case 32: return launch_bwd<32>(a, N, E, B, t_if != nullptr, tiles, st);

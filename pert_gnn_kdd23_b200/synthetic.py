@@ -204,7 +204,7 @@ def make_data_list(cfg_id, num_graphs=None, seed=None, patterns=1, edge_attr_col
 # own sample assembly + train/test loop (oracle/gen_golden_loop.py -> tests/golden/ref_loop.npz) and, with the same
 # seed, the device-side pattern store (store.py).
 def make_trace_artifacts(seed=7, n_ms=48, n_patterns=14, n_entries=6, n_traces=72, n_timestamps=5, n_if=32, n_rpc=6,
-                         nodes=(5, 40), resource_frac=0.7, y_max=10):
+                         nodes=(5, 40), resource_frac=0.7, y_max=10, runtime2graph=None, patterns_per_entry=(1, 3)):
     """-> dict(runtime2graph, entry2runtimes, tr2data, resource_index [(timestamp, msname)], resource_values [R,8],
     n_ms, n_if, n_rpc).
       runtime2graph[rt] = {edge_index [2,e] i64, edge_attr [e,4] i64, ms_id [n,1] i64, num_nodes int, node_depth [n,1] i64}
@@ -213,8 +213,9 @@ def make_trace_artifacts(seed=7, n_ms=48, n_patterns=14, n_entries=6, n_traces=7
     Microservice ids repeat inside a pattern (PERT graphs have several stage nodes per microservice), which exercises
     the last-occurrence rule of the reference's feature join (pert_gnn.py:54-65)."""
     rng = np.random.default_rng(seed)
-    runtime2graph = {}
-    for rt in range(n_patterns):
+    given = runtime2graph is not None          # patterns built elsewhere (e.g. pertgraph.build_pert_graphs)
+    runtime2graph = dict(runtime2graph) if given else {}
+    for rt in range(0 if given else n_patterns):
         n = int(rng.integers(nodes[0], nodes[1] + 1))
         m = min(3 * n, n * (n - 1) // 2)
         L = int(min(6, max(2, round(math.log2(n)))))
@@ -232,7 +233,7 @@ def make_trace_artifacts(seed=7, n_ms=48, n_patterns=14, n_entries=6, n_traces=7
     rts = list(runtime2graph.keys())
     entry2runtimes = {}
     for entry in range(n_entries):
-        k = int(rng.integers(1, 4))
+        k = int(rng.integers(patterns_per_entry[0], patterns_per_entry[1] + 1))
         chosen = [int(x) for x in rng.choice(rts, size=k, replace=False)]
         p = rng.random(k) + 0.2
         p = p / p.sum()
@@ -291,3 +292,36 @@ def make_span_tables(seed=11, n_traces=24, n_ms=40, calls=(1, 30), n_if=32, n_rp
                     "rpctype": rng.integers(0, n_rpc, n).astype(np.int64),
                     "endTimestamp": rows[:, 0] + np.abs(rows[:, 3])})
     return out
+
+
+def make_pert_artifacts(seed=3, n_patterns=256, n_entries=64, n_traces=4096, calls=(60, 72), device="cuda", n_ms=4096,
+                        n_if=1024, n_rpc=8, kind="pert"):
+    """PERT-exact synthetic artefacts: span tables -> host row filters (misc.py:87-105,138-142) -> PERT (or
+    span) graphs built ON THE GPU (pertgraph.build_pert_graphs) -> the processed/ artefact schema of
+    make_trace_artifacts with ONE pattern per entry, so a trace's sample is one PERT graph (nodes = 2 calls + distinct
+    microservices, edges = 4 calls).  -> (artifacts, info) with info = rows / nodes / edges / seconds of the build."""
+    import time
+
+    from . import pertgraph
+
+    tabs = make_span_tables(seed, n_patterns, n_ms=n_ms, calls=calls, n_if=n_if, n_rpc=n_rpc, anomalies=False)
+    tables, roots = [], []
+    for tab in tabs:
+        root = pertgraph.get_root_ms(tab)
+        keep = pertgraph.drop_wrong_edges(tab, root)
+        tables.append({k: v[keep] for k, v in tab.items()})
+        roots.append(root)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    pg = pertgraph.build_pert_graphs(tables, roots, device, kind=kind).check()
+    torch.cuda.synchronize(device)
+    secs = time.perf_counter() - t0
+    r2g = {}
+    for i in range(len(pg)):
+        p = pg.pattern(i)
+        r2g[100 + i] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in p.items()}
+    art = make_trace_artifacts(seed, n_ms=n_ms, n_entries=n_entries, n_traces=n_traces, n_if=n_if, n_rpc=n_rpc,
+                               y_max=5000, runtime2graph=r2g, patterns_per_entry=(1, 1))
+    info = {"patterns": len(pg), "span_rows": int(sum(len(t["um"]) for t in tables)), "nodes": int(pg.node_ptr[-1]),
+            "edges": int(pg.edge_ptr[-1]), "build_s": secs}
+    return art, info

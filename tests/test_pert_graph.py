@@ -204,7 +204,8 @@ def test_cuda_pert_graph_errors():
 
 
 @pytest.mark.gpu
-def test_spans_to_training_batch_on_device():
+@pytest.mark.parametrize("kind", ["pert", "span"])
+def test_spans_to_training_batch_on_device(kind):
     """Span rows -> PERT patterns (CUDA) -> resident pattern store -> collated batch -> model forward, next to the
     same chain with the oracle's patterns collated on the host: identical batches, same predictions."""
     from pert_gnn_kdd23_b200 import pertgraph
@@ -219,13 +220,17 @@ def test_spans_to_training_batch_on_device():
         root = pertgraph.get_root_ms(tab)
         tables.append(_cleaned(tab, pertgraph.drop_wrong_edges(tab, root)))
         roots.append(root)
-    pg = _build(tables, roots)
+    pg = pertgraph.build_pert_graphs(tables, roots, "cuda", kind=kind).check()
     art_dev, art_ora = dict(art), dict(art)
     art_dev["runtime2graph"], art_ora["runtime2graph"] = {}, {}
     for t, rt in enumerate(art["runtime2graph"]):
         p = pg.pattern(t)
         art_dev["runtime2graph"][rt] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in p.items()}
-        ms, ei, ea, nd, _ = _oracle_graph(tables[t], roots[t])
+        if kind == "pert":
+            ms, ei, ea, nd, _ = _oracle_graph(tables[t], roots[t])
+        else:
+            c = tables[t]
+            ms, ei, ea, nd, _ = O.span_graph(c["um"], c["dm"], c["interface"], c["rpctype"], roots[t])
         art_ora["runtime2graph"][rt] = {"edge_index": torch.from_numpy(ei), "edge_attr": torch.from_numpy(ea),
                                         "ms_id": torch.from_numpy(ms).reshape(-1, 1), "num_nodes": len(ms),
                                         "node_depth": torch.from_numpy(nd)}
