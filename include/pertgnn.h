@@ -24,8 +24,9 @@
  *     chain (fork/join by events, capture-safe; PERT_ENGINE_FORK=0 disables); the host-side issue of engine calls on
  *     one device is serialised by a mutex, so engines driven from several host threads / streams stay correct (their
  *     side work shares that one auxiliary stream); (3) the cached
- *     cuTensorMapEncodeTiled driver entry point; (4) environment switches read once: PERT_GEMM_TC, PERT_GEMM_TMA,
- *     PERT_TCONV_TILE, PERT_ENGINE_FORK (debug A/B only).
+ *     cuTensorMapEncodeTiled driver entry point; (4) environment switches read once (debug / measurement A/B only):
+ *     PERT_GEMM_TC, PERT_GEMM_TMA, PERT_GEMM_TN_ACC, PERT_TCONV_TILE, PERT_TCONV_VPL, PERT_TCONV_VPL_BWD,
+ *     PERT_TILE_LIST, PERT_BN_FUSE, PERT_ENGINE_FORK, PERT_PEER_MODE.
  *     With that, operator-level calls are re-entrant and thread-safe across streams;
  *   - rows of float matrices must be 16-byte aligned (ld % 4 == 0, base pointer 16-byte aligned)
  *     unless stated otherwise.
