@@ -56,7 +56,7 @@ class SAGEDeterministic(torch.nn.Module):
 
         eng = self._engine
         if flat is None:
-            if eng is not None and eng.fp.owns(self):
+            if eng is not None and eng.fp.owns_fast():      # per-step path: two pointer checks instead of one per parameter
                 return eng
             reg = self.__dict__.get("_flat_params")
             flat = reg if (reg is not None and reg.owns(self)) else FlatParams(self, bind_grads=False)

@@ -36,12 +36,14 @@ class FlatParams:
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
+        self._layout = []                              # (offset, shape, contiguous strides) of every parameter
         for p in params:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
             if bind_grads:
                 p.grad = self.grad[off:off + k].view_as(p)
+            self._layout.append((off, tuple(p.shape), tuple(p.stride())))
             off += al(k)
         self.params = params
         self.numel = n
@@ -60,6 +62,17 @@ class FlatParams:
         hi = lo + self.flat.numel() * 4
         ps = [p for p in module.parameters() if p.requires_grad]
         return len(ps) == len(self.params) and all(lo <= p.data_ptr() < hi for p in ps)
+
+    def owns_fast(self):
+        """Cheap form of ``owns`` for the per-step path: the first and the last parameter still live in the flat buffer
+        (``module.to()`` / re-flattening moves all of them; ``load_state_dict`` copies in place)."""
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        return lo <= self.params[0].data_ptr() < hi and lo <= self.params[-1].data_ptr() < hi
+
+    def views_of(self, buf):
+        """One view per parameter (its shape) into ``buf``, a flat tensor laid out like ``flat`` / ``grad``."""
+        return [buf.as_strided(shape, stride, off) for off, shape, stride in self._layout]
 
     def zero_grad(self):
         self.grad.zero_()

@@ -495,3 +495,38 @@ def test_fused_adam_matches_torch_adam():
         opt_c.step(grad_scale=0.5)
     for pc, po in zip(lin_c.parameters(), lin_o.parameters()):
         assert_close(pc, po, rtol=1e-5, what="adam param")
+
+
+def test_dropin_backward_autograd_semantics():
+    """The drop-in model is ONE autograd node.  With every .grad None and no hooks (the reference loop after
+    optimizer.zero_grad()) the gradient views are attached directly; every other state must behave like plain autograd:
+    a second backward accumulates, a parameter hook fires and can rewrite the gradient."""
+    _, model = make_models(1)
+    b = make_batch(1, 16).to("cuda")
+    model.train()
+
+    def loss():
+        gp, lp = model(*forward_args(b))
+        return model_oracle.torch_quantile_loss(b.y.float(), gp.flatten(), 0.5) + 1e-3 * lp.square().mean()
+
+    loss().backward()                                   # direct path
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    assert len(g1) >= 10
+    gb = model._engine.last_grad_buffer
+    lo, hi = gb.data_ptr(), gb.data_ptr() + gb.numel() * 4
+    assert all(lo <= p.grad.data_ptr() < hi for p in model.parameters() if p.grad is not None)
+    loss().backward()                                   # .grad present -> autograd accumulates
+    for n, p in model.named_parameters():
+        if n in g1:
+            ref = 2 * g1[n]
+            assert float((p.grad - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-7, n
+    # hooks: fired, and their return value replaces the gradient
+    for p in model.parameters():
+        p.grad = None
+    w = model.convs[0].lin_value.weight
+    seen = []
+    h = w.register_hook(lambda g: seen.append(g.shape) or g * 0.0)
+    loss().backward()
+    h.remove()
+    assert seen == [w.shape] and float(w.grad.abs().max()) == 0.0
+    assert float(model.convs[0].lin_skip.weight.grad.abs().max()) > 0.0
