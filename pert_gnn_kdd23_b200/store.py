@@ -56,16 +56,18 @@ class PatternStore:
         for rt in self.rt_ids:
             g = runtime2graph[rt]
             n = int(g["num_nodes"])
-            m = g["ms_id"].reshape(-1).to(torch.int64).numpy()
+            # patterns may come straight from pertgraph.build_*_graphs (CUDA tensors): the host copy below only sizes
+            # batches and finds the last occurrence of every microservice
+            m = g["ms_id"].reshape(-1).to(torch.int64).cpu().numpy()
             assert m.shape[0] == n
-            ei = g["edge_index"].numpy()
-            ea = g["edge_attr"].numpy()
+            ei = g["edge_index"].cpu().numpy()
+            ea = g["edge_attr"].cpu().numpy()
             cols = ea.shape[1] if cols is None else cols
             assert ea.shape[1] == cols
             nptr.append(nptr[-1] + n)
             eptr.append(eptr[-1] + ei.shape[1])
             ms.append(m)
-            depth.append(g["node_depth"].reshape(-1).to(torch.int64).numpy())
+            depth.append(g["node_depth"].reshape(-1).to(torch.int64).cpu().numpy())
             # get_x's dict ms2nid keeps the LAST node of every microservice (pert_gnn.py:54-65)
             lo = np.zeros(n, dtype=np.uint8)
             seen = {}

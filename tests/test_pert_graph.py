@@ -225,7 +225,7 @@ def test_spans_to_training_batch_on_device(kind):
     art_dev["runtime2graph"], art_ora["runtime2graph"] = {}, {}
     for t, rt in enumerate(art["runtime2graph"]):
         p = pg.pattern(t)
-        art_dev["runtime2graph"][rt] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in p.items()}
+        art_dev["runtime2graph"][rt] = p                 # CUDA tensors, as build_*_graphs returns them
         if kind == "pert":
             ms, ei, ea, nd, _ = _oracle_graph(tables[t], roots[t])
         else:
