@@ -91,6 +91,22 @@ def test_oracle_time_tie_rule():
     assert ea[6:, 2].tolist() == [1, 0, 1, 1, 0, 0]
 
 
+def test_no_cpu_fallback_and_generator_contract():
+    from pert_gnn_kdd23_b200 import _lib, pertgraph
+
+    a, b = make_span_tables(4, 6), make_span_tables(4, 6)
+    for ta, tb in zip(a, b):                                       # deterministic in the seed (goldens rely on it)
+        assert all(np.array_equal(ta[k], tb[k]) for k in ta)
+        assert np.array_equal(ta["endTimestamp"], ta["timestamp"] + np.abs(ta["rt"]))      # preprocess.py:263
+        root = pertgraph.get_root_ms(ta)
+        i = int(np.argmax(np.abs(ta["rt"])))
+        assert ta["timestamp"][i] == ta["timestamp"].min() and ta["um"][i] == root          # misc.py:138-142
+    c = _cleaned(a[0], pertgraph.drop_wrong_edges(a[0], pertgraph.get_root_ms(a[0])))
+    for build in (pertgraph.build_pert_graphs, pertgraph.build_span_graphs):
+        with pytest.raises(_lib.PertGnnError):
+            build([c], [pertgraph.get_root_ms(a[0])], "cpu")        # the product path has no CPU implementation
+
+
 # ------------------------------------------------------------------------------------------------- GPU
 def _build(tables, roots):
     from pert_gnn_kdd23_b200 import pertgraph
