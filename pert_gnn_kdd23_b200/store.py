@@ -39,6 +39,27 @@ class _PertBatchOut(C.Structure):
                                  "edge_attr", "entry_id", "y", "ptr", "pattern_probs")]
 
 
+def _last_occurrence_flags(all_ms, nptr):
+    """flags[i] = 1 iff node i is the LAST node of its microservice inside its pattern (patterns = nptr slices)."""
+    n_all = int(all_ms.shape[0])
+    flags = np.zeros(n_all, dtype=np.uint8)
+    if n_all:
+        pid = np.repeat(np.arange(len(nptr) - 1, dtype=np.int64), np.diff(nptr))
+        lo = int(all_ms.min())
+        key = pid * (int(all_ms.max()) - lo + 1) + (all_ms - lo)
+        _, first_rev = np.unique(key[::-1], return_index=True)
+        flags[n_all - 1 - first_rev] = 1
+    return flags
+
+
+class _BulkPatterns:
+    """Concatenated host arrays of many patterns (PatternStore.from_graphs)."""
+
+    def __init__(self, rt_ids, node_ptr, edge_ptr, ms_id, node_depth, edge_index, edge_attr):
+        self.rt_ids, self.node_ptr, self.edge_ptr = rt_ids, node_ptr, edge_ptr
+        self.ms_id, self.node_depth, self.edge_index, self.edge_attr = ms_id, node_depth, edge_index, edge_attr
+
+
 class PatternStore:
     """Patterns, entries, resource table and traces on one CUDA device."""
 
@@ -47,40 +68,49 @@ class PatternStore:
         if dev.type != "cuda":
             raise _lib.PertGnnError("PatternStore lives on a CUDA device (no CPU fallback for the hot path)")
         self.device = dev
-        # ---- patterns, in the dict order of runtime2graph
-        self.rt_ids = list(runtime2graph.keys())
+        # ---- patterns, in the dict order of runtime2graph (or the bulk arrays of pertgraph.PertGraphs, see from_graphs)
+        if isinstance(runtime2graph, _BulkPatterns):
+            bp = runtime2graph
+            self.rt_ids = list(bp.rt_ids)
+            nptr, eptr = bp.node_ptr.astype(np.int64), bp.edge_ptr.astype(np.int64)
+            ms = [bp.ms_id.astype(np.int64)]
+            depth = [bp.node_depth.astype(np.int64)]
+            src, dst = [bp.edge_index[0].astype(np.int32)], [bp.edge_index[1].astype(np.int32)]
+            attr = [bp.edge_attr.astype(np.int64)]
+            cols = bp.edge_attr.shape[1]
+        else:
+            self.rt_ids = list(runtime2graph.keys())
+            nptr, eptr = [0], [0]
+            ms, depth, src, dst, attr = [], [], [], [], []
+            cols = None
+            for rt in self.rt_ids:
+                g = runtime2graph[rt]
+                n = int(g["num_nodes"])
+                # patterns may be CUDA tensors (pertgraph.PertGraphs.pattern): the host copy sizes batches and finds the
+                # last occurrence of every microservice; for many patterns use PatternStore.from_graphs (one bulk copy)
+                m = g["ms_id"].reshape(-1).to(torch.int64).cpu().numpy()
+                assert m.shape[0] == n
+                ei = g["edge_index"].cpu().numpy()
+                ea = g["edge_attr"].cpu().numpy()
+                cols = ea.shape[1] if cols is None else cols
+                assert ea.shape[1] == cols
+                nptr.append(nptr[-1] + n)
+                eptr.append(eptr[-1] + ei.shape[1])
+                ms.append(m)
+                depth.append(g["node_depth"].reshape(-1).to(torch.int64).cpu().numpy())
+                src.append(ei[0].astype(np.int32))
+                dst.append(ei[1].astype(np.int32))
+                attr.append(ea.astype(np.int64))
         rt_index = {rt: i for i, rt in enumerate(self.rt_ids)}
-        nptr, eptr = [0], [0]
-        ms, depth, last, src, dst, attr = [], [], [], [], [], []
-        cols = None
-        for rt in self.rt_ids:
-            g = runtime2graph[rt]
-            n = int(g["num_nodes"])
-            # patterns may come straight from pertgraph.build_*_graphs (CUDA tensors): the host copy below only sizes
-            # batches and finds the last occurrence of every microservice
-            m = g["ms_id"].reshape(-1).to(torch.int64).cpu().numpy()
-            assert m.shape[0] == n
-            ei = g["edge_index"].cpu().numpy()
-            ea = g["edge_attr"].cpu().numpy()
-            cols = ea.shape[1] if cols is None else cols
-            assert ea.shape[1] == cols
-            nptr.append(nptr[-1] + n)
-            eptr.append(eptr[-1] + ei.shape[1])
-            ms.append(m)
-            depth.append(g["node_depth"].reshape(-1).to(torch.int64).cpu().numpy())
-            # get_x's dict ms2nid keeps the LAST node of every microservice (pert_gnn.py:54-65)
-            lo = np.zeros(n, dtype=np.uint8)
-            seen = {}
-            for i, v in enumerate(m.tolist()):
-                seen[v] = i
-            lo[list(seen.values())] = 1
-            last.append(lo)
-            src.append(ei[0].astype(np.int32))
-            dst.append(ei[1].astype(np.int32))
-            attr.append(ea.astype(np.int64))
+        nptr, eptr = np.asarray(nptr, dtype=np.int64), np.asarray(eptr, dtype=np.int64)
+        # get_x's dict ms2nid keeps the LAST node of every microservice of a pattern (pert_gnn.py:54-65): vectorised as
+        # the first occurrence of (pattern, ms) in the reversed node list
+        all_ms = np.concatenate(ms) if ms else np.zeros(0, dtype=np.int64)
+        last_flags = _last_occurrence_flags(all_ms, nptr)
+        last = [last_flags]
         self.attr_cols = int(cols)
-        pat_nodes = np.diff(np.array(nptr))
-        pat_edges = np.diff(np.array(eptr))
+        pat_nodes = np.diff(nptr)
+        pat_edges = np.diff(eptr)
         # ---- entries, in the dict order of entry2runtimes[entry] (get_all_runtimes_id_probs, pert_gnn.py:70-74)
         n_ent = max(entry2runtimes.keys()) + 1
         ent_ptr, ent_pat, ent_prob = [0], [], []
@@ -93,7 +123,6 @@ class PatternStore:
                 ent_nodes[e] += pat_nodes[k]
                 ent_edges[e] += pat_edges[k]
             ent_ptr.append(len(ent_pat))
-        all_ms = np.concatenate(ms) if ms else np.zeros(0, dtype=np.int64)
         res_ms = np.array([m for _, m in resource_index], dtype=np.int64)
         res_ts = np.array([t for t, _ in resource_index], dtype=np.int64)
         self.n_ms = int(n_ms if n_ms is not None else max(int(all_ms.max(initial=0)), int(res_ms.max(initial=0))) + 1)
@@ -139,8 +168,25 @@ class PatternStore:
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
 
     @classmethod
+    def from_graphs(cls, graphs, runtime_ids, entry2runtimes, resource_index, resource_values, tr2data, device=None,
+                    n_ms=None):
+        """Patterns straight from ``pertgraph.build_pert_graphs`` / ``build_span_graphs`` (``graphs``: PertGraphs;
+        ``runtime_ids[i]`` names pattern i): ONE device->host copy of the concatenated tensors instead of one per
+        pattern, no per-pattern Python work."""
+        dev = torch.device(device) if device is not None else graphs.ms_id.device
+        bp = _BulkPatterns(list(runtime_ids), np.asarray(graphs.node_ptr), np.asarray(graphs.edge_ptr),
+                           graphs.ms_id.cpu().numpy().reshape(-1), graphs.node_depth.cpu().numpy().reshape(-1),
+                           graphs.edge_index.cpu().numpy(), graphs.edge_attr.cpu().numpy())
+        assert len(bp.rt_ids) == len(bp.node_ptr) - 1
+        return cls(bp, entry2runtimes, resource_index, resource_values, tr2data, dev, n_ms=n_ms)
+
+    @classmethod
     def from_artifacts(cls, art, device):
-        """``art``: dict with the reference's artefacts (synthetic.make_trace_artifacts schema)."""
+        """``art``: dict with the reference's artefacts (synthetic.make_trace_artifacts schema; with ``graphs`` +
+        ``runtime_ids`` -- synthetic.make_pert_artifacts -- the patterns are taken from the device-resident PertGraphs)."""
+        if art.get("graphs") is not None:
+            return cls.from_graphs(art["graphs"], art["runtime_ids"], art["entry2runtimes"], art["resource_index"],
+                                   art["resource_values"], art["tr2data"], device, n_ms=art.get("n_ms"))
         return cls(art["runtime2graph"], art["entry2runtimes"], art["resource_index"], art["resource_values"],
                    art["tr2data"], device, n_ms=art.get("n_ms"))
 

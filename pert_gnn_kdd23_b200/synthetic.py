@@ -316,12 +316,12 @@ def make_pert_artifacts(seed=3, n_patterns=256, n_entries=64, n_traces=4096, cal
     pg = pertgraph.build_pert_graphs(tables, roots, device, kind=kind).check()
     torch.cuda.synchronize(device)
     secs = time.perf_counter() - t0
-    r2g = {}
-    for i in range(len(pg)):
-        p = pg.pattern(i)
-        r2g[100 + i] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in p.items()}
+    # entries / traces / resources around the patterns; the pattern dict only carries the ids here (the graphs stay on the
+    # device: art["graphs"] + art["runtime_ids"] go to PatternStore.from_graphs)
+    ids = [100 + i for i in range(len(pg))]
     art = make_trace_artifacts(seed, n_ms=n_ms, n_entries=n_entries, n_traces=n_traces, n_if=n_if, n_rpc=n_rpc,
-                               y_max=5000, runtime2graph=r2g, patterns_per_entry=(1, 1))
+                               y_max=5000, runtime2graph={i: None for i in ids}, patterns_per_entry=(1, 1))
+    art["graphs"], art["runtime_ids"] = pg, ids
     info = {"patterns": len(pg), "span_rows": int(sum(len(t["um"]) for t in tables)), "nodes": int(pg.node_ptr[-1]),
             "edges": int(pg.edge_ptr[-1]), "build_s": secs}
     return art, info

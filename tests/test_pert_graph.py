@@ -251,10 +251,14 @@ def test_spans_to_training_batch_on_device(kind):
                                         "ms_id": torch.from_numpy(ms).reshape(-1, 1), "num_nodes": len(ms),
                                         "node_depth": torch.from_numpy(nd)}
     sa, sb = PatternStore.from_artifacts(art_dev, "cuda"), PatternStore.from_artifacts(art_ora, "cuda")
+    # bulk ingest of the PertGraphs object (one D2H copy, vectorised last-occurrence flags) == per-pattern ingest
+    sc = PatternStore.from_graphs(pg, list(art["runtime2graph"].keys()), art["entry2runtimes"], art["resource_index"],
+                                  art["resource_values"], art["tr2data"], "cuda", n_ms=art.get("n_ms"))
     ids = list(range(16))
-    ba, bb = sa.assemble(ids), sb.assemble(ids)
+    ba, bb, bc = sa.assemble(ids), sb.assemble(ids), sc.assemble(ids)
     for k in ("x", "edge_index", "edge_attr", "cat_X", "node_depth", "batch", "ptr", "rt_probs"):
         assert torch.equal(ba[k], bb[k]), k
+        assert torch.equal(bc[k], bb[k]), k
     torch.manual_seed(0)
     model = SAGEDeterministic(9, [40], 8, art["n_if"], art["n_rpc"], 32, 2, 0.0).cuda().eval()
 
