@@ -57,6 +57,59 @@ def drop_wrong_edges(table, root):
     return idx.astype(np.int64)
 
 
+def _group_pick(cols, last=False):
+    """Boolean mask over rows: the first (or last) row, in table order, of every distinct tuple of ``cols``."""
+    n = cols[0].shape[0]
+    mask = np.zeros(n, dtype=bool)
+    if n == 0:
+        return mask
+    order = np.lexsort(tuple(reversed(cols)))              # stable: equal tuples keep table order
+    new = np.ones(n, dtype=bool)
+    diff = np.zeros(n - 1, dtype=bool)
+    for c in cols:
+        cs = c[order]
+        diff |= cs[1:] != cs[:-1]
+    new[1:] = diff
+    if last:
+        pick = np.ones(n, dtype=bool)
+        pick[:-1] = new[1:]
+    else:
+        pick = new
+    mask[order[pick]] = True
+    return mask
+
+
+def clean_span_tables_flat(columns, row_ptr):
+    """``get_root_ms`` + ``drop_wrong_edges`` for MANY traces at once, without a Python loop over traces.
+    ``columns``: dict of int64 arrays over all rows (um, dm, rpcid, rt, timestamp [, ...]) grouped by trace;
+    ``row_ptr`` [T+1].  -> (keep: surviving row indices in table order, new_row_ptr [T+1], roots [T]).
+    Same result as the per-trace functions (misc.py:138-142, :87-105), tests/test_pert_graph.py."""
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    T = len(row_ptr) - 1
+    lens = np.diff(row_ptr)
+    if T <= 0 or (lens <= 0).any():
+        raise ValueError("every trace needs at least one span row")
+    um, dm = np.asarray(columns["um"], dtype=np.int64), np.asarray(columns["dm"], dtype=np.int64)
+    rpcid = np.asarray(columns["rpcid"], dtype=np.int64)
+    a, ts = np.abs(np.asarray(columns["rt"], dtype=np.int64)), np.asarray(columns["timestamp"], dtype=np.int64)
+    tid = np.repeat(np.arange(T, dtype=np.int64), lens)
+    starts = row_ptr[:-1]
+    amax, tmin = np.maximum.reduceat(a, starts), np.minimum.reduceat(ts, starts)
+    cand = np.flatnonzero((a == amax[tid]) & (ts == tmin[tid]))
+    tr, first = np.unique(tid[cand], return_index=True)            # cand ascending -> first candidate row per trace
+    if tr.shape[0] != T:
+        raise IndexError("a trace has no root row (largest |rt| at the smallest timestamp)")
+    roots = um[cand[first]]
+    idx = np.flatnonzero(um != dm)                                                          # :89
+    idx = idx[_group_pick([tid[idx], rpcid[idx]])]                                          # :92 keep first
+    idx = idx[dm[idx] != roots[tid[idx]]]                                                   # :95
+    idx = idx[_group_pick([tid[idx], um[idx], dm[idx]], last=True)]                         # :97 keep last
+    lo, hi = np.minimum(um[idx], dm[idx]), np.maximum(um[idx], dm[idx])
+    idx = idx[_group_pick([tid[idx], lo, hi])]                                              # :100-103 keep first
+    new_ptr = np.concatenate([[0], np.cumsum(np.bincount(tid[idx], minlength=T))]).astype(np.int64)
+    return idx.astype(np.int64), new_ptr, roots.astype(np.int64)
+
+
 class PertGraphs:
     """T PERT graphs, concatenated on the device.  ``edge_index`` holds trace-LOCAL node ids (the per-pattern tensors
     of runtime2pertgraph_map); trace t owns nodes ``node_ptr[t]:node_ptr[t+1]`` and edges ``edge_ptr[t]:edge_ptr[t+1]``."""

@@ -77,6 +77,29 @@ def test_host_row_filters_match_reference():
             assert np.array_equal(pertgraph.drop_wrong_edges(tab, root), O.drop_wrong_edges(tab, root))
 
 
+def test_flat_row_filters_equal_per_trace_filters():
+    """clean_span_tables_flat (all traces at once, no Python loop) == get_root_ms + drop_wrong_edges per trace."""
+    from pert_gnn_kdd23_b200 import pertgraph
+
+    for seed, n, calls in ((11, 24, (1, 30)), (5, 60, (1, 80)), (6, 10, (200, 400))):
+        tabs = make_span_tables(seed, n, calls=calls)
+        row_ptr = np.concatenate([[0], np.cumsum([len(t["um"]) for t in tabs])])
+        cols = {k: np.concatenate([t[k] for t in tabs]) for k in tabs[0]}
+        keep, new_ptr, roots = pertgraph.clean_span_tables_flat(cols, row_ptr)
+        exp_keep, exp_roots = [], []
+        for t, tab in enumerate(tabs):
+            r = pertgraph.get_root_ms(tab)
+            exp_roots.append(r)
+            exp_keep.append(pertgraph.drop_wrong_edges(tab, r) + row_ptr[t])
+        assert np.array_equal(roots, np.array(exp_roots))
+        assert np.array_equal(keep, np.concatenate(exp_keep))
+        assert np.array_equal(np.diff(new_ptr), np.array([len(k) for k in exp_keep]))
+    bad = {k: v.copy() for k, v in cols.items()}
+    bad["timestamp"][int(np.argmax(np.abs(bad["rt"][:row_ptr[1]])))] += 10 ** 6      # trace 0 loses its root row
+    with pytest.raises(IndexError):
+        pertgraph.clean_span_tables_flat(bad, row_ptr)
+
+
 def test_oracle_time_tie_rule():
     """Stable sort by time only (misc.py:290): equal times keep row order, a row's start before its end -- also for a
     zero-length call."""
